@@ -1,0 +1,257 @@
+/*
+ * gcf.h -- C-ABI of libgcf.so: the B200 (sm_100a) graph-collaborative-filtering hot path.
+ *
+ * The reference (Cmint22/Recommendation) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md section 8b); its boundary is the Python class/function surface of each script.
+ * Every entry point below therefore cites the reference *Python* code whose arithmetic it
+ * replaces (file:line relative to the reference tree).  The Python shims in
+ * recommendation_b200/ keep the reference signatures and call these symbols through
+ * ctypes (recommendation_b200/_lib.py); INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no torch types.
+ *   - every pointer is a CUDA *device* pointer owned by the caller unless the parameter
+ *     is documented "host".  The library never allocates or frees tensors; scratch is a
+ *     caller-provided workspace sized by the matching *_workspace_bytes() query.
+ *   - every call is asynchronous on the given stream (a cudaStream_t passed as void*),
+ *     has no implicit device synchronisation and no global mutable state.
+ *   - return value: 0 = ok, <0 = error; gcf_last_error() returns a thread-local message.
+ *   - dense matrices are fp32 row-major with an explicit leading dimension (in elements).
+ *   - node / batch indices coming from the reference API are int64 (torch.LongTensor);
+ *     CSR structure built by this library is int32.
+ */
+#ifndef GCF_H_
+#define GCF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCF_OK            0
+#define GCF_EINVAL      (-1)
+#define GCF_ECUDA       (-2)
+#define GCF_EWORKSPACE  (-3)
+#define GCF_EUNSUPPORTED (-4)
+
+typedef void* gcf_stream_t; /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------- */
+const char* gcf_version(void);
+const char* gcf_last_error(void);
+
+/* ---- (1) adjacency build: integer kernels --------------------------------------------- */
+
+/* deg[idx[e]] += 1 for e in [0,n).  deg is int32[n_nodes], zeroed by the callee.
+ * Replaces PyG gcn_norm's scatter_add degree (lightgcn.py:17,25) and scipy's
+ * adj.sum(1) for 0/1 adjacencies (selfcf.py:243, ssl4rec.py:85). */
+int gcf_degree_count(const int64_t* idx, int64_t n, int32_t* deg, int64_t n_nodes, gcf_stream_t stream);
+
+/* rows = [u | i+U], cols = [i+U | u]  (each int64[2E]).
+ * Replaces load_data's edge_index build (lightgcn.py:36-39, gcl.py:72-77). */
+int gcf_bipartite_edge_index(const int64_t* users, const int64_t* items, int64_t n_edges, int64_t n_users,
+                             int64_t* rows, int64_t* cols, gcf_stream_t stream);
+
+/* COO (int64 rows/cols, optional fp32 vals; NULL vals = all ones) -> canonical CSR:
+ * sorted by (row, col) with a hand-written stable LSD radix sort, duplicate (row,col)
+ * entries summed in their original order.  Outputs: row_ptr int32[n_rows+1],
+ * col_idx int32[capacity nnz], out_vals fp32[capacity nnz], nnz_out int64 device scalar
+ * (number of distinct entries).  Replaces scipy's csr_matrix((v,(r,c))) + tmp+tmp.T
+ * canonicalisation (selfcf.py:297-306, ssl4rec.py:79-84) and torch's coalescing of the
+ * uncoalesced COO tensors (ncl.py:76-85,203-209). */
+size_t gcf_coo_to_csr_workspace_bytes(int64_t nnz, int64_t n_rows, int64_t n_cols);
+int gcf_coo_to_csr_stable(const int64_t* rows, const int64_t* cols, const float* vals, int64_t nnz,
+                          int64_t n_rows, int64_t n_cols,
+                          int32_t* row_ptr, int32_t* col_idx, float* out_vals, int64_t* nnz_out,
+                          void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+
+/* Normalise CSR values.  mode 0 = none (copy), 1 = sym: (dinv[r]*a)*dinv[c] with
+ * dinv = rowsum^-1/2 and inf -> 0 (square only), 2 = row: rowsum^-1 * a, inf -> 0.
+ * rowsum_out fp32[n_rows] receives the row sums (integer valued for 0/1 graphs: the
+ * degrees), dinv_out fp32[n_rows] the scaling vector.  Replaces
+ * Graph.normalize_graph_mat (selfcf.py:240-255, ncl.py:30-44, mhcn.py:70-84),
+ * ssl4rec.py:85-88 and PyG gcn_norm (lightgcn.py:25). */
+int gcf_norm_values(int32_t mode, const int32_t* row_ptr, const int32_t* col_idx, const float* vals_in,
+                    int64_t n_rows, int64_t n_cols, float* vals_out, float* rowsum_out, float* dinv_out,
+                    gcf_stream_t stream);
+
+/* CSR -> CSR of the transpose (stable: rows ascending inside each output row).
+ * Needed for the backward of non-symmetric operators (mhcn.py:440-456 R / R^T,
+ * diffnet.py:1127,1131 S and A).  nnz is the exact entry count. */
+size_t gcf_csr_transpose_workspace_bytes(int64_t nnz, int64_t n_rows, int64_t n_cols);
+int gcf_csr_transpose(const int32_t* row_ptr, const int32_t* col_idx, const float* vals,
+                      int64_t n_rows, int64_t n_cols, int64_t nnz,
+                      int32_t* t_row_ptr, int32_t* t_col_idx, float* t_vals,
+                      void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+
+/* ---- (2) SpMM / propagation ----------------------------------------------------------- */
+
+/* CSR operator plus its (optional) long-row schedule.  Rows with more than `chunk`
+ * entries are split into chunks of `chunk` entries, each processed by one warp; the
+ * last-arriving chunk of a row reduces the partial sums in chunk order (deterministic). */
+typedef struct gcf_csr {
+  int64_t n_rows, n_cols, nnz;
+  const int32_t* row_ptr;        /* [n_rows+1] */
+  const int32_t* col_idx;        /* [nnz] */
+  const float*   vals;           /* [nnz] */
+  int32_t chunk;                 /* long-row threshold / chunk length (0 = no schedule) */
+  int32_t n_long;                /* number of rows with degree > chunk */
+  int32_t n_chunks;              /* total chunks over all long rows */
+  const int32_t* long_rows;      /* [n_long] row ids */
+  const int32_t* long_chunk_ptr; /* [n_long+1] first chunk of each long row */
+  const int32_t* chunk_long;     /* [n_chunks] index into long_rows */
+} gcf_csr_t;
+
+#define GCF_MAX_ADDENDS 8
+#define GCF_EPILOGUE_NONE   0
+#define GCF_EPILOGUE_L2NORM 1
+
+/* workspace: n_chunks*d floats of partial sums + n_long int32 counters.  The counter
+ * region (the LAST n_long*4 bytes, 256-byte aligned start, see gcf_spmm_counter_offset)
+ * must be zero before the first call; the kernel leaves it zero again. */
+size_t gcf_spmm_workspace_bytes(const gcf_csr_t* A, int32_t d);
+size_t gcf_spmm_counter_offset(const gcf_csr_t* A, int32_t d);
+
+/* T = A * X  (fp32, [n_rows, d]);  then
+ *   Y   (nullable) = T
+ *   OUT (nullable) = post * ( alpha * f(T) + sum_j betas[j] * addends[j] ),  f = identity | row-L2-normalise
+ * addends / betas are HOST arrays (n_addends <= GCF_MAX_ADDENDS) of device pointers / scalars,
+ * every addend has leading dimension ld_out.
+ * Replaces torch.sparse.mm (ncl.py:419, selfcf.py:479, directau.py:290, mhcn.py:440-456,
+ * diffnet.py:1127,1131), PyG LGConv.propagate (lightgcn.py:25) and the per-layer
+ * F.normalize / stack().mean() / x += out epilogues (ncl.py:421, selfcf.py:481-482,
+ * lightgcn.py:26, sept.py:224, mhcn.py:441-457). */
+int gcf_spmm_csr_f32(const gcf_csr_t* A, int32_t d, const float* X, int64_t ldx,
+                     float* Y, int64_t ldy, float* OUT, int64_t ld_out,
+                     int32_t epilogue, float alpha, float post,
+                     int32_t n_addends, const float* const* addends, const float* betas,
+                     void* workspace, size_t workspace_bytes, int32_t variant, gcf_stream_t stream);
+
+/* K-layer LightGCN propagation: E0 = X0, E(k) = A * E(k-1);
+ *   final = scale * sum_{k=0..K} E(k)        (scale = 1/(K+1) for mean, 1 for sum)
+ * layers: HOST array of K device pointers [n_rows, d] (ld = d) receiving E(1)..E(K);
+ * layers[K-1] may be NULL when E(K) itself is not needed (it is folded into `final`).
+ * Replaces LGCNEncoder.forward (ncl.py:415-422, directau.py:286-293),
+ * LGCN_Encoder.forward (selfcf.py:475-485), LightGCN.forward (lightgcn.py:21-27). */
+int gcf_propagate_fwd(const gcf_csr_t* A, int32_t d, int32_t n_layers, const float* X0,
+                      float* const* layers, float* final_out, float scale,
+                      void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+
+/* Backward of gcf_propagate_fwd for a symmetric operator A (or pass A^T):
+ *   G(K) = scale*g_final + extra[K];  G(k) = A^T * G(k+1) + scale*g_final + extra[k];  g_X0 = G(0)
+ * extra: HOST array of K+1 nullable device pointers (gradients that reached individual
+ * layer outputs E(k), e.g. NCL's ssl_layer_loss, ncl.py:318-323); may be NULL.
+ * ping/pong: two [n_rows, d] scratch buffers.  Replaces autograd's sparse addmm backward
+ * (SURVEY.md row a10). */
+int gcf_propagate_bwd(const gcf_csr_t* At, int32_t d, int32_t n_layers, const float* g_final,
+                      const float* const* extra, float scale, float* ping, float* pong, float* g_x0,
+                      void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+
+/* ---- (4) gather / scatter-add / sampler ----------------------------------------------- */
+
+/* out[t, :] = table[idx[t], :]   (x[idx], ncl.py:314-316, lightgcn.py:95-102, ...) */
+int gcf_gather_rows(const float* table, int64_t ld, int64_t n_table_rows, int32_t d,
+                    const int64_t* idx, int64_t n, float* out, int64_t ld_out, gcf_stream_t stream);
+
+/* table_grad[idx[t], :] += src[t, :]   (backward of x[idx]: index_put_(accumulate=True)).
+ * mode 0: warp-aggregated atomics (match.any groups equal indices inside a warp, one
+ *         red.global.add.v4.f32 per distinct row per warp) -- fp32 order not deterministic;
+ * mode 1: deterministic -- indices radix-sorted (stable) and each destination row summed
+ *         in source order by one sub-warp.  Needs the workspace. */
+size_t gcf_scatter_add_workspace_bytes(int64_t n, int64_t n_table_rows, int32_t mode);
+int gcf_scatter_add_rows(const float* src, int64_t ld_src, int32_t d, const int64_t* idx, int64_t n,
+                         float* table_grad, int64_t ld, int64_t n_table_rows, int32_t mode,
+                         void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+
+/* Philox4x32-10 counter-based negative sampler.  For triple t and negative slot j the
+ * candidate stream is Philox(key=seed, counter=(t*n_negs+j, trial/4, offset_lo, offset_hi)),
+ * candidate = mulhi32(word, n_items).  Without a positives CSR (pos_row_ptr == NULL) the
+ * first candidate is taken (lightgcn.py:91-94: torch.randint, no rejection); with it,
+ * candidates found in the user's sorted positive list are rejected, up to max_trials
+ * (ncl.py:91-114 caps at 100; selfcf.py:188-211 / directau.py:14-32 are unbounded).
+ * out int64[n * n_negs]. */
+int gcf_sample_negatives(uint64_t seed, uint64_t offset, const int64_t* users, int64_t n, int32_t n_negs,
+                         int64_t n_items, const int32_t* pos_row_ptr, const int32_t* pos_col_idx,
+                         int32_t max_trials, int64_t* out, gcf_stream_t stream);
+
+/* ---- (3) losses ----------------------------------------------------------------------- */
+
+#define GCF_BPR_LOG_EPS_SIGMOID 0 /* -log(eps + sigmoid(x))      ncl.py:116-120, mhcn.py:35-39 */
+#define GCF_BPR_SOFTPLUS        1 /* -log(sigmoid(x))            lightgcn.py:108, gcl.py:221   */
+#define GCF_REDUCE_MEAN 0
+#define GCF_REDUCE_SUM  1         /* diffnet.py:1113 */
+
+/* Fused gather + BPR (+ squared-L2 reg of the gathered rows):
+ *   x_t   = <u_t, p_t> - mean_j <u_t, n_tj>
+ *   loss  = reduce_t l(x_t) + reg_u*sum|u_t|^2 + reg_p*sum|p_t|^2 + reg_n*sum|n_tj|^2
+ * coef_out[t] = dl/dx_t (already divided by n for the mean) is kept for the backward.
+ * lightgcn.py:95-118: (reg, reg, 0); gcl.py:216-223: reg/B each; ncl.py:116-120: zeros. */
+size_t gcf_bpr_workspace_bytes(int64_t n_triples);
+int gcf_bpr_fwd(const float* user_emb, int64_t ld_user, const float* item_emb, int64_t ld_item, int32_t d,
+                const int64_t* u_idx, const int64_t* p_idx, const int64_t* n_idx, int64_t n_triples, int32_t n_negs,
+                int32_t variant, float eps, int32_t reduction, float reg_u, float reg_p, float reg_n,
+                float* loss_out, float* coef_out, void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+
+/* Backward: accumulates (warp-aggregated red.add) into g_user / g_item, which the caller
+ * zero-initialises (or which already hold other gradient terms).  grad_out: device scalar
+ * dL/dloss (NULL = 1). */
+int gcf_bpr_bwd(const float* user_emb, int64_t ld_user, const float* item_emb, int64_t ld_item, int32_t d,
+                const int64_t* u_idx, const int64_t* p_idx, const int64_t* n_idx, int64_t n_triples, int32_t n_negs,
+                const float* coef, const float* grad_out, float reg_u, float reg_p, float reg_n,
+                float* g_user, int64_t ldg_user, float* g_item, int64_t ldg_item, gcf_stream_t stream);
+
+/* Fused dense Adam / AdamW step (torch.optim.Adam semantics, ncl.py:305, lightgcn.py:80).
+ * step = 1-based step count. */
+int gcf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int32_t decoupled,
+                  int64_t step, gcf_stream_t stream);
+
+/* ---- InfoNCE family on tcgen05 tensor cores (bf16 operands, fp32 accumulate + LSE) ----
+ *
+ * Q [M, d] fp32, Kmat [N, d] fp32 (rows are L2-normalised inside when cos != 0).
+ *   s_ij = <q_i, k_j> / tau
+ *   row_lse[i] = log sum_j exp(s_ij)                      (always)
+ *   col_lse[j] = log sum_i exp(s_ij)                      (when col_lse != NULL; gcl.py:28-35)
+ *   pos[i]     = s_{i, pos_idx[i]}  (pos_idx NULL -> diagonal j = i)
+ * The B x N logits are never materialised.  The scalar losses are assembled from these
+ * vectors by the shim:
+ *   InfoNCE          ncl.py:125-130, ssl4rec.py:19-23 : mean_i(row_lse - pos)
+ *   ssl_layer_loss   ncl.py:358-367                   : sum_i(row_lse - pos)
+ *   batch_softmax    ssl4rec.py:25-30                 : mean_i -log(exp(pos-row_lse)+1e-6)
+ *   info_nce_loss    gcl.py:28-35                     : (mean(row_lse-pos)+mean(col_lse-pos))/2
+ */
+size_t gcf_infonce_workspace_bytes(int64_t M, int64_t N, int32_t d);
+int gcf_infonce_fwd(const float* Q, int64_t ldq, int64_t M, const float* Kmat, int64_t ldk, int64_t N, int32_t d,
+                    int32_t cos, float tau, const int64_t* pos_idx,
+                    float* row_lse, float* col_lse, float* pos,
+                    void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+
+/* Backward: given w_row[i] = dL/d row_lse[i], w_col[j] = dL/d col_lse[j] (nullable),
+ * w_pos[i] = dL/d pos[i]:   dS_ij = w_row[i] softmax_row_ij + w_col[j] softmax_col_ij + w_pos[i] [j == pos_i]
+ * and gQ += dS K / tau, gK += dS^T Q / tau, chained through the row normalisation when
+ * cos != 0.  gQ [M,d] / gK [N,d] are overwritten (not accumulated). */
+int gcf_infonce_bwd(const float* Q, int64_t ldq, int64_t M, const float* Kmat, int64_t ldk, int64_t N, int32_t d,
+                    int32_t cos, float tau, const int64_t* pos_idx,
+                    const float* row_lse, const float* col_lse,
+                    const float* w_row, const float* w_col, const float* w_pos,
+                    float* gQ, int64_t ldgq, float* gK, int64_t ldgk,
+                    void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+
+/* DirectAU (directau.py:240-251).  x, y: [B, d] fp32 rows (normalised inside).
+ *   align   = mean_b |x^_b - y^_b|^2
+ *   unif(x) = log( mean_{i<j} exp(-t * |x^_i - x^_j|^2) + 1e-8 ),  Gram matrix on tensor cores
+ * out[0] = align, out[1] = unif(x), out[2] = unif(y). */
+size_t gcf_directau_workspace_bytes(int64_t B, int32_t d);
+int gcf_directau_fwd(const float* x, int64_t ldx, const float* y, int64_t ldy, int64_t B, int32_t d, float t,
+                     float* out3, void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+/* w3 = device [3] upstream gradients of (align, unif(x), unif(y)); gx, gy overwritten. */
+int gcf_directau_bwd(const float* x, int64_t ldx, const float* y, int64_t ldy, int64_t B, int32_t d, float t,
+                     const float* out3, const float* w3, float* gx, int64_t ldgx, float* gy, int64_t ldgy,
+                     void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCF_H_ */

@@ -1,0 +1,98 @@
+"""Build libgcf.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python -m recommendation_b200.build [--force] [--verbose]
+
+Every .cu under csrc/ is compiled with
+    nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3
+into build/gcf/*.o (git-ignored) and linked into recommendation_b200/libgcf.so, which travels to
+the GPU box with the repo snapshot.  nvcc cross-compiles, so this runs on a CPU-only machine.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+ROOT = PKG_DIR.parent
+CSRC = PKG_DIR / "csrc"
+OBJ_DIR = ROOT / "build" / "gcf"
+LIB_PATH = PKG_DIR / "libgcf.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def _digest(src: Path) -> str:
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for dep in [src, *sorted(CSRC.glob("*.cuh")), ROOT / "include" / "gcf.h"]:
+        h.update(dep.read_bytes())
+    return h.hexdigest()
+
+
+def _compile_one(nvcc: str, src: Path, force: bool, verbose: bool) -> Path:
+    obj = OBJ_DIR / (src.stem + ".o")
+    stamp = OBJ_DIR / (src.stem + ".sha")
+    dig = _digest(src)
+    if not force and obj.exists() and stamp.exists() and stamp.read_text() == dig:
+        return obj
+    cmd = [nvcc, *NVCC_FLAGS, "-I", str(ROOT / "include"), "-c", str(src), "-o", str(obj)]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src.name}:\n{res.stdout}\n{res.stderr}")
+    if verbose and res.stderr.strip():
+        print(res.stderr)
+    stamp.write_text(dig)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    nvcc = _nvcc()
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    sources = sorted(CSRC.glob("*.cu"))
+    if not sources:
+        raise RuntimeError(f"no CUDA sources under {CSRC}")
+    with ThreadPoolExecutor(max_workers=min(8, len(sources))) as pool:
+        objs = list(pool.map(lambda s: _compile_one(nvcc, s, force, verbose), sources))
+    newest = max(o.stat().st_mtime for o in objs)
+    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < newest:
+        cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs),
+               "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return LIB_PATH
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(description=__doc__)
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args(argv)
+    print(build(force=args.force, verbose=args.verbose))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,323 @@
+// Fused gather + BPR loss (+ squared-L2 regulariser of the gathered rows), forward and backward.
+//
+// Replaces the eager op chains x[idx] -> mul -> sum -> sigmoid -> log -> mean (+ norm(2).pow(2))
+// of ncl.py:116-120,314-317, lightgcn.py:95-118, gcl.py:216-223, mhcn.py:35-39, diffnet.py:1110-1115
+// and, in the backward, the three index_put_(accumulate=True) scatter-adds.
+//
+// Layout: a sub-warp of LPR = d/4 lanes owns a run of kRun consecutive triples; every lane keeps
+// a float4 slice of the user / positive / negative rows.  Consecutive triples with the same user
+// (the full-batch LightGCN case once the triples are in CSR order) reuse the user row and, in the
+// backward, accumulate the user gradient in registers: one red.global.add.v4.f32 per run instead of
+// one per triple.  The [T, d] gathered tensors of the reference are never materialised.
+#include "common.cuh"
+
+namespace gcf {
+
+constexpr int kRun = 8;
+constexpr int kBprThreads = 256;
+
+template <int LPR, int VPL, bool GUARD>
+__device__ __forceinline__ void load_row(const float* __restrict__ base, long long ld, long long row, int sl, int dvec,
+                                         float4 (&r)[VPL]) {
+  const float4* p = reinterpret_cast<const float4*>(base + row * ld);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int idx = sl + k * LPR;
+    r[k] = (!GUARD || idx < dvec) ? __ldg(p + idx) : f4_zero();
+  }
+}
+
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v, unsigned mask) {
+#pragma unroll
+  for (int off = LPR / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off);
+  return v;
+}
+
+__device__ __forceinline__ void bpr_pointwise(int variant, float eps, float x, float& loss, float& dl) {
+  if (variant == GCF_BPR_LOG_EPS_SIGMOID) {
+    const float sg = 1.f / (1.f + expf(-x));
+    loss = -logf(eps + sg);
+    dl = -sg * (1.f - sg) / (eps + sg);
+  } else {
+    // -log(sigmoid(x)) = softplus(-x), evaluated without overflow
+    loss = fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
+    dl = -1.f / (1.f + expf(x));
+  }
+}
+
+template <int LPR, int VPL, bool GUARD>
+__global__ void __launch_bounds__(kBprThreads)
+bpr_fwd_kernel(const float* __restrict__ uemb, long long ldu, const float* __restrict__ iemb, long long ldi, int dvec,
+               const int64_t* __restrict__ u_idx, const int64_t* __restrict__ p_idx, const int64_t* __restrict__ n_idx,
+               long long n, int n_negs, int variant, float eps, float w_loss, float reg_u, float reg_p, float reg_n,
+               float* __restrict__ coef_out, double* __restrict__ block_partials) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const long long group = ((long long)blockIdx.x * (kBprThreads / 32) + (threadIdx.x >> 5)) * RPW + sub;
+  const long long t0 = group * kRun;
+  const float inv_negs = 1.f / (float)n_negs;
+
+  double local = 0.0;
+  long long cur_u = -1;
+  float4 ur[VPL];
+  float su = 0.f;
+  if (t0 < n) {
+    const long long t1 = min(t0 + (long long)kRun, n);
+#pragma unroll 2
+    for (long long t = t0; t < t1; ++t) {
+      const long long u = ld_stream_i64(u_idx + t);
+      const long long p = ld_stream_i64(p_idx + t);
+      float4 pr[VPL];
+      load_row<LPR, VPL, GUARD>(iemb, ldi, p, sl, dvec, pr);
+      if (u != cur_u) {
+        load_row<LPR, VPL, GUARD>(uemb, ldu, u, sl, dvec, ur);
+        cur_u = u;
+        su = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) su += f4_dot(ur[k], ur[k]);
+        su = group_sum<LPR>(su, mask);
+      }
+      float dp = 0.f, sp = 0.f, dn = 0.f, sn = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) { dp += f4_dot(ur[k], pr[k]); sp += f4_dot(pr[k], pr[k]); }
+      for (int j = 0; j < n_negs; ++j) {
+        const long long q = ld_stream_i64(n_idx + t * n_negs + j);
+        float4 nr[VPL];
+        load_row<LPR, VPL, GUARD>(iemb, ldi, q, sl, dvec, nr);
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) { dn += f4_dot(ur[k], nr[k]); sn += f4_dot(nr[k], nr[k]); }
+      }
+      dp = group_sum<LPR>(dp, mask);
+      dn = group_sum<LPR>(dn, mask);
+      sp = group_sum<LPR>(sp, mask);
+      sn = group_sum<LPR>(sn, mask);
+      const float x = dp - dn * inv_negs;
+      float loss, dl;
+      bpr_pointwise(variant, eps, x, loss, dl);
+      if (sl == 0) {
+        coef_out[t] = dl * w_loss;
+        local += (double)(loss * w_loss) + (double)(reg_u * su) + (double)(reg_p * sp) + (double)(reg_n * sn);
+      }
+    }
+  }
+  // block reduction of the double partials (only sub-warp leaders hold non-zero values)
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+  __shared__ double warp_part[kBprThreads / 32];
+  if (lane == 0) warp_part[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kBprThreads / 32; ++w) s += warp_part[w];
+    block_partials[blockIdx.x] = s;
+  }
+}
+
+// deterministic final reduction: one block sums the per-block partials in a fixed order
+__global__ void __launch_bounds__(256) bpr_reduce_kernel(const double* __restrict__ partials, long long n_blocks,
+                                                       float* __restrict__ loss_out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n_blocks; i += 256) s += partials[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss_out = (float)sh[0];
+}
+
+template <int LPR, int VPL, bool GUARD>
+__device__ __forceinline__ void red_row(float* __restrict__ base, long long ld, long long row, int sl, int dvec,
+                                        const float4 (&v)[VPL]) {
+  float* p = base + row * ld;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int idx = sl + k * LPR;
+    if (!GUARD || idx < dvec) {
+      // no "memory" clobber on purpose: gradient tables never alias the embedding tables, so
+      // the compiler may hoist the next triple's gathers above these reductions.
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + 4 * idx), "f"(v[k].x), "f"(v[k].y),
+                   "f"(v[k].z), "f"(v[k].w));
+    }
+  }
+}
+
+template <int LPR, int VPL, bool GUARD>
+__global__ void __launch_bounds__(kBprThreads)
+bpr_bwd_kernel(const float* __restrict__ uemb, long long ldu, const float* __restrict__ iemb, long long ldi, int dvec,
+               const int64_t* __restrict__ u_idx, const int64_t* __restrict__ p_idx, const int64_t* __restrict__ n_idx,
+               long long n, int n_negs, const float* __restrict__ coef, const float* __restrict__ grad_out,
+               float reg_u, float reg_p, float reg_n, float* __restrict__ g_user, long long ldgu,
+               float* __restrict__ g_item, long long ldgi) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const long long group = ((long long)blockIdx.x * (kBprThreads / 32) + (threadIdx.x >> 5)) * RPW + sub;
+  const long long t0 = group * kRun;
+  if (t0 >= n) return;
+  const long long t1 = min(t0 + (long long)kRun, n);
+  const float g = (grad_out != nullptr) ? __ldg(grad_out) : 1.f;
+  const float inv_negs = 1.f / (float)n_negs;
+  const float ru2 = 2.f * reg_u * g, rp2 = 2.f * reg_p * g, rn2 = 2.f * reg_n * g;
+
+  long long cur_u = -1;
+  float4 ur[VPL], gu[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) gu[k] = f4_zero();
+
+#pragma unroll 2
+  for (long long t = t0; t < t1; ++t) {
+    const long long u = ld_stream_i64(u_idx + t);
+    const long long p = ld_stream_i64(p_idx + t);
+    const float c = ld_stream_f32(coef + t) * g;
+    float4 pr[VPL];
+    load_row<LPR, VPL, GUARD>(iemb, ldi, p, sl, dvec, pr);
+    if (u != cur_u) {
+      if (cur_u >= 0) red_row<LPR, VPL, GUARD>(g_user, ldgu, cur_u, sl, dvec, gu);
+      load_row<LPR, VPL, GUARD>(uemb, ldu, u, sl, dvec, ur);
+      cur_u = u;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) gu[k] = f4_zero();
+    }
+    // d/du: c * (p - mean_j n_j) + 2 reg_u u ;  d/dp: c * u + 2 reg_p p ;  d/dn_j: -c/n_negs * u + 2 reg_n n_j
+    float4 gp[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      gp[k] = make_float4(rp2 * pr[k].x, rp2 * pr[k].y, rp2 * pr[k].z, rp2 * pr[k].w);
+      f4_fma(gp[k], c, ur[k]);
+      f4_fma(gu[k], c, pr[k]);
+      f4_fma(gu[k], ru2, ur[k]);
+    }
+    red_row<LPR, VPL, GUARD>(g_item, ldgi, p, sl, dvec, gp);
+    const float cn = -c * inv_negs;
+    for (int j = 0; j < n_negs; ++j) {
+      const long long q = ld_stream_i64(n_idx + t * n_negs + j);
+      float4 nr[VPL], gn[VPL];
+      load_row<LPR, VPL, GUARD>(iemb, ldi, q, sl, dvec, nr);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        gn[k] = make_float4(rn2 * nr[k].x, rn2 * nr[k].y, rn2 * nr[k].z, rn2 * nr[k].w);
+        f4_fma(gn[k], cn, ur[k]);
+        f4_fma(gu[k], cn, nr[k]);
+      }
+      red_row<LPR, VPL, GUARD>(g_item, ldgi, q, sl, dvec, gn);
+    }
+  }
+  if (cur_u >= 0) red_row<LPR, VPL, GUARD>(g_user, ldgu, cur_u, sl, dvec, gu);
+}
+
+static inline long long bpr_blocks(long long n, int lpr) {
+  const long long groups_per_block = (long long)(kBprThreads / 32) * (32 / lpr);
+  return cdiv(cdiv(n, kRun), groups_per_block);
+}
+
+static inline int lpr_for(int d) {
+  switch (d) {
+    case 16: return 4;
+    case 32: return 8;
+    case 64: return 16;
+    default: return 32;
+  }
+}
+
+}  // namespace gcf
+
+using namespace gcf;
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" size_t gcf_bpr_workspace_bytes(int64_t n_triples) {
+  // one double per block of the forward kernel; LPR = 32 has the fewest triples per block, so it bounds the block count
+  const long long blocks = bpr_blocks(n_triples > 0 ? n_triples : 1, 32);
+  return align_up((size_t)blocks * sizeof(double));
+}
+
+#define GCF_BPR_DISPATCH(KERNEL, ...)                                                            \
+  do {                                                                                           \
+    switch (d) {                                                                                 \
+      case 16:  KERNEL<4, 1, false><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;           \
+      case 32:  KERNEL<8, 1, false><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;           \
+      case 64:  KERNEL<16, 1, false><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;          \
+      case 128: KERNEL<32, 1, false><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;          \
+      case 256: KERNEL<32, 2, false><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;          \
+      default:                                                                                   \
+        if (d <= 128)      KERNEL<32, 1, true><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__);       \
+        else if (d <= 256) KERNEL<32, 2, true><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__);       \
+        else if (d <= 512) KERNEL<32, 4, true><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__);       \
+        else               KERNEL<32, 8, true><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__);       \
+    }                                                                                            \
+  } while (0)
+
+static int bpr_check(const char* who, const float* user_emb, int64_t ld_user, const float* item_emb, int64_t ld_item,
+                     int32_t d, const int64_t* u_idx, const int64_t* p_idx, const int64_t* n_idx, int64_t n,
+                     int32_t n_negs) {
+  if (d <= 0 || (d & 3) != 0 || d > 1024) {
+    set_error("%s: d=%d unsupported (need d %% 4 == 0 and d <= 1024)", who, d);
+    return GCF_EUNSUPPORTED;
+  }
+  GCF_REQUIRE(n >= 0 && n_negs >= 1, "%s: bad n_triples / n_negs", who);
+  GCF_REQUIRE(user_emb && item_emb && aligned16(user_emb) && aligned16(item_emb), "%s: null/misaligned tables", who);
+  GCF_REQUIRE(ld_user >= d && ld_item >= d && (ld_user & 3) == 0 && (ld_item & 3) == 0, "%s: bad leading dims", who);
+  GCF_REQUIRE(n == 0 || (u_idx && p_idx && n_idx), "%s: null index arrays", who);
+  return GCF_OK;
+}
+
+extern "C" int gcf_bpr_fwd(const float* user_emb, int64_t ld_user, const float* item_emb, int64_t ld_item, int32_t d,
+                           const int64_t* u_idx, const int64_t* p_idx, const int64_t* n_idx, int64_t n_triples,
+                           int32_t n_negs, int32_t variant, float eps, int32_t reduction, float reg_u, float reg_p,
+                           float reg_n, float* loss_out, float* coef_out, void* workspace, size_t workspace_bytes,
+                           gcf_stream_t stream) {
+  int rc = bpr_check("gcf_bpr_fwd", user_emb, ld_user, item_emb, ld_item, d, u_idx, p_idx, n_idx, n_triples, n_negs);
+  if (rc != GCF_OK) return rc;
+  GCF_REQUIRE(loss_out != nullptr && (n_triples == 0 || coef_out != nullptr), "gcf_bpr_fwd: null outputs");
+  GCF_REQUIRE(variant == GCF_BPR_LOG_EPS_SIGMOID || variant == GCF_BPR_SOFTPLUS, "gcf_bpr_fwd: bad variant");
+  GCF_REQUIRE(reduction == GCF_REDUCE_MEAN || reduction == GCF_REDUCE_SUM, "gcf_bpr_fwd: bad reduction");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_triples == 0) {
+    GCF_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+    return GCF_OK;
+  }
+  const long long grid = bpr_blocks(n_triples, lpr_for(d));
+  GCF_REQUIRE(grid < 2147483647LL, "gcf_bpr_fwd: too many triples for one launch");
+  const size_t need = align_up((size_t)grid * sizeof(double));
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("gcf_bpr_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return GCF_EWORKSPACE;
+  }
+  double* partials = static_cast<double*>(workspace);
+  const float w_loss = (reduction == GCF_REDUCE_MEAN) ? (1.f / (float)n_triples) : 1.f;
+  const int dvec = d / 4;
+  GCF_BPR_DISPATCH(bpr_fwd_kernel, user_emb, ld_user, item_emb, ld_item, dvec, u_idx, p_idx, n_idx, n_triples, n_negs,
+                   variant, eps, w_loss, reg_u, reg_p, reg_n, coef_out, partials);
+  GCF_LAUNCH_CHECK("bpr_fwd_kernel");
+  bpr_reduce_kernel<<<1, 256, 0, st>>>(partials, grid, loss_out);
+  GCF_LAUNCH_CHECK("bpr_reduce_kernel");
+  return GCF_OK;
+}
+
+extern "C" int gcf_bpr_bwd(const float* user_emb, int64_t ld_user, const float* item_emb, int64_t ld_item, int32_t d,
+                           const int64_t* u_idx, const int64_t* p_idx, const int64_t* n_idx, int64_t n_triples,
+                           int32_t n_negs, const float* coef, const float* grad_out, float reg_u, float reg_p,
+                           float reg_n, float* g_user, int64_t ldg_user, float* g_item, int64_t ldg_item,
+                           gcf_stream_t stream) {
+  int rc = bpr_check("gcf_bpr_bwd", user_emb, ld_user, item_emb, ld_item, d, u_idx, p_idx, n_idx, n_triples, n_negs);
+  if (rc != GCF_OK) return rc;
+  GCF_REQUIRE(g_user && g_item && aligned16(g_user) && aligned16(g_item), "gcf_bpr_bwd: null/misaligned gradient tables");
+  GCF_REQUIRE(ldg_user >= d && ldg_item >= d && (ldg_user & 3) == 0 && (ldg_item & 3) == 0, "gcf_bpr_bwd: bad gradient leading dims");
+  if (n_triples == 0) return GCF_OK;
+  GCF_REQUIRE(coef != nullptr, "gcf_bpr_bwd: null coef");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long grid = bpr_blocks(n_triples, lpr_for(d));
+  GCF_REQUIRE(grid < 2147483647LL, "gcf_bpr_bwd: too many triples for one launch");
+  const int dvec = d / 4;
+  GCF_BPR_DISPATCH(bpr_bwd_kernel, user_emb, ld_user, item_emb, ld_item, dvec, u_idx, p_idx, n_idx, n_triples, n_negs,
+                   coef, grad_out, reg_u, reg_p, reg_n, g_user, ldg_user, g_item, ldg_item);
+  GCF_LAUNCH_CHECK("bpr_bwd_kernel");
+  return GCF_OK;
+}

@@ -1,0 +1,87 @@
+// Shared helpers for libgcf (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+#include "../../include/gcf.h"
+
+namespace gcf {
+
+void set_error(const char* fmt, ...);
+int sm_count();
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace.
+struct Arena {
+  char* base; size_t cap; size_t off;
+  Arena(void* p, size_t n) : base(static_cast<char*>(p)), cap(n), off(0) {}
+  template <typename T> T* take(size_t count) {
+    size_t bytes = align_up(count * sizeof(T));
+    if (base == nullptr || off + bytes > cap) { off = cap + 1; return nullptr; }
+    T* r = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return r;
+  }
+  bool ok() const { return off <= cap; }
+};
+
+}  // namespace gcf
+
+#define GCF_REQUIRE(cond, ...)                                  \
+  do {                                                          \
+    if (!(cond)) { gcf::set_error(__VA_ARGS__); return GCF_EINVAL; } \
+  } while (0)
+
+#define GCF_LAUNCH_CHECK(name)                                                  \
+  do {                                                                          \
+    cudaError_t e_ = cudaGetLastError();                                        \
+    if (e_ != cudaSuccess) {                                                    \
+      gcf::set_error("%s: CUDA error: %s", name, cudaGetErrorString(e_));       \
+      return GCF_ECUDA;                                                         \
+    }                                                                           \
+  } while (0)
+
+#define GCF_CUDA(call)                                                          \
+  do {                                                                          \
+    cudaError_t e_ = (call);                                                    \
+    if (e_ != cudaSuccess) {                                                    \
+      gcf::set_error("%s failed: %s", #call, cudaGetErrorString(e_));           \
+      return GCF_ECUDA;                                                         \
+    }                                                                           \
+  } while (0)
+
+// ---- device helpers --------------------------------------------------------------------
+namespace gcf {
+
+__device__ __forceinline__ int ld_stream_i32(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ long long ld_stream_i64(const int64_t* p) {
+  long long v;
+  asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+// 128-bit vector reduction (sm_90+): one L2 atomic transaction per 16 bytes.
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4_fma(float4& a, float s, const float4& x) {
+  a.x = fmaf(s, x.x, a.x); a.y = fmaf(s, x.y, a.y); a.z = fmaf(s, x.z, a.z); a.w = fmaf(s, x.w, a.w);
+}
+__device__ __forceinline__ void f4_add(float4& a, const float4& x) { a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w; }
+__device__ __forceinline__ float f4_dot(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+}  // namespace gcf

@@ -1,0 +1,424 @@
+// CSR SpMM and K-layer LightGCN propagation for sm_100a.
+//
+// Replaces torch.sparse.mm (ncl.py:419, selfcf.py:479, directau.py:290) / PyG LGConv.propagate
+// (lightgcn.py:25) and the layer-combination epilogues (ncl.py:421, selfcf.py:481-482,
+// lightgcn.py:26).  HBM/L2-bound gather kernel -- no tensor cores on purpose.
+//
+// Work decomposition
+//   * a sub-warp of LPR = d/4 lanes owns one output row; each lane keeps a float4 slice of
+//     the row in registers and streams the row's (col, val) pairs: the sub-warp loads LPR
+//     consecutive pairs with one coalesced request, then broadcasts them lane by lane
+//     (shfl) and issues UNR independent 128-bit gathers of X rows before consuming them.
+//   * rows longer than `chunk` entries (power-law hubs) are cut into chunks; one full warp
+//     per chunk, partial sums go to scratch and the last-arriving chunk of a row (atomic
+//     ticket, no spinning) reduces them in chunk order and runs the epilogue.  Long chunks
+//     occupy the lowest block ids so they are scheduled first.
+//   * epilogue fused: optional raw store, optional row-L2-normalise, linear combination
+//     with up to 8 addend matrices (layer mean / sum, backward residual terms).
+#include "common.cuh"
+#include <algorithm>
+
+namespace gcf {
+
+struct Epi {
+  float* Y; long long ldy;
+  float* O; long long ldo;
+  int epilogue; float alpha, post;
+  int n_add;
+  const float* add[GCF_MAX_ADDENDS];
+  float beta[GCF_MAX_ADDENDS];
+};
+
+struct LongPlan {
+  int chunk, n_long, n_chunks;
+  const int* long_rows;
+  const int* long_chunk_ptr;
+  const int* chunk_long;
+  float* partial;
+  int* counters;
+};
+
+constexpr int kWarpsPerBlock = 8;
+
+template <int LPR, int VPL, int UNR, bool GUARD>
+__device__ __forceinline__ void accumulate(const int* __restrict__ col_idx, const float* __restrict__ vals,
+                                           int begin, int end, int stride, const float* __restrict__ X,
+                                           long long ldx, int sl, unsigned mask, int dvec, float4 (&acc)[VPL]) {
+  for (int base = begin; base < end; base += stride) {
+    const int j = base + sl;
+    int c = 0;
+    float v = 0.f;
+    if (j < end) {
+      c = ld_stream_i32(col_idx + j);
+      v = ld_stream_f32(vals + j);
+    }
+    const int cnt = min(LPR, end - base);
+    if (cnt == LPR) {
+#pragma unroll
+      for (int t0 = 0; t0 < LPR; t0 += UNR) {
+        float4 x[UNR][VPL];
+        float w[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int ct = __shfl_sync(mask, c, t0 + u, LPR);
+          w[u] = __shfl_sync(mask, v, t0 + u, LPR);
+          const float4* xr = reinterpret_cast<const float4*>(X + (long long)ct * ldx);
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) {
+            const int idx = sl + k * LPR;
+            x[u][k] = (!GUARD || idx < dvec) ? __ldg(xr + idx) : f4_zero();
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) f4_fma(acc[k], w[u], x[u][k]);
+      }
+    } else {
+      // ragged tail: replay the last valid column with weight 0 to keep UNR loads in flight
+      for (int t0 = 0; t0 < cnt; t0 += UNR) {
+        float4 x[UNR][VPL];
+        float w[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int t = t0 + u;
+          const int tt = min(t, cnt - 1);
+          const int ct = __shfl_sync(mask, c, tt, LPR);
+          const float wt = __shfl_sync(mask, v, tt, LPR);
+          w[u] = (t < cnt) ? wt : 0.f;
+          const float4* xr = reinterpret_cast<const float4*>(X + (long long)ct * ldx);
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) {
+            const int idx = sl + k * LPR;
+            x[u][k] = (!GUARD || idx < dvec) ? __ldg(xr + idx) : f4_zero();
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) f4_fma(acc[k], w[u], x[u][k]);
+      }
+    }
+  }
+}
+
+template <int LPR, int VPL, bool GUARD>
+__device__ __forceinline__ void finish_row(const Epi& ep, long long row, int sl, unsigned mask, int dvec,
+                                           float4 (&acc)[VPL]) {
+  if (ep.Y != nullptr) {
+    float4* y = reinterpret_cast<float4*>(ep.Y + row * ep.ldy);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int idx = sl + k * LPR;
+      if (!GUARD || idx < dvec) y[idx] = acc[k];
+    }
+  }
+  if (ep.O != nullptr) {
+    float inv = 1.f;
+    if (ep.epilogue == GCF_EPILOGUE_L2NORM) {
+      float ss = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) ss += f4_dot(acc[k], acc[k]);
+#pragma unroll
+      for (int off = LPR / 2; off > 0; off >>= 1) ss += __shfl_xor_sync(mask, ss, off);
+      inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(|x|, eps)
+    }
+    const float a = ep.alpha * inv;
+    float4* o = reinterpret_cast<float4*>(ep.O + row * ep.ldo);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int idx = sl + k * LPR;
+      if (!GUARD || idx < dvec) {
+        float4 r = f4_zero();
+        for (int q = 0; q < ep.n_add; ++q) {
+          const float4 z = __ldg(reinterpret_cast<const float4*>(ep.add[q] + row * ep.ldo) + idx);
+          f4_fma(r, ep.beta[q], z);
+        }
+        f4_fma(r, a, acc[k]);
+        r.x *= ep.post; r.y *= ep.post; r.z *= ep.post; r.w *= ep.post;
+        o[idx] = r;
+      }
+    }
+  }
+}
+
+template <int LPR, int VPL, int UNR, bool GUARD, int MINB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
+spmm_csr_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx, const float* __restrict__ vals,
+                long long n_rows, const float* __restrict__ X, long long ldx, int dvec, Epi ep, LongPlan lp,
+                int long_blocks) {
+  constexpr int RPW = 32 / LPR;  // rows per warp
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR;
+  const int sl = lane % LPR;
+  const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+
+  float4 acc[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) acc[k] = f4_zero();
+
+  if ((int)blockIdx.x < long_blocks) {
+    // ---- long-row chunk: one warp per chunk ----
+    const int chunk_id = blockIdx.x * kWarpsPerBlock + warp;
+    if (chunk_id >= lp.n_chunks) return;
+    const int L = lp.chunk_long[chunk_id];
+    const int row = lp.long_rows[L];
+    const int c0 = lp.long_chunk_ptr[L];
+    const int nck = lp.long_chunk_ptr[L + 1] - c0;
+    const int rs = row_ptr[row], re = row_ptr[row + 1];
+    const int s = rs + (chunk_id - c0) * lp.chunk;
+    const int e = min(s + lp.chunk, re);
+    accumulate<LPR, VPL, UNR, GUARD>(col_idx, vals, s + sub * LPR, e, LPR * RPW, X, ldx, sl, mask, dvec, acc);
+    __syncwarp();
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, off);
+        acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, off);
+        acc[k].z += __shfl_xor_sync(0xffffffffu, acc[k].z, off);
+        acc[k].w += __shfl_xor_sync(0xffffffffu, acc[k].w, off);
+      }
+    const long long dpad = (long long)dvec * 4;
+    if (sub == 0) {
+      float4* part = reinterpret_cast<float4*>(lp.partial + (long long)chunk_id * dpad);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int idx = sl + k * LPR;
+        if (!GUARD || idx < dvec) part[idx] = acc[k];
+      }
+    }
+    __threadfence();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(lp.counters + L, 1) == nck - 1);
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    if (sub == 0) {
+      float4 tot[VPL];
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) tot[k] = f4_zero();
+      for (int q = 0; q < nck; ++q) {
+        const float4* p = reinterpret_cast<const float4*>(lp.partial + (long long)(c0 + q) * dpad);
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          const int idx = sl + k * LPR;
+          if (!GUARD || idx < dvec) f4_add(tot[k], __ldcg(p + idx));
+        }
+      }
+      finish_row<LPR, VPL, GUARD>(ep, row, sl, mask, dvec, tot);
+    }
+    if (lane == 0) lp.counters[L] = 0;  // self-resetting ticket for the next launch
+    return;
+  }
+
+  // ---- regular rows: one sub-warp per row ----
+  const long long row = ((long long)(blockIdx.x - long_blocks) * kWarpsPerBlock + warp) * RPW + sub;
+  if (row >= n_rows) return;
+  const int s = row_ptr[row], e = row_ptr[row + 1];
+  if (lp.n_long > 0 && e - s > lp.chunk) return;  // owned by the long path
+  accumulate<LPR, VPL, UNR, GUARD>(col_idx, vals, s, e, LPR, X, ldx, sl, mask, dvec, acc);
+  finish_row<LPR, VPL, GUARD>(ep, row, sl, mask, dvec, acc);
+}
+
+template <int LPR, int VPL, int UNR, bool GUARD, int MINB>
+static int launch(const gcf_csr_t* A, const float* X, long long ldx, int dvec, const Epi& ep, const LongPlan& lp,
+                  cudaStream_t st) {
+  constexpr int RPW = 32 / LPR;
+  const int long_blocks = (int)cdiv(lp.n_chunks, kWarpsPerBlock);
+  const long long short_blocks = cdiv(A->n_rows, (long long)kWarpsPerBlock * RPW);
+  const long long grid = long_blocks + short_blocks;
+  if (grid <= 0) return GCF_OK;
+  GCF_REQUIRE(grid < 2147483647LL, "gcf_spmm_csr_f32: grid too large");
+  spmm_csr_kernel<LPR, VPL, UNR, GUARD, MINB><<<(unsigned)grid, kWarpsPerBlock * 32, 0, st>>>(
+      A->row_ptr, A->col_idx, A->vals, A->n_rows, X, ldx, dvec, ep, lp, long_blocks);
+  GCF_LAUNCH_CHECK("spmm_csr_kernel");
+  return GCF_OK;
+}
+
+__global__ void axpby_kernel(float4* __restrict__ out, const float4* __restrict__ a, float sa,
+                             const float4* __restrict__ b, float sb, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 x = a[i];
+    float4 r = make_float4(sa * x.x, sa * x.y, sa * x.z, sa * x.w);
+    if (b != nullptr) {
+      float4 y = b[i];
+      r.x = fmaf(sb, y.x, r.x); r.y = fmaf(sb, y.y, r.y); r.z = fmaf(sb, y.z, r.z); r.w = fmaf(sb, y.w, r.w);
+    }
+    out[i] = r;
+  }
+}
+
+}  // namespace gcf
+
+using namespace gcf;
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" size_t gcf_spmm_counter_offset(const gcf_csr_t* A, int32_t d) {
+  if (A == nullptr || A->n_long <= 0) return 0;
+  return align_up((size_t)A->n_chunks * (size_t)d * sizeof(float));
+}
+
+extern "C" size_t gcf_spmm_workspace_bytes(const gcf_csr_t* A, int32_t d) {
+  if (A == nullptr || A->n_long <= 0) return 0;
+  return gcf_spmm_counter_offset(A, d) + align_up((size_t)A->n_long * sizeof(int32_t));
+}
+
+extern "C" int gcf_spmm_csr_f32(const gcf_csr_t* A, int32_t d, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                                float* OUT, int64_t ld_out, int32_t epilogue, float alpha, float post,
+                                int32_t n_addends, const float* const* addends, const float* betas, void* workspace,
+                                size_t workspace_bytes, int32_t variant, gcf_stream_t stream) {
+  GCF_REQUIRE(A != nullptr && X != nullptr, "gcf_spmm_csr_f32: null operator or X");
+  GCF_REQUIRE(A->n_rows >= 0 && A->n_cols >= 0, "gcf_spmm_csr_f32: negative shape");
+  GCF_REQUIRE(Y != nullptr || OUT != nullptr, "gcf_spmm_csr_f32: no output requested");
+  if (d <= 0 || (d & 3) != 0 || d > 1024) {
+    set_error("gcf_spmm_csr_f32: d=%d unsupported (need d %% 4 == 0 and d <= 1024)", d);
+    return GCF_EUNSUPPORTED;
+  }
+  GCF_REQUIRE(ldx >= d && (ldx & 3) == 0 && aligned16(X), "gcf_spmm_csr_f32: X must be 16B aligned with ld %% 4 == 0");
+  GCF_REQUIRE(Y == nullptr || (ldy >= d && (ldy & 3) == 0 && aligned16(Y)), "gcf_spmm_csr_f32: bad Y alignment/ld");
+  GCF_REQUIRE(OUT == nullptr || (ld_out >= d && (ld_out & 3) == 0 && aligned16(OUT)), "gcf_spmm_csr_f32: bad OUT alignment/ld");
+  GCF_REQUIRE(n_addends >= 0 && n_addends <= GCF_MAX_ADDENDS, "gcf_spmm_csr_f32: n_addends out of range");
+  GCF_REQUIRE(n_addends == 0 || (addends != nullptr && betas != nullptr && OUT != nullptr),
+              "gcf_spmm_csr_f32: addends need OUT, pointer and beta arrays");
+  GCF_REQUIRE(epilogue == GCF_EPILOGUE_NONE || epilogue == GCF_EPILOGUE_L2NORM, "gcf_spmm_csr_f32: bad epilogue");
+  if (A->n_rows == 0) return GCF_OK;
+  GCF_REQUIRE(A->row_ptr != nullptr, "gcf_spmm_csr_f32: null row_ptr");
+
+  Epi ep;
+  ep.Y = Y; ep.ldy = ldy; ep.O = OUT; ep.ldo = ld_out;
+  ep.epilogue = epilogue; ep.alpha = alpha; ep.post = post; ep.n_add = n_addends;
+  for (int q = 0; q < GCF_MAX_ADDENDS; ++q) { ep.add[q] = nullptr; ep.beta[q] = 0.f; }
+  for (int q = 0; q < n_addends; ++q) {
+    GCF_REQUIRE(addends[q] != nullptr && aligned16(addends[q]), "gcf_spmm_csr_f32: addend %d null or misaligned", q);
+    ep.add[q] = addends[q];
+    ep.beta[q] = betas[q];
+  }
+
+  LongPlan lp;
+  lp.chunk = 0; lp.n_long = 0; lp.n_chunks = 0;
+  lp.long_rows = nullptr; lp.long_chunk_ptr = nullptr; lp.chunk_long = nullptr; lp.partial = nullptr; lp.counters = nullptr;
+  if (A->n_long > 0) {
+    GCF_REQUIRE(A->chunk > 0 && A->n_chunks > 0 && A->long_rows && A->long_chunk_ptr && A->chunk_long,
+                "gcf_spmm_csr_f32: incomplete long-row schedule");
+    const size_t need = gcf_spmm_workspace_bytes(A, d);
+    if (workspace == nullptr || workspace_bytes < need) {
+      set_error("gcf_spmm_csr_f32: workspace too small (%zu < %zu)", workspace_bytes, need);
+      return GCF_EWORKSPACE;
+    }
+    lp.chunk = A->chunk; lp.n_long = A->n_long; lp.n_chunks = A->n_chunks;
+    lp.long_rows = A->long_rows; lp.long_chunk_ptr = A->long_chunk_ptr; lp.chunk_long = A->chunk_long;
+    lp.partial = reinterpret_cast<float*>(workspace);
+    lp.counters = reinterpret_cast<int*>(static_cast<char*>(workspace) + gcf_spmm_counter_offset(A, d));
+  }
+
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int dvec = d / 4;
+  switch (d) {
+    case 16: return launch<4, 1, 4, false, 4>(A, X, ldx, dvec, ep, lp, st);
+    case 32: return launch<8, 1, 8, false, 3>(A, X, ldx, dvec, ep, lp, st);
+    case 64:  // variants are tuning knobs (UNR loads in flight x resident blocks), same arithmetic
+      if (variant == 1) return launch<16, 1, 4, false, 4>(A, X, ldx, dvec, ep, lp, st);
+      if (variant == 2) return launch<16, 1, 16, false, 2>(A, X, ldx, dvec, ep, lp, st);
+      if (variant == 3) return launch<16, 1, 8, false, 4>(A, X, ldx, dvec, ep, lp, st);
+      return launch<16, 1, 8, false, 3>(A, X, ldx, dvec, ep, lp, st);
+    case 128:
+      if (variant == 1) return launch<32, 1, 4, false, 4>(A, X, ldx, dvec, ep, lp, st);
+      if (variant == 2) return launch<32, 1, 16, false, 2>(A, X, ldx, dvec, ep, lp, st);
+      if (variant == 3) return launch<32, 1, 8, false, 4>(A, X, ldx, dvec, ep, lp, st);
+      return launch<32, 1, 8, false, 3>(A, X, ldx, dvec, ep, lp, st);
+    case 256: return launch<32, 2, 4, false, 2>(A, X, ldx, dvec, ep, lp, st);
+    default: break;
+  }
+  if (d <= 128) return launch<32, 1, 8, true, 3>(A, X, ldx, dvec, ep, lp, st);
+  if (d <= 256) return launch<32, 2, 4, true, 2>(A, X, ldx, dvec, ep, lp, st);
+  if (d <= 512) return launch<32, 4, 2, true, 1>(A, X, ldx, dvec, ep, lp, st);
+  return launch<32, 8, 2, true, 1>(A, X, ldx, dvec, ep, lp, st);
+}
+
+extern "C" int gcf_propagate_fwd(const gcf_csr_t* A, int32_t d, int32_t n_layers, const float* X0,
+                                 float* const* layers, float* final_out, float scale, void* workspace,
+                                 size_t workspace_bytes, gcf_stream_t stream) {
+  GCF_REQUIRE(A != nullptr && X0 != nullptr, "gcf_propagate_fwd: null operator or X0");
+  GCF_REQUIRE(n_layers >= 1 && n_layers <= GCF_MAX_ADDENDS, "gcf_propagate_fwd: n_layers must be in [1, %d]", GCF_MAX_ADDENDS);
+  GCF_REQUIRE(A->n_rows == A->n_cols, "gcf_propagate_fwd: operator must be square");
+  GCF_REQUIRE(layers != nullptr, "gcf_propagate_fwd: null layers array");
+  const float* cur = X0;
+  for (int k = 1; k <= n_layers; ++k) {
+    float* y = layers[k - 1];
+    if (k < n_layers) {
+      GCF_REQUIRE(y != nullptr, "gcf_propagate_fwd: layers[%d] is NULL (only the last may be)", k - 1);
+      int rc = gcf_spmm_csr_f32(A, d, cur, d, y, d, nullptr, 0, GCF_EPILOGUE_NONE, 1.f, 1.f, 0, nullptr, nullptr,
+                                workspace, workspace_bytes, 0, stream);
+      if (rc != GCF_OK) return rc;
+      cur = y;
+    } else {
+      GCF_REQUIRE(y != nullptr || final_out != nullptr, "gcf_propagate_fwd: nothing to compute for the last layer");
+      const float* adds[GCF_MAX_ADDENDS];
+      float betas[GCF_MAX_ADDENDS];
+      int na = 0;
+      if (final_out != nullptr) {
+        adds[na] = X0; betas[na] = 1.f; ++na;
+        for (int q = 0; q < n_layers - 1; ++q) { adds[na] = layers[q]; betas[na] = 1.f; ++na; }
+      }
+      int rc = gcf_spmm_csr_f32(A, d, cur, d, y, d, final_out, d, GCF_EPILOGUE_NONE, 1.f, scale, na, adds, betas,
+                                workspace, workspace_bytes, 0, stream);
+      if (rc != GCF_OK) return rc;
+    }
+  }
+  return GCF_OK;
+}
+
+extern "C" int gcf_propagate_bwd(const gcf_csr_t* At, int32_t d, int32_t n_layers, const float* g_final,
+                                 const float* const* extra, float scale, float* ping, float* pong, float* g_x0,
+                                 void* workspace, size_t workspace_bytes, gcf_stream_t stream) {
+  GCF_REQUIRE(At != nullptr && g_x0 != nullptr, "gcf_propagate_bwd: null operator or output");
+  GCF_REQUIRE(n_layers >= 1 && n_layers <= GCF_MAX_ADDENDS, "gcf_propagate_bwd: n_layers must be in [1, %d]", GCF_MAX_ADDENDS);
+  GCF_REQUIRE(At->n_rows == At->n_cols, "gcf_propagate_bwd: operator must be square");
+  GCF_REQUIRE(n_layers == 1 || (ping != nullptr && pong != nullptr), "gcf_propagate_bwd: ping/pong scratch required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int K = n_layers;
+  const long long n4 = (long long)At->n_rows * d / 4;
+  auto ex = [&](int k) -> const float* { return extra != nullptr ? extra[k] : nullptr; };
+  GCF_REQUIRE(g_final != nullptr || ex(K) != nullptr, "gcf_propagate_bwd: no gradient reaches the last layer");
+
+  // G(K): only materialised when an extra gradient reaches E(K); otherwise fold scale*g into the first SpMM.
+  const float* cur = nullptr;  // G(k+1)
+  float cur_alpha = 1.f;
+  float* bufs[2] = {ping, pong};
+  int which = 0;
+  if (ex(K) != nullptr) {
+    GCF_REQUIRE(ping != nullptr, "gcf_propagate_bwd: ping scratch required when extra[K] is given");
+    const int blocks = (int)std::min<long long>(cdiv(n4, 256), (long long)sm_count() * 8);
+    if (g_final != nullptr)
+      axpby_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<float4*>(ping), reinterpret_cast<const float4*>(g_final),
+                                           scale, reinterpret_cast<const float4*>(ex(K)), 1.f, n4);
+    else
+      axpby_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<float4*>(ping), reinterpret_cast<const float4*>(ex(K)),
+                                           1.f, nullptr, 0.f, n4);
+    GCF_LAUNCH_CHECK("axpby_kernel");
+    cur = ping;
+    which = 1;
+  } else {
+    cur = g_final;
+    cur_alpha = scale;
+  }
+  for (int k = K - 1; k >= 0; --k) {
+    float* out = (k == 0) ? g_x0 : bufs[which];
+    const float* adds[2];
+    float betas[2];
+    int na = 0;
+    if (g_final != nullptr) { adds[na] = g_final; betas[na] = scale; ++na; }
+    if (ex(k) != nullptr) { adds[na] = ex(k); betas[na] = 1.f; ++na; }
+    int rc = gcf_spmm_csr_f32(At, d, cur, d, nullptr, 0, out, d, GCF_EPILOGUE_NONE, cur_alpha, 1.f, na, adds, betas,
+                              workspace, workspace_bytes, 0, stream);
+    if (rc != GCF_OK) return rc;
+    cur = out;
+    cur_alpha = 1.f;
+    which ^= 1;
+  }
+  return GCF_OK;
+}

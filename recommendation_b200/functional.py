@@ -1,0 +1,320 @@
+"""torch.autograd bridges from the reference's tensor-level operations to the libgcf kernels.
+
+Each function names the reference op chain it replaces.  Tensors are fp32, contiguous, on CUDA;
+anything else raises -- there is no eager fallback.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .graph import CSRGraph
+
+_DETERMINISTIC = os.environ.get("GCF_DETERMINISTIC", "0") == "1"
+
+
+def set_deterministic(flag: bool) -> None:
+    """Route gather backward through the sorted (order-reproducible) scatter-add."""
+    global _DETERMINISTIC
+    _DETERMINISTIC = bool(flag)
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device (got {t.device}); recommendation_b200 has no CPU path")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (got {t.dtype})")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rows_view(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
+    """Accept [n, d] tensors whose rows are contiguous (stride(1) == 1); returns (tensor, leading dim)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device (got {t.device})")
+    if t.dtype != torch.float32 or t.dim() != 2:
+        raise TypeError(f"{name} must be a 2-D float32 tensor")
+    if t.stride(1) != 1 or t.stride(0) < t.shape[1] or t.stride(0) % 4 != 0 or t.data_ptr() % 16 != 0:
+        t = t.contiguous()
+    return t, t.stride(0)
+
+
+def _idx(t, device, name: str) -> torch.Tensor:
+    """Reference call sites pass Python lists or LongTensors (ncl.py:314-316); normalise to int64 CUDA."""
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t, dtype=torch.int64)
+    if t.dtype != torch.int64:
+        t = t.to(torch.int64)
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
+# =========================================================================================
+# SpMM / propagation
+# =========================================================================================
+def spmm_raw(graph: CSRGraph, x: torch.Tensor, *, y: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+             epilogue: int = _lib.EPILOGUE_NONE, alpha: float = 1.0, post: float = 1.0,
+             addends: Sequence[torch.Tensor] = (), betas: Sequence[float] = (), variant: int = 0) -> None:
+    """Direct (non-autograd) call of gcf_spmm_csr_f32; see include/gcf.h for the epilogue algebra."""
+    lib = _lib.load()
+    d = x.shape[1]
+    ws, ws_bytes = graph.workspace(d)
+    _lib.check(lib.gcf_spmm_csr_f32(graph.struct_ref(), d, _lib.ptr(x), x.stride(0),
+                                    _lib.ptr(y), y.stride(0) if y is not None else 0,
+                                    _lib.ptr(out), out.stride(0) if out is not None else 0,
+                                    epilogue, alpha, post, len(addends), _lib.ptr_array(list(addends)),
+                                    _lib.float_array(list(betas)), _lib.ptr(ws), ws_bytes, variant,
+                                    _lib.current_stream()), "gcf_spmm_csr_f32")
+
+
+class _SpMM(torch.autograd.Function):
+    """Y = A @ X   (torch.sparse.mm, ncl.py:419 / selfcf.py:479 / mhcn.py:440-456)."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, graph: CSRGraph):
+        x = _f32c(x, "x")
+        if x.shape[0] != graph.n_cols:
+            raise ValueError(f"spmm: X has {x.shape[0]} rows, operator has {graph.n_cols} columns")
+        y = torch.empty(graph.n_rows, x.shape[1], dtype=torch.float32, device=x.device)
+        spmm_raw(graph, x, y=y)
+        ctx.graph = graph
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        gy = _f32c(gy, "grad")
+        gt = ctx.graph.transpose()
+        gx = torch.empty(gt.n_rows, gy.shape[1], dtype=torch.float32, device=gy.device)
+        spmm_raw(gt, gy, y=gx)
+        return gx, None
+
+
+def spmm(graph: CSRGraph, x: torch.Tensor) -> torch.Tensor:
+    return _SpMM.apply(x, graph)
+
+
+class _Propagate(torch.autograd.Function):
+    """K-layer LightGCN propagation with fused layer combination (gcf_propagate_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, x0: torch.Tensor, graph: CSRGraph, n_layers: int, scale: float, want_layers: bool):
+        lib = _lib.load()
+        x0 = _f32c(x0, "x0")
+        if graph.n_rows != graph.n_cols or x0.shape[0] != graph.n_rows:
+            raise ValueError("propagate: operator must be square and match x0's row count")
+        n, d = x0.shape
+        layers: List[Optional[torch.Tensor]] = [torch.empty_like(x0) for _ in range(n_layers - 1)]
+        layers.append(torch.empty_like(x0) if want_layers else None)
+        final = torch.empty_like(x0)
+        ws, ws_bytes = graph.workspace(d)
+        _lib.check(lib.gcf_propagate_fwd(graph.struct_ref(), d, n_layers, _lib.ptr(x0), _lib.ptr_array(layers),
+                                         _lib.ptr(final), scale, _lib.ptr(ws), ws_bytes, _lib.current_stream()),
+                   "gcf_propagate_fwd")
+        ctx.graph, ctx.n_layers, ctx.scale, ctx.want_layers = graph, n_layers, scale, want_layers
+        ctx.set_materialize_grads(False)  # unused layer outputs arrive as None, not as zero tensors
+        if want_layers:
+            return (final, *layers)
+        return (final,)
+
+    @staticmethod
+    def backward(ctx, g_final, *g_layers):
+        lib = _lib.load()
+        graph_t = ctx.graph.transpose()
+        k = ctx.n_layers
+        extra: List[Optional[torch.Tensor]] = [None] * (k + 1)
+        ref = g_final
+        for i, g in enumerate(g_layers):
+            if g is not None:
+                extra[i + 1] = _f32c(g, "layer grad")
+                ref = ref if ref is not None else g
+        if ref is None:
+            return None, None, None, None, None
+        if g_final is not None:
+            g_final = _f32c(g_final, "grad")
+        elif extra[k] is None:
+            g_final = torch.zeros_like(ref)  # rare: gradient only reaches an inner layer output
+        n, d = ref.shape
+        ping = torch.empty(n, d, dtype=torch.float32, device=ref.device) if (k > 1 or extra[k] is not None) else None
+        pong = torch.empty(n, d, dtype=torch.float32, device=ref.device) if k > 1 else None
+        g_x0 = torch.empty(n, d, dtype=torch.float32, device=ref.device)
+        ws, ws_bytes = graph_t.workspace(d)
+        _lib.check(lib.gcf_propagate_bwd(graph_t.struct_ref(), d, k, _lib.ptr(g_final), _lib.ptr_array(extra),
+                                         ctx.scale, _lib.ptr(ping), _lib.ptr(pong), _lib.ptr(g_x0), _lib.ptr(ws),
+                                         ws_bytes, _lib.current_stream()), "gcf_propagate_bwd")
+        # E(0) = x0 receives scale * g_final directly: already folded into G(0) by the kernel epilogue
+        return g_x0, None, None, None, None
+
+
+def propagate(graph: CSRGraph, x0: torch.Tensor, n_layers: int, *, mode: str = "mean",
+              return_layers: bool = False):
+    """final = mean|sum over [E0, A E0, ..., A^K E0].
+
+    mode="mean": LGCNEncoder / LGCN_Encoder (ncl.py:415-422, selfcf.py:475-485, directau.py:286-293)
+    mode="sum" : LightGCN.forward's `x += out` (lightgcn.py:21-27)
+    return_layers=True also returns [E1..EK] (E0 is x0 itself), as in ncl.py:417-422.
+    """
+    if mode not in ("mean", "sum"):
+        raise ValueError("mode must be 'mean' or 'sum'")
+    if n_layers < 1:
+        raise ValueError("n_layers must be >= 1")
+    scale = 1.0 / (n_layers + 1) if mode == "mean" else 1.0
+    outs = _Propagate.apply(x0, graph, int(n_layers), float(scale), bool(return_layers))
+    if return_layers:
+        return outs[0], list(outs[1:])
+    return outs[0]
+
+
+# =========================================================================================
+# gather / scatter-add
+# =========================================================================================
+def scatter_add_rows_(table_grad: torch.Tensor, idx: torch.Tensor, src: torch.Tensor, *, deterministic: Optional[bool] = None) -> None:
+    """table_grad[idx[t]] += src[t]   (index_put_(accumulate=True), the backward of x[idx])."""
+    lib = _lib.load()
+    det = _DETERMINISTIC if deterministic is None else deterministic
+    src, lds = _rows_view(src, "src")
+    n, d = src.shape
+    mode = 1 if det else 0
+    ws_bytes = lib.gcf_scatter_add_workspace_bytes(n, table_grad.shape[0], mode)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=src.device) if ws_bytes else None
+    _lib.check(lib.gcf_scatter_add_rows(_lib.ptr(src), lds, d, _lib.ptr(idx), n, _lib.ptr(table_grad),
+                                        table_grad.stride(0), table_grad.shape[0], mode, _lib.ptr(ws), ws_bytes,
+                                        _lib.current_stream()), "gcf_scatter_add_rows")
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table: torch.Tensor, idx: torch.Tensor):
+        lib = _lib.load()
+        table, ld = _rows_view(table, "table")
+        n_rows, d = table.shape
+        out = torch.empty(idx.numel(), d, dtype=torch.float32, device=table.device)
+        _lib.check(lib.gcf_gather_rows(_lib.ptr(table), ld, n_rows, d, _lib.ptr(idx), idx.numel(), _lib.ptr(out), d,
+                                       _lib.current_stream()), "gcf_gather_rows")
+        ctx.save_for_backward(idx)
+        ctx.shape = (n_rows, d)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        g = _f32c(g, "grad")
+        table_grad = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
+        scatter_add_rows_(table_grad, idx, g)
+        return table_grad, None
+
+
+def gather_rows(table: torch.Tensor, idx) -> torch.Tensor:
+    """table[idx] with a warp-aggregated scatter-add backward (ncl.py:314-316, selfcf.py:504-511, ...)."""
+    idx = _idx(idx, table.device, "idx")
+    if os.environ.get("GCF_CHECK_INDEX") == "1" and idx.numel():  # costs a device sync; off by default
+        if int(idx.min()) < 0 or int(idx.max()) >= table.shape[0]:
+            raise IndexError("gather_rows: index out of range")
+    return _GatherRows.apply(table, idx)
+
+
+# =========================================================================================
+# negative sampler
+# =========================================================================================
+def sample_negatives(n: int, n_items: int, *, seed: int, offset: int = 0, n_negs: int = 1,
+                     users: Optional[torch.Tensor] = None, positives: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                     max_trials: int = 100, device=None) -> torch.Tensor:
+    """Philox4x32-10 negatives; with `positives=(row_ptr, col_idx)` (per-user sorted item CSR) candidates
+    that are training positives of `users[t]` are rejected (ncl.py:91-114), otherwise uniform as
+    torch.randint (lightgcn.py:91-94).  Returns int64 [n] (n_negs == 1) or [n, n_negs]."""
+    lib = _lib.load()
+    dev = device if device is not None else (users.device if users is not None else torch.device("cuda", torch.cuda.current_device()))
+    out = torch.empty(n * n_negs, dtype=torch.int64, device=dev)
+    rp = ci = None
+    if positives is not None:
+        rp, ci = positives
+        if users is None:
+            raise ValueError("rejection sampling needs the user of each triple")
+        users = _idx(users, dev, "users")
+    _lib.check(lib.gcf_sample_negatives(int(seed) & (2**64 - 1), int(offset) & (2**64 - 1), _lib.ptr(users), n, n_negs,
+                                        n_items, _lib.ptr(rp), _lib.ptr(ci), max_trials, _lib.ptr(out),
+                                        _lib.current_stream()), "gcf_sample_negatives")
+    return out if n_negs == 1 else out.view(n, n_negs)
+
+
+# =========================================================================================
+# fused BPR
+# =========================================================================================
+class _BprFused(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, user_emb, item_emb, u_idx, p_idx, n_idx, n_negs, variant, eps, reduction, reg_u, reg_p, reg_n):
+        lib = _lib.load()
+        user_emb, ldu = _rows_view(user_emb, "user_emb")
+        item_emb, ldi = _rows_view(item_emb, "item_emb")
+        d = user_emb.shape[1]
+        if item_emb.shape[1] != d:
+            raise ValueError("user/item embedding widths differ")
+        n = u_idx.numel()
+        dev = user_emb.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        coef = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        ws_bytes = lib.gcf_bpr_workspace_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.gcf_bpr_fwd(_lib.ptr(user_emb), ldu, _lib.ptr(item_emb), ldi, d, _lib.ptr(u_idx), _lib.ptr(p_idx),
+                                   _lib.ptr(n_idx), n, n_negs, variant, eps, reduction, reg_u, reg_p, reg_n,
+                                   _lib.ptr(loss), _lib.ptr(coef), _lib.ptr(ws), ws_bytes, _lib.current_stream()),
+                   "gcf_bpr_fwd")
+        ctx.save_for_backward(user_emb, item_emb, u_idx, p_idx, n_idx, coef)
+        ctx.args = (ldu, ldi, d, n, n_negs, reg_u, reg_p, reg_n)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        user_emb, item_emb, u_idx, p_idx, n_idx, coef = ctx.saved_tensors
+        ldu, ldi, d, n, n_negs, reg_u, reg_p, reg_n = ctx.args
+        g = g.contiguous().to(torch.float32)
+        g_user = torch.zeros(user_emb.shape, dtype=torch.float32, device=user_emb.device)
+        g_item = torch.zeros(item_emb.shape, dtype=torch.float32, device=item_emb.device)
+        _lib.check(lib.gcf_bpr_bwd(_lib.ptr(user_emb), ldu, _lib.ptr(item_emb), ldi, d, _lib.ptr(u_idx), _lib.ptr(p_idx),
+                                   _lib.ptr(n_idx), n, n_negs, _lib.ptr(coef), _lib.ptr(g), reg_u, reg_p, reg_n,
+                                   _lib.ptr(g_user), d, _lib.ptr(g_item), d, _lib.current_stream()), "gcf_bpr_bwd")
+        return (g_user, g_item) + (None,) * 10
+
+
+def bpr_loss_gather(user_emb: torch.Tensor, item_emb: torch.Tensor, u_idx, p_idx, n_idx, *,
+                    variant: str = "softplus", eps: float = 1e-5, reduction: str = "mean",
+                    reg_u: float = 0.0, reg_p: float = 0.0, reg_n: float = 0.0) -> torch.Tensor:
+    """reduce_t l(<u,p> - mean_j <u,n_j>) + reg_u*sum|u|^2 + reg_p*sum|p|^2 + reg_n*sum|n|^2 with the three
+    gathers fused in.  variant "log_eps_sigmoid" = ncl.py:116-120; "softplus" = lightgcn.py:108 / gcl.py:221."""
+    dev = user_emb.device
+    u_idx, p_idx, n_idx = _idx(u_idx, dev, "u_idx"), _idx(p_idx, dev, "p_idx"), _idx(n_idx, dev, "n_idx")
+    n = u_idx.numel()
+    if p_idx.numel() != n or n_idx.numel() % max(n, 1) != 0:
+        raise ValueError("u_idx / p_idx / n_idx lengths are inconsistent")
+    n_negs = n_idx.numel() // n if n else 1
+    var = {"log_eps_sigmoid": _lib.BPR_LOG_EPS_SIGMOID, "softplus": _lib.BPR_SOFTPLUS}[variant]
+    red = {"mean": _lib.REDUCE_MEAN, "sum": _lib.REDUCE_SUM}[reduction]
+    return _BprFused.apply(user_emb, item_emb, u_idx, p_idx, n_idx.reshape(-1), n_negs, var, float(eps), red,
+                           float(reg_u), float(reg_p), float(reg_n))
+
+
+def bpr_loss_rows(user_rows: torch.Tensor, pos_rows: torch.Tensor, neg_rows: torch.Tensor, *,
+                  variant: str = "log_eps_sigmoid", eps: float = 1e-5, reduction: str = "mean") -> torch.Tensor:
+    """BPR on already-gathered [B, d] rows -- the reference's bpr_loss(user_emb, pos_item_emb, neg_item_emb)
+    signature (ncl.py:116-120).  Runs the same fused kernel with identity indices."""
+    b = user_rows.shape[0]
+    items = torch.cat([pos_rows, neg_rows], dim=0)
+    ar = torch.arange(b, dtype=torch.int64, device=user_rows.device)
+    return bpr_loss_gather(user_rows, items, ar, ar, ar + b, variant=variant, eps=eps, reduction=reduction)
+
+
+# =========================================================================================
+# optimiser
+# =========================================================================================
+def adam_step_(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int, *,
+               lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, decoupled: bool = False) -> None:
+    lib = _lib.load()
+    for name, t in (("param", param), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise TypeError(f"adam_step_: {name} must be a contiguous float32 CUDA tensor")
+    _lib.check(lib.gcf_adam_step(_lib.ptr(param), _lib.ptr(grad), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq), param.numel(),
+                                 lr, betas[0], betas[1], eps, weight_decay, 1 if decoupled else 0, int(step),
+                                 _lib.current_stream()), "gcf_adam_step")

@@ -1,0 +1,248 @@
+"""Device-resident CSR adjacency and its construction through the integer kernels of libgcf.
+
+Host-side mirror of the reference's graph containers:
+  * `Interaction.__create_sparse_bipartite_adjacency` + `Graph.normalize_graph_mat`
+    (selfcf.py:240-255,297-306; ssl4rec.py:79-88)                  -> CSRGraph.from_pairs(norm="sym")
+  * `Interaction._build_adj` raw COO with duplicates (ncl.py:76-85, directau.py:132-141)
+                                                                     -> CSRGraph.from_pairs(norm="none")
+  * `load_data` edge_index + PyG gcn_norm (lightgcn.py:36-39,25)     -> CSRGraph.from_edge_index(norm="sym")
+  * `TorchGraphInterface.convert_sparse_mat_to_tensor` (ncl.py:203-209, selfcf.py:219-225)
+                                                                     -> CSRGraph.from_scipy
+All index arithmetic (sort, duplicate merge, degrees) runs in CUDA kernels; only the long-row
+schedule (a few thousand hub rows) is planned on the host from the row pointer.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_NORM_CODES = {"none": _lib.NORM_NONE, "sym": _lib.NORM_SYM, "row": _lib.NORM_ROW}
+DEFAULT_CHUNK = int(os.environ.get("GCF_SPMM_CHUNK", "256"))
+
+
+@dataclass
+class LongRowPlan:
+    """Rows longer than `chunk` entries, cut into chunks of `chunk` entries (host arrays, int32)."""
+
+    chunk: int
+    long_rows: np.ndarray       # [n_long]
+    long_chunk_ptr: np.ndarray  # [n_long + 1]
+    chunk_long: np.ndarray      # [n_chunks]
+
+    @property
+    def n_long(self) -> int:
+        return int(self.long_rows.shape[0])
+
+    @property
+    def n_chunks(self) -> int:
+        return int(self.chunk_long.shape[0])
+
+
+def plan_long_rows(row_ptr: np.ndarray, chunk: int) -> LongRowPlan:
+    """Degree-bucketed schedule: which rows are split, and into how many chunks (pure numpy)."""
+    if chunk <= 0:
+        raise ValueError("chunk must be positive")
+    row_ptr = np.asarray(row_ptr, dtype=np.int64)
+    deg = np.diff(row_ptr)
+    long_rows = np.nonzero(deg > chunk)[0].astype(np.int32)
+    n_chunks_per_row = -(-deg[long_rows] // chunk)
+    long_chunk_ptr = np.zeros(long_rows.shape[0] + 1, dtype=np.int64)
+    np.cumsum(n_chunks_per_row, out=long_chunk_ptr[1:])
+    chunk_long = np.repeat(np.arange(long_rows.shape[0], dtype=np.int32), n_chunks_per_row)
+    if long_chunk_ptr[-1] >= 2**31:
+        raise ValueError("too many chunks")
+    return LongRowPlan(chunk, long_rows, long_chunk_ptr.astype(np.int32), chunk_long.astype(np.int32))
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: recommendation_b200 has no CPU path")
+
+
+class CSRGraph:
+    """CSR operator on the GPU (int32 structure, fp32 values) + long-row schedule + SpMM scratch."""
+
+    def __init__(self, row_ptr: torch.Tensor, col_idx: torch.Tensor, vals: torch.Tensor, n_rows: int, n_cols: int,
+                 *, symmetric: bool = False, chunk: Optional[int] = None, rowsum: Optional[torch.Tensor] = None,
+                 dinv: Optional[torch.Tensor] = None):
+        for name, t, dt in (("row_ptr", row_ptr, torch.int32), ("col_idx", col_idx, torch.int32), ("vals", vals, torch.float32)):
+            _require_cuda(t, name)
+            if t.dtype != dt or not t.is_contiguous():
+                raise ValueError(f"{name} must be contiguous {dt}")
+        if row_ptr.numel() != n_rows + 1:
+            raise ValueError("row_ptr must have n_rows + 1 entries")
+        self.row_ptr, self.col_idx, self.vals = row_ptr, col_idx, vals
+        self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self.nnz = int(col_idx.numel())
+        self.symmetric = bool(symmetric)
+        self.rowsum, self.dinv = rowsum, dinv
+        self.device = row_ptr.device
+        self._transpose: Optional["CSRGraph"] = None
+        self._workspaces: Dict[int, torch.Tensor] = {}
+        self.chunk = DEFAULT_CHUNK if chunk is None else int(chunk)
+        plan = plan_long_rows(row_ptr.cpu().numpy(), self.chunk)
+        self.plan = plan
+        self._long_rows = torch.from_numpy(plan.long_rows).to(self.device)
+        self._long_chunk_ptr = torch.from_numpy(plan.long_chunk_ptr).to(self.device)
+        self._chunk_long = torch.from_numpy(plan.chunk_long).to(self.device)
+        self._struct = _lib.CsrStruct(
+            n_rows=self.n_rows, n_cols=self.n_cols, nnz=self.nnz,
+            row_ptr=row_ptr.data_ptr(), col_idx=col_idx.data_ptr() if self.nnz else None,
+            vals=vals.data_ptr() if self.nnz else None,
+            chunk=plan.chunk if plan.n_long else 0, n_long=plan.n_long, n_chunks=plan.n_chunks,
+            long_rows=self._long_rows.data_ptr() if plan.n_long else None,
+            long_chunk_ptr=self._long_chunk_ptr.data_ptr() if plan.n_long else None,
+            chunk_long=self._chunk_long.data_ptr() if plan.n_long else None,
+        )
+
+    # ---- construction ---------------------------------------------------------------------
+    @classmethod
+    def from_coo(cls, rows: torch.Tensor, cols: torch.Tensor, vals: Optional[torch.Tensor], n_rows: int, n_cols: int,
+                 *, norm: str = "none", symmetric: bool = False, chunk: Optional[int] = None) -> "CSRGraph":
+        """COO (int64 indices, duplicates allowed) -> canonical CSR, then value normalisation."""
+        if norm not in _NORM_CODES:
+            raise ValueError(f"norm must be one of {sorted(_NORM_CODES)}")
+        lib = _lib.load()
+        _require_cuda(rows, "rows")
+        _require_cuda(cols, "cols")
+        rows = rows.to(torch.int64).contiguous()
+        cols = cols.to(torch.int64).contiguous()
+        nnz_in = int(rows.numel())
+        if cols.numel() != nnz_in:
+            raise ValueError("rows and cols must have the same length")
+        if vals is not None:
+            _require_cuda(vals, "vals")
+            vals = vals.to(torch.float32).contiguous()
+            if vals.numel() != nnz_in:
+                raise ValueError("vals must match rows/cols")
+        dev = rows.device
+        stream = _lib.current_stream()
+        row_ptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+        col_idx = torch.empty(max(nnz_in, 1), dtype=torch.int32, device=dev)
+        out_vals = torch.empty(max(nnz_in, 1), dtype=torch.float32, device=dev)
+        nnz_out = torch.zeros(1, dtype=torch.int64, device=dev)
+        ws_bytes = lib.gcf_coo_to_csr_workspace_bytes(nnz_in, n_rows, n_cols)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.gcf_coo_to_csr_stable(_lib.ptr(rows), _lib.ptr(cols), _lib.ptr(vals), nnz_in, n_rows, n_cols,
+                                             _lib.ptr(row_ptr), _lib.ptr(col_idx), _lib.ptr(out_vals), _lib.ptr(nnz_out),
+                                             _lib.ptr(ws), ws_bytes, stream), "gcf_coo_to_csr_stable")
+        nnz = int(nnz_out.item())
+        del ws
+        col_idx = col_idx[:nnz].clone() if nnz < col_idx.numel() else col_idx
+        out_vals = out_vals[:nnz].clone() if nnz < out_vals.numel() else out_vals
+        rowsum = torch.empty(n_rows, dtype=torch.float32, device=dev)
+        dinv = torch.empty(n_rows, dtype=torch.float32, device=dev)
+        normed = torch.empty_like(out_vals)
+        if n_rows > 0:
+            _lib.check(lib.gcf_norm_values(_NORM_CODES[norm], _lib.ptr(row_ptr), _lib.ptr(col_idx), _lib.ptr(out_vals),
+                                           n_rows, n_cols, _lib.ptr(normed), _lib.ptr(rowsum), _lib.ptr(dinv), stream),
+                       "gcf_norm_values")
+        return cls(row_ptr, col_idx, normed, n_rows, n_cols, symmetric=symmetric, chunk=chunk, rowsum=rowsum, dinv=dinv)
+
+    @classmethod
+    def from_edge_index(cls, edge_index: torch.Tensor, num_nodes: int, *, norm: str = "sym",
+                        symmetric: bool = True, chunk: Optional[int] = None) -> "CSRGraph":
+        """edge_index [2, E'] (PyG convention: message flows row -> col, out[col] += w * x[row]).
+
+        The operator applied to X is therefore M with M[col, row] = w, i.e. CSR rows = edge_index[1].
+        For the bidirectional edge list of lightgcn.py:36-39 M is symmetric.
+        """
+        if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise ValueError("edge_index must have shape [2, E]")
+        return cls.from_coo(edge_index[1], edge_index[0], None, num_nodes, num_nodes, norm=norm,
+                            symmetric=symmetric, chunk=chunk)
+
+    @classmethod
+    def from_pairs(cls, users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int, *, norm: str = "sym",
+                   chunk: Optional[int] = None) -> "CSRGraph":
+        """Bipartite user-item pairs -> symmetric (U+I)x(U+I) adjacency [[0,R],[R^T,0]]."""
+        lib = _lib.load()
+        _require_cuda(users, "users")
+        users = users.to(torch.int64).contiguous()
+        items = items.to(torch.int64).contiguous()
+        e = int(users.numel())
+        rows = torch.empty(2 * e, dtype=torch.int64, device=users.device)
+        cols = torch.empty(2 * e, dtype=torch.int64, device=users.device)
+        _lib.check(lib.gcf_bipartite_edge_index(_lib.ptr(users), _lib.ptr(items), e, n_users, _lib.ptr(rows), _lib.ptr(cols),
+                                                _lib.current_stream()), "gcf_bipartite_edge_index")
+        n = n_users + n_items
+        return cls.from_coo(rows, cols, None, n, n, norm=norm, symmetric=True, chunk=chunk)
+
+    @classmethod
+    def from_scipy(cls, mat, *, norm: str = "none", device: Optional[torch.device] = None,
+                   symmetric: Optional[bool] = None, chunk: Optional[int] = None) -> "CSRGraph":
+        """Any scipy.sparse matrix (the reference's `data.norm_adj`); COO triplets are uploaded as they are
+        (duplicates kept, like convert_sparse_mat_to_tensor) and canonicalised on the GPU."""
+        coo = mat.tocoo()
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        rows = torch.from_numpy(np.ascontiguousarray(coo.row, dtype=np.int64)).to(dev)
+        cols = torch.from_numpy(np.ascontiguousarray(coo.col, dtype=np.int64)).to(dev)
+        vals = torch.from_numpy(np.ascontiguousarray(coo.data, dtype=np.float32)).to(dev)
+        n_rows, n_cols = coo.shape
+        if symmetric is None:
+            symmetric = False
+            if n_rows == n_cols:
+                diff = (mat - mat.T)
+                symmetric = diff.nnz == 0 or float(abs(diff).max()) == 0.0
+        return cls.from_coo(rows, cols, vals, n_rows, n_cols, norm=norm, symmetric=symmetric, chunk=chunk)
+
+    # ---- derived operators ----------------------------------------------------------------
+    def transpose(self) -> "CSRGraph":
+        """CSR of the transpose (self when the operator is symmetric); cached."""
+        if self.symmetric:
+            return self
+        if self._transpose is None:
+            lib = _lib.load()
+            dev = self.device
+            t_row_ptr = torch.empty(self.n_cols + 1, dtype=torch.int32, device=dev)
+            t_col_idx = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)[: self.nnz]
+            t_vals = torch.empty(max(self.nnz, 1), dtype=torch.float32, device=dev)[: self.nnz]
+            ws_bytes = lib.gcf_csr_transpose_workspace_bytes(self.nnz, self.n_rows, self.n_cols)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.gcf_csr_transpose(_lib.ptr(self.row_ptr), _lib.ptr(self.col_idx), _lib.ptr(self.vals),
+                                             self.n_rows, self.n_cols, self.nnz, _lib.ptr(t_row_ptr), _lib.ptr(t_col_idx),
+                                             _lib.ptr(t_vals), _lib.ptr(ws), ws_bytes, _lib.current_stream()),
+                       "gcf_csr_transpose")
+            self._transpose = CSRGraph(t_row_ptr, t_col_idx, t_vals, self.n_cols, self.n_rows, chunk=self.chunk)
+            self._transpose._transpose = self
+        return self._transpose
+
+    # ---- plumbing for the kernels ---------------------------------------------------------
+    @property
+    def struct(self) -> "_lib.CsrStruct":
+        return self._struct
+
+    def struct_ref(self):
+        return ctypes.byref(self._struct)
+
+    def workspace(self, d: int) -> Tuple[Optional[torch.Tensor], int]:
+        """Zero-initialised SpMM scratch for embedding width d (partial sums + self-resetting tickets)."""
+        ws = self._workspaces.get(d)
+        if ws is None:
+            nbytes = _lib.load().gcf_spmm_workspace_bytes(self.struct_ref(), d)
+            ws = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=self.device)
+            self._workspaces[d] = ws
+        return ws, ws.numel()
+
+    def degrees(self) -> torch.Tensor:
+        """Row sums of the un-normalised adjacency (integer-valued for 0/1 graphs)."""
+        if self.rowsum is None:
+            raise RuntimeError("this CSRGraph was not built through from_coo; no row sums recorded")
+        return self.rowsum
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+
+        return sp.csr_matrix((self.vals.cpu().numpy(), self.col_idx.cpu().numpy(), self.row_ptr.cpu().numpy()),
+                             shape=(self.n_rows, self.n_cols))
+
+    def __repr__(self) -> str:
+        return (f"CSRGraph({self.n_rows}x{self.n_cols}, nnz={self.nnz}, symmetric={self.symmetric}, "
+                f"long_rows={self.plan.n_long}, chunks={self.plan.n_chunks})")

@@ -1,0 +1,455 @@
+"""GPU parity: the CUDA path (through the C-ABI of libgcf.so) against the CPU oracle and the golden fixtures
+generated from the reference.  Bit-exact for index / integer work; fp32 tolerances of the north star
+(rtol 1e-3) for propagated embeddings, losses and gradients -- most checks are far tighter."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph_ref, losses_ref, lightgcn_ref, philox_ref
+from recommendation_b200 import _lib, functional as F_, synth
+from recommendation_b200.graph import CSRGraph
+from recommendation_b200.lightgcn import LightGCN, FusedLightGCNTrainer, build_edge_index, bpr_step_loss, train_step
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-3, 1e-6  # north-star tolerance for fp32 results
+ULP2 = 2.4e-7
+
+
+def dev_t(a, cuda, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(cuda)
+
+
+def random_coo(rng, n_rows, n_cols, nnz, dup_frac=0.1, hub=False):
+    r = rng.integers(0, n_rows, nnz)
+    c = rng.integers(0, n_cols, nnz)
+    if hub:  # a few very long rows / hot columns
+        r[: nnz // 3] = rng.integers(0, 3, nnz // 3)
+        c[nnz // 3: nnz // 2] = rng.integers(0, 2, nnz // 2 - nnz // 3)
+    nd = int(nnz * dup_frac)
+    if nd:
+        src = rng.integers(0, nnz, nd)
+        r = np.concatenate([r, r[src]]); c = np.concatenate([c, c[src]])
+    v = (rng.random(r.shape[0]) + 0.5).astype(np.float32)
+    return r.astype(np.int64), c.astype(np.int64), v
+
+
+# ====================================================================== graph build
+@pytest.mark.parametrize("with_vals", [False, True])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (7, 5, 0), (50, 70, 300), (1000, 900, 20000), (70000, 65000, 300000)])
+def test_coo_to_csr_bit_exact(cuda, shape, with_vals):
+    n_rows, n_cols, nnz = shape
+    rng = np.random.default_rng(nnz + 1)
+    r, c, v = random_coo(rng, n_rows, n_cols, nnz, hub=nnz > 1000)
+    g = CSRGraph.from_coo(dev_t(r, cuda), dev_t(c, cuda), dev_t(v, cuda) if with_vals else None, n_rows, n_cols, norm="none")
+    rp, ci, vals = graph_ref.coo_to_canonical_csr(r, c, v if with_vals else None, n_rows, n_cols)
+    assert np.array_equal(g.row_ptr.cpu().numpy(), rp)
+    assert np.array_equal(g.col_idx.cpu().numpy(), ci)
+    # duplicates are summed in their original order on both sides -> bit-exact values
+    assert np.array_equal(g.vals.cpu().numpy(), vals)
+
+
+def test_degree_count_and_edge_index_bit_exact(cuda):
+    inter = synth.power_law_bipartite(300, 500, 4000, seed=3)
+    U, I = inter.n_users, inter.n_items
+    ei = build_edge_index(dev_t(inter.users, cuda), dev_t(inter.items, cuda), U)
+    want = graph_ref.bipartite_edge_index(inter.users, inter.items, U)
+    assert np.array_equal(ei.cpu().numpy(), want)
+    lib = _lib.load()
+    deg = torch.empty(U + I, dtype=torch.int32, device=cuda)
+    _lib.check(lib.gcf_degree_count(_lib.ptr(ei[1].contiguous()), ei.shape[1], _lib.ptr(deg), U + I, _lib.current_stream()), "deg")
+    assert np.array_equal(deg.cpu().numpy(), graph_ref.degrees(want[1], U + I))
+
+
+def test_sym_graph_matches_reference_fixture(cuda, golden):
+    g = golden("selfcf_graph")
+    U, I = int(g["n_users"]), int(g["n_items"])
+    csr = CSRGraph.from_pairs(dev_t(g["u_idx"], cuda), dev_t(g["i_idx"], cuda), U, I, norm="sym")
+    assert np.array_equal(csr.row_ptr.cpu().numpy(), g["norm_indptr"])
+    assert np.array_equal(csr.col_idx.cpu().numpy(), g["norm_indices"])
+    assert np.array_equal(csr.degrees().cpu().numpy(), g["rowsum"])          # degrees: bit-exact
+    np.testing.assert_allclose(csr.vals.cpu().numpy(), g["norm_data"], rtol=ULP2, atol=0)  # <= 2 ulp
+
+
+def test_raw_graph_matches_ncl_fixture(cuda, golden):
+    g = golden("ncl_graph")
+    U, I = int(g["n_users"]), int(g["n_items"])
+    csr = CSRGraph.from_coo(dev_t(g["coo_row"], cuda), dev_t(g["coo_col"], cuda), dev_t(g["coo_data"], cuda), U + I, U + I, norm="none")
+    rp, ci, v = graph_ref.coo_to_canonical_csr(g["coo_row"], g["coo_col"], g["coo_data"], U + I, U + I)
+    assert np.array_equal(csr.row_ptr.cpu().numpy(), rp) and np.array_equal(csr.col_idx.cpu().numpy(), ci)
+    assert np.array_equal(csr.vals.cpu().numpy(), v)
+
+
+@pytest.mark.parametrize("mode", ["sym", "row"])
+def test_norm_values_with_isolated_nodes(cuda, mode):
+    rng = np.random.default_rng(5)
+    n = 400
+    r, c, v = random_coo(rng, n, n, 3000)
+    r[r % 7 == 0] = 1  # rows 0, 7, 14, ... become empty -> rowsum 0 -> inf -> 0
+    csr = CSRGraph.from_coo(dev_t(r, cuda), dev_t(c, cuda), dev_t(v, cuda), n, n, norm=mode)
+    rp, ci, vals = graph_ref.coo_to_canonical_csr(r, c, v, n, n)
+    want, rowsum, dinv = graph_ref.normalize_csr(rp, ci, vals, n, n, mode)
+    assert (rowsum == 0).any()
+    got = csr.vals.cpu().numpy()
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, want, rtol=2 * ULP2, atol=0)
+    np.testing.assert_allclose(csr.rowsum.cpu().numpy(), rowsum, rtol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(60, 90, 500), (5000, 3000, 100000)])
+def test_csr_transpose_bit_exact(cuda, shape):
+    n_rows, n_cols, nnz = shape
+    rng = np.random.default_rng(11)
+    r, c, v = random_coo(rng, n_rows, n_cols, nnz, hub=True)
+    csr = CSRGraph.from_coo(dev_t(r, cuda), dev_t(c, cuda), dev_t(v, cuda), n_rows, n_cols, norm="none")
+    t = csr.transpose()
+    rp, ci, vals = graph_ref.coo_to_canonical_csr(r, c, v, n_rows, n_cols)
+    trp, tci, tv = graph_ref.csr_transpose(rp, ci, vals, n_rows, n_cols)
+    assert np.array_equal(t.row_ptr.cpu().numpy(), trp)
+    assert np.array_equal(t.col_idx.cpu().numpy(), tci)
+    assert np.array_equal(t.vals.cpu().numpy(), tv)
+
+
+# ====================================================================== SpMM
+@pytest.mark.parametrize("d", [16, 32, 64, 128, 256, 8, 48, 200, 320, 520])
+def test_spmm_matches_oracle(cuda, d):
+    rng = np.random.default_rng(d)
+    n_rows, n_cols, nnz = 700, 500, 9000
+    r, c, v = random_coo(rng, n_rows, n_cols, nnz, hub=True)
+    csr = CSRGraph.from_coo(dev_t(r, cuda), dev_t(c, cuda), dev_t(v, cuda), n_rows, n_cols, norm="none", chunk=64)
+    assert csr.plan.n_long > 0
+    x = rng.standard_normal((n_cols, d)).astype(np.float32)
+    y = torch.empty(n_rows, d, device=cuda)
+    F_.spmm_raw(csr, dev_t(x, cuda), y=y)
+    want = graph_ref.spmm_csr(csr.row_ptr.cpu().numpy(), csr.col_idx.cpu().numpy(), csr.vals.cpu().numpy(), x)
+    np.testing.assert_allclose(y.cpu().numpy(), want, rtol=1e-4, atol=1e-4)
+    # run twice: the self-resetting chunk tickets must leave the workspace reusable
+    y2 = torch.empty_like(y)
+    F_.spmm_raw(csr, dev_t(x, cuda), y=y2)
+    assert torch.equal(y, y2), "long-row reduction must be deterministic and re-runnable"
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("d", [64, 128])
+def test_spmm_variants_agree(cuda, d, variant):
+    inter = synth.power_law_bipartite(3000, 4000, 100000, seed=1)
+    csr = CSRGraph.from_pairs(dev_t(inter.users, cuda), dev_t(inter.items, cuda), 3000, 4000, norm="sym")
+    x = torch.randn(7000, d, device=cuda)
+    y0 = torch.empty_like(x); y1 = torch.empty_like(x)
+    F_.spmm_raw(csr, x, y=y0, variant=0)
+    F_.spmm_raw(csr, x, y=y1, variant=variant)
+    assert torch.equal(y0, y1)  # same summation order in every variant
+
+
+def test_spmm_epilogues(cuda):
+    rng = np.random.default_rng(2)
+    n, d = 600, 64
+    r, c, v = random_coo(rng, n, n, 8000, hub=True)
+    csr = CSRGraph.from_coo(dev_t(r, cuda), dev_t(c, cuda), dev_t(v, cuda), n, n, norm="row", chunk=128)
+    x = torch.randn(n, d, device=cuda)
+    z1, z2 = torch.randn(n, d, device=cuda), torch.randn(n, d, device=cuda)
+    y = torch.empty(n, d, device=cuda); o = torch.empty(n, d, device=cuda)
+    F_.spmm_raw(csr, x, y=y, out=o, epilogue=_lib.EPILOGUE_L2NORM, alpha=0.7, post=0.5, addends=[z1, z2], betas=[1.0, -2.0])
+    t = graph_ref.spmm_csr(csr.row_ptr.cpu().numpy(), csr.col_idx.cpu().numpy(), csr.vals.cpu().numpy(), x.cpu().numpy())
+    np.testing.assert_allclose(y.cpu().numpy(), t, rtol=1e-4, atol=1e-5)
+    nrm = np.maximum(np.linalg.norm(t, axis=1, keepdims=True), 1e-12)
+    want = 0.5 * (0.7 * t / nrm + z1.cpu().numpy().astype(np.float64) - 2.0 * z2.cpu().numpy())
+    np.testing.assert_allclose(o.cpu().numpy(), want, rtol=1e-4, atol=1e-5)
+
+
+def test_spmm_autograd_nonsymmetric(cuda):
+    rng = np.random.default_rng(4)
+    r, c, v = random_coo(rng, 300, 200, 4000, hub=True)
+    csr = CSRGraph.from_coo(dev_t(r, cuda), dev_t(c, cuda), dev_t(v, cuda), 300, 200, norm="row")
+    x = torch.randn(200, 32, device=cuda, requires_grad=True)
+    w = torch.randn(300, 32, device=cuda)
+    (F_.spmm(csr, x) * w).sum().backward()
+    dense = torch.from_numpy(csr.to_scipy().toarray()).double()
+    want = dense.T @ w.cpu().double()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_empty_and_ragged_operators(cuda):
+    # no entries at all, a single row, rows with exactly LPR / LPR+1 entries
+    csr = CSRGraph.from_coo(torch.zeros(0, dtype=torch.int64, device=cuda), torch.zeros(0, dtype=torch.int64, device=cuda), None, 5, 5)
+    x = torch.randn(5, 64, device=cuda)
+    y = torch.full((5, 64), 7.0, device=cuda)
+    F_.spmm_raw(csr, x, y=y)
+    assert torch.count_nonzero(y) == 0
+    for deg in (1, 15, 16, 17, 31, 32, 33, 255, 256, 257):
+        r = np.zeros(deg, np.int64); c = np.arange(deg, dtype=np.int64)
+        csr = CSRGraph.from_coo(dev_t(r, cuda), dev_t(c, cuda), None, 2, 300)
+        x = torch.randn(300, 64, device=cuda)
+        y = torch.empty(2, 64, device=cuda)
+        F_.spmm_raw(csr, x, y=y)
+        np.testing.assert_allclose(y[0].cpu().numpy(), x[:deg].double().sum(0).cpu().numpy(), rtol=1e-4, atol=1e-5)
+        assert torch.count_nonzero(y[1]) == 0
+
+
+# ====================================================================== propagation (fixtures from the reference)
+def test_propagate_matches_selfcf_encoder_fixture(cuda, golden):
+    g, e = golden("selfcf_graph"), golden("selfcf_encoder")
+    U, I = int(g["n_users"]), int(g["n_items"])
+    csr = CSRGraph.from_pairs(dev_t(g["u_idx"], cuda), dev_t(g["i_idx"], cuda), U, I, norm="sym")
+    uw = dev_t(e["user_w"], cuda).requires_grad_(True)
+    iw = dev_t(e["item_w"], cuda).requires_grad_(True)
+    final = F_.propagate(csr, torch.cat([uw, iw]), int(e["n_layers"]), mode="mean")
+    np.testing.assert_allclose(final[:U].detach().cpu().numpy(), e["user_all"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(final[U:].detach().cpu().numpy(), e["item_all"], rtol=RTOL, atol=ATOL)
+    ((final[:U] * dev_t(e["proj_u"], cuda)).sum() + (final[U:] * dev_t(e["proj_i"], cuda)).sum()).backward()
+    np.testing.assert_allclose(uw.grad.cpu().numpy(), e["grad_user_w"], rtol=RTOL, atol=1e-5)
+    np.testing.assert_allclose(iw.grad.cpu().numpy(), e["grad_item_w"], rtol=RTOL, atol=1e-5)
+
+
+def test_propagate_matches_ncl_encoder_fixture(cuda, golden):
+    g, e = golden("ncl_graph"), golden("ncl_encoder")
+    U, I = int(g["n_users"]), int(g["n_items"])
+    csr = CSRGraph.from_coo(dev_t(g["coo_row"], cuda), dev_t(g["coo_col"], cuda), dev_t(g["coo_data"], cuda), U + I, U + I,
+                            norm="none", symmetric=True)
+    uw = dev_t(e["user_w"], cuda).requires_grad_(True)
+    iw = dev_t(e["item_w"], cuda).requires_grad_(True)
+    x0 = torch.cat([uw, iw])
+    final, layers = F_.propagate(csr, x0, int(e["n_layers"]), mode="mean", return_layers=True)
+    all_emb = [x0] + layers
+    np.testing.assert_allclose(final[:U].detach().cpu().numpy(), e["user_out"], rtol=RTOL, atol=1e-5)
+    np.testing.assert_allclose(final[U:].detach().cpu().numpy(), e["item_out"], rtol=RTOL, atol=1e-5)
+    for k, t in enumerate(all_emb):
+        np.testing.assert_allclose(t.detach().cpu().numpy(), e["all_emb"][k], rtol=RTOL, atol=1e-5)
+    proj = dev_t(e["proj_layers"], cuda)
+    loss = (final[:U] * dev_t(e["proj_u"], cuda)).sum() + (final[U:] * dev_t(e["proj_i"], cuda)).sum()
+    loss = loss + sum((t * proj[k]).sum() for k, t in enumerate(all_emb))
+    loss.backward()  # gradients reach every layer output: exercises the `extra` path of gcf_propagate_bwd
+    np.testing.assert_allclose(uw.grad.cpu().numpy(), e["grad_user_w"], rtol=RTOL, atol=1e-4)
+    np.testing.assert_allclose(iw.grad.cpu().numpy(), e["grad_item_w"], rtol=RTOL, atol=1e-4)
+
+
+@pytest.mark.parametrize("k,mode", [(1, "mean"), (2, "sum"), (3, "sum"), (4, "mean"), (6, "mean")])
+def test_propagate_vs_oracle_small_graph(cuda, k, mode):
+    inter = synth.power_law_bipartite(3000, 4000, 100000, seed=k)
+    U, I, d = 3000, 4000, 64
+    csr = CSRGraph.from_pairs(dev_t(inter.users, cuda), dev_t(inter.items, cuda), U, I, norm="sym")
+    x0 = (torch.randn(U + I, d) * 0.1)
+    xg = x0.to(cuda).requires_grad_(True)
+    final = F_.propagate(csr, xg, k, mode=mode)
+    rp, ci, v = csr.row_ptr.cpu().numpy(), csr.col_idx.cpu().numpy(), csr.vals.cpu().numpy()
+    _, want = graph_ref.propagate(rp, ci, v, x0.numpy(), k, mode)
+    np.testing.assert_allclose(final.detach().cpu().numpy(), want, rtol=RTOL, atol=1e-6)
+    w = torch.randn(U + I, d)
+    (final * w.to(cuda)).sum().backward()
+    _, gwant = graph_ref.propagate(rp, ci, v, w.numpy(), k, mode)  # symmetric operator
+    np.testing.assert_allclose(xg.grad.cpu().numpy(), gwant, rtol=RTOL, atol=1e-5)
+
+
+# ====================================================================== gather / scatter / sampler / adam
+@pytest.mark.parametrize("d", [16, 64, 128, 200])
+@pytest.mark.parametrize("det", [False, True])
+def test_gather_and_scatter_add(cuda, d, det):
+    rng = np.random.default_rng(d)
+    table = torch.randn(500, d, device=cuda, requires_grad=True)
+    idx_np = np.concatenate([rng.integers(0, 500, 3000), np.full(400, 7), np.full(300, 499)])  # hot rows
+    rng.shuffle(idx_np)
+    idx = dev_t(idx_np, cuda)
+    out = F_.gather_rows(table, idx)
+    assert torch.equal(out, table.detach()[idx])  # gather: bit-exact
+    w = torch.randn(idx.numel(), d, device=cuda)
+    F_.set_deterministic(det)
+    try:
+        (out * w).sum().backward()
+    finally:
+        F_.set_deterministic(False)
+    want = torch.zeros(500, d, dtype=torch.float64).index_add_(0, torch.from_numpy(idx_np), w.cpu().double())
+    np.testing.assert_allclose(table.grad.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-4)
+    if det:
+        table2 = table.detach().clone().requires_grad_(True)
+        F_.set_deterministic(True)
+        try:
+            (F_.gather_rows(table2, idx) * w).sum().backward()
+        finally:
+            F_.set_deterministic(False)
+        assert torch.equal(table.grad, table2.grad), "deterministic scatter-add must be run-to-run identical"
+
+
+def test_gather_accepts_python_lists(cuda):
+    table = torch.randn(50, 32, device=cuda)
+    assert torch.equal(F_.gather_rows(table, [3, 3, 49, 0]), table[[3, 3, 49, 0]])
+    assert F_.gather_rows(table, []).shape == (0, 32)
+
+
+def test_sampler_bit_exact_vs_oracle(cuda):
+    n, n_items = 5000, 4099
+    got = F_.sample_negatives(n, n_items, seed=0x1234567890ABCDEF, offset=3, device=cuda)
+    want = philox_ref.sample_negatives(0x1234567890ABCDEF, 3, n, 1, n_items)
+    assert np.array_equal(got.cpu().numpy(), want)
+    got = F_.sample_negatives(n, n_items, seed=9, offset=(1 << 40) + 5, n_negs=3, device=cuda)
+    want = philox_ref.sample_negatives(9, (1 << 40) + 5, n, 3, n_items).reshape(n, 3)
+    assert np.array_equal(got.cpu().numpy(), want)
+    # rejection against per-user sorted positives
+    inter = synth.power_law_bipartite(200, 300, 6000, seed=8)
+    rp, ci, _ = graph_ref.coo_to_canonical_csr(inter.users, inter.items, None, 200, 300)
+    users = np.random.default_rng(0).integers(0, 200, n)
+    got = F_.sample_negatives(n, 300, seed=77, offset=1, users=dev_t(users, cuda), positives=(dev_t(rp, cuda), dev_t(ci, cuda)),
+                              max_trials=100, device=cuda)
+    want = philox_ref.sample_negatives(77, 1, n, 1, 300, users, rp, ci, max_trials=100)
+    assert np.array_equal(got.cpu().numpy(), want)
+    pos = set(zip(inter.users.tolist(), inter.items.tolist()))
+    assert not any((u, j) in pos for u, j in zip(users.tolist(), got.cpu().tolist()))
+
+
+@pytest.mark.parametrize("wd,decoupled", [(0.0, False), (1e-2, False), (1e-2, True)])
+def test_adam_matches_torch(cuda, wd, decoupled):
+    torch.manual_seed(0)
+    p0 = torch.randn(1000, 64)
+    ref = p0.clone().requires_grad_(True)
+    opt = (torch.optim.AdamW if decoupled else torch.optim.Adam)([ref], lr=0.01, weight_decay=wd)
+    p = p0.to(cuda); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in range(1, 6):
+        g = torch.randn(1000, 64)
+        ref.grad = g.clone(); opt.step()
+        F_.adam_step_(p, g.to(cuda), m, v, step, lr=0.01, weight_decay=wd, decoupled=decoupled)
+    np.testing.assert_allclose(p.cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+
+
+# ====================================================================== BPR
+def test_bpr_matches_ncl_fixture(cuda, golden):
+    z = golden("ncl_losses")
+    ue, pe, ne = (dev_t(z[k], cuda).requires_grad_(True) for k in ("ue", "pe", "ne"))
+    loss = F_.bpr_loss_rows(ue, pe, ne, variant="log_eps_sigmoid", eps=1e-5)
+    np.testing.assert_allclose(loss.item(), z["bpr"], rtol=RTOL)
+    loss.backward()
+    for t, k in ((ue, "g_bpr_u"), (pe, "g_bpr_p"), (ne, "g_bpr_n")):
+        np.testing.assert_allclose(t.grad.cpu().numpy(), z[k], rtol=RTOL, atol=1e-7)
+
+
+def test_bpr_matches_gcl_fixture(cuda, golden):
+    z = golden("gcl_losses")
+    ue, pe, ne = (dev_t(z[k], cuda).requires_grad_(True) for k in ("ue", "pe", "ne"))
+    b = ue.shape[0]
+    items = torch.cat([pe, ne])
+    ar = torch.arange(b, device=cuda)
+    r = float(z["reg_weight"]) / b
+    loss = F_.bpr_loss_gather(ue, items, ar, ar, ar + b, variant="softplus", reg_u=r, reg_p=r, reg_n=r)
+    np.testing.assert_allclose(loss.item(), z["bpr_reg"], rtol=RTOL)
+    loss.backward()
+    for t, k in ((ue, "g_u"), (pe, "g_p"), (ne, "g_n")):
+        np.testing.assert_allclose(t.grad.cpu().numpy(), z[k], rtol=RTOL, atol=1e-7)
+
+
+@pytest.mark.parametrize("d", [16, 64, 128, 72])
+@pytest.mark.parametrize("n_negs", [1, 3])
+@pytest.mark.parametrize("sorted_users", [False, True])
+def test_bpr_lightgcn_form_vs_oracle(cuda, d, n_negs, sorted_users):
+    rng = np.random.default_rng(d + n_negs)
+    U, I, T = 300, 400, 5003
+    ue = torch.randn(U, d) * 0.3; ie = torch.randn(I, d) * 0.3
+    pu = rng.integers(0, U, T); pi = rng.integers(0, I, T)
+    if sorted_users:
+        pu = np.sort(pu)
+    ni = rng.integers(0, I, (T, n_negs)) if n_negs > 1 else rng.integers(0, I, T)
+    ue_c, ie_c = ue.clone().requires_grad_(True), ie.clone().requires_grad_(True)
+    want = losses_ref.bpr_lightgcn(ue_c.double(), ie_c.double(), torch.from_numpy(pu), torch.from_numpy(pi), torch.from_numpy(ni), 1e-3)
+    want.backward()
+    ue_g, ie_g = ue.to(cuda).requires_grad_(True), ie.to(cuda).requires_grad_(True)
+    got = bpr_step_loss(ue_g, ie_g, dev_t(pu, cuda), dev_t(pi, cuda), dev_t(ni, cuda), 1e-3)
+    np.testing.assert_allclose(got.item(), want.item(), rtol=1e-5)
+    got.backward()
+    np.testing.assert_allclose(ue_g.grad.cpu().numpy(), ue_c.grad.numpy(), rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(ie_g.grad.cpu().numpy(), ie_c.grad.numpy(), rtol=RTOL, atol=1e-7)
+
+
+def test_bpr_empty_batch(cuda):
+    ue = torch.randn(10, 64, device=cuda, requires_grad=True); ie = torch.randn(10, 64, device=cuda, requires_grad=True)
+    e = torch.zeros(0, dtype=torch.int64, device=cuda)
+    assert F_.bpr_loss_gather(ue, ie, e, e, e).item() == 0.0
+
+
+# ====================================================================== LightGCN model + step
+def _tiny_problem(seed=0, U=300, I=500, E=4000):
+    inter = synth.power_law_bipartite(U, I, E, seed=seed)
+    return inter, torch.from_numpy(inter.users), torch.from_numpy(inter.items)
+
+
+def test_lightgcn_forward_backward_vs_oracle(cuda):
+    inter, pu, pi = _tiny_problem()
+    U, I, d, K = inter.n_users, inter.n_items, 64, 3
+    torch.manual_seed(1)
+    model = LightGCN(U, I, d, K).to(cuda)
+    assert sorted(model.state_dict().keys()) == ["item_embedding.weight", "user_embedding.weight"]
+    uw = model.user_embedding.weight.detach().cpu().clone().requires_grad_(True)
+    iw = model.item_embedding.weight.detach().cpu().clone().requires_grad_(True)
+    ei = build_edge_index(pu, pi, U)
+    neg = torch.from_numpy(np.random.default_rng(0).integers(0, I, pu.numel()))
+    want = lightgcn_ref.lightgcn_step_loss(uw, iw, ei, pu, pi, neg, K, 1e-4)
+    want.backward()
+    ue, ie = model(ei.to(cuda))
+    ue_w, ie_w = lightgcn_ref.lightgcn_forward(uw.detach(), iw.detach(), ei, K)
+    np.testing.assert_allclose(ue.detach().cpu().numpy(), ue_w.numpy(), rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(ie.detach().cpu().numpy(), ie_w.numpy(), rtol=RTOL, atol=1e-6)
+    got = bpr_step_loss(ue, ie, pu.to(cuda), pi.to(cuda), neg.to(cuda), 1e-4)
+    np.testing.assert_allclose(got.item(), want.item(), rtol=1e-5)
+    got.backward()
+    np.testing.assert_allclose(model.user_embedding.weight.grad.cpu().numpy(), uw.grad.numpy(), rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(model.item_embedding.weight.grad.cpu().numpy(), iw.grad.numpy(), rtol=RTOL, atol=1e-7)
+
+
+def test_train_steps_track_reference_optimisation(cuda):
+    """Three full optimiser steps (forward, BPR+reg, backward, Adam) with identical pre-drawn negatives:
+    public-API path, fused-trainer path and the CPU restatement of lightgcn.py stay together."""
+    inter, pu, pi = _tiny_problem(seed=2)
+    U, I, d, K = inter.n_users, inter.n_items, 64, 3
+    torch.manual_seed(3)
+    model = LightGCN(U, I, d, K).to(cuda)
+    uw = model.user_embedding.weight.detach().cpu().clone().requires_grad_(True)
+    iw = model.item_embedding.weight.detach().cpu().clone().requires_grad_(True)
+    ref_opt = torch.optim.Adam([uw, iw], lr=0.01)
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    ei = build_edge_index(pu, pi, U)
+    ei_c = ei.to(cuda)
+    graph = model.graph_for(ei_c)
+    fused = FusedLightGCNTrainer(graph, U, I, model.table.detach().clone(), pu, pi, n_layers=K, lr=0.01, reg_weight=1e-4)
+    cfg = {"n_neg": 1, "reg_weight": 1e-4, "loss_type": "bpr"}
+    rng = np.random.default_rng(5)
+    for step in range(3):
+        neg = torch.from_numpy(rng.integers(0, I, pu.numel()))
+        ref_opt.zero_grad()
+        want = lightgcn_ref.lightgcn_step_loss(uw, iw, ei, pu, pi, neg, K, 1e-4)
+        want.backward(); ref_opt.step()
+        got = train_step(model, opt, ei_c, pu.to(cuda), pi.to(cuda), I, cfg, neg_i=neg.to(cuda))
+        got_f = fused.step(neg_i=neg.to(cuda))
+        np.testing.assert_allclose(got.item(), want.item(), rtol=1e-4)
+        np.testing.assert_allclose(got_f.item(), want.item(), rtol=1e-4)
+    np.testing.assert_allclose(model.user_embedding.weight.detach().cpu().numpy(), uw.detach().numpy(), rtol=RTOL, atol=2e-5)
+    np.testing.assert_allclose(model.item_embedding.weight.detach().cpu().numpy(), iw.detach().numpy(), rtol=RTOL, atol=2e-5)
+    np.testing.assert_allclose(fused.table[:U].cpu().numpy(), uw.detach().numpy(), rtol=RTOL, atol=2e-5)
+    np.testing.assert_allclose(fused.table[U:].cpu().numpy(), iw.detach().numpy(), rtol=RTOL, atol=2e-5)
+
+
+# ====================================================================== full-size properties (BASELINE cfg 1)
+def test_cfg1_size_properties(cuda):
+    """At the full Gowalla-shaped size the oracle is too slow for every check, so use size-independent properties:
+    structural identities of the CSR, linearity and symmetry of the operator, and a float64 spot check of rows."""
+    inter, d, K = synth.config_graph("cfg1")
+    U, I = inter.n_users, inter.n_items
+    csr = CSRGraph.from_pairs(dev_t(inter.users, cuda), dev_t(inter.items, cuda), U, I, norm="sym")
+    assert csr.nnz == 2 * inter.n_edges  # synthetic pairs are unique
+    rp = csr.row_ptr.cpu().numpy(); ci = csr.col_idx.cpu().numpy()
+    deg = np.concatenate([np.bincount(inter.users, minlength=U), np.bincount(inter.items, minlength=I)])
+    assert np.array_equal(np.diff(rp), deg)                      # degrees bit-exact
+    assert np.array_equal(csr.degrees().cpu().numpy(), deg.astype(np.float32))
+    row_of = np.repeat(np.arange(U + I), deg)
+    assert (np.diff(ci)[np.diff(row_of) == 0] > 0).all()          # strictly ascending columns inside every row
+    t = csr.transpose()
+    assert t is csr
+    x = torch.randn(U + I, d, device=cuda); y = torch.randn(U + I, d, device=cuda)
+    ax, ay, axy = (torch.empty_like(x) for _ in range(3))
+    F_.spmm_raw(csr, x, y=ax); F_.spmm_raw(csr, y, y=ay); F_.spmm_raw(csr, x + 2 * y, y=axy)
+    torch.testing.assert_close(axy, ax + 2 * ay, rtol=1e-4, atol=1e-5)                      # linearity
+    torch.testing.assert_close((y * ax).sum().double(), (x * ay).sum().double(), rtol=1e-4, atol=1e-3)  # <y,Ax> = <Ay,x>
+    rows = np.random.default_rng(0).integers(0, U + I, 200)
+    rows = np.concatenate([rows, np.argsort(-deg)[:5]])          # include the hub rows (long path)
+    v = csr.vals.cpu().numpy(); xc = x.cpu().numpy().astype(np.float64)
+    for r in rows:
+        want = (v[rp[r]:rp[r + 1], None].astype(np.float64) * xc[ci[rp[r]:rp[r + 1]]]).sum(0)
+        np.testing.assert_allclose(ax[r].cpu().numpy(), want, rtol=1e-4, atol=1e-5)

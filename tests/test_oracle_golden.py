@@ -1,0 +1,231 @@
+"""Pin the CPU oracle against outputs of the reference itself (tests/golden/*.npz, see make_golden.py) and against
+Random123's known-answer vectors.  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph_ref, losses_ref, lightgcn_ref, philox_ref
+
+ULP2 = 2.4e-7  # 2 ulp of fp32: numpy power(-0.5) vs 1/sqrt disagree by <= 1 ulp each
+
+
+def T(a, grad=False):
+    t = torch.from_numpy(np.asarray(a)).clone()
+    if grad:
+        t.requires_grad_(True)
+    return t
+
+
+# ---------------------------------------------------------------- graph build
+def test_sym_graph_matches_selfcf(golden):
+    g = golden("selfcf_graph")
+    U, I = int(g["n_users"]), int(g["n_items"])
+    ei = graph_ref.bipartite_edge_index(g["u_idx"], g["i_idx"], U)
+    rp, ci, mult = graph_ref.coo_to_canonical_csr(ei[0], ei[1], None, U + I, U + I)
+    assert np.array_equal(rp, g["ui_indptr"])
+    assert np.array_equal(ci, g["ui_indices"])
+    assert np.array_equal(mult, g["ui_data"])  # duplicates summed: exact small integers
+    assert mult.max() >= 2, "fixture must contain duplicate interactions"
+    vals, rowsum, dinv = graph_ref.normalize_csr(rp, ci, mult, U + I, U + I, "sym")
+    assert np.array_equal(rowsum, g["rowsum"])
+    assert np.array_equal(rp, g["norm_indptr"]) and np.array_equal(ci, g["norm_indices"])
+    np.testing.assert_allclose(vals, g["norm_data"], rtol=ULP2, atol=0)
+
+
+def test_sym_graph_matches_ssl4rec(golden):
+    g = golden("ssl4rec_losses")
+    U, I = int(g["n_users"]), int(g["n_items"])
+    ei = graph_ref.bipartite_edge_index(g["u_idx"], g["i_idx"], U)
+    rp, ci, mult = graph_ref.coo_to_canonical_csr(ei[0], ei[1], None, U + I, U + I)
+    vals, _, _ = graph_ref.normalize_csr(rp, ci, mult, U + I, U + I, "sym")
+    assert np.array_equal(rp, g["norm_indptr"]) and np.array_equal(ci, g["norm_indices"])
+    np.testing.assert_allclose(vals, g["norm_data"], rtol=ULP2, atol=0)
+
+
+def test_raw_graph_matches_ncl(golden):
+    g = golden("ncl_graph")
+    U, I = int(g["n_users"]), int(g["n_items"])
+    # reference: interleaved (u,i),(i,u) insertion order with duplicates kept (ncl.py:76-85)
+    ref = graph_ref.coo_to_canonical_csr(g["coo_row"], g["coo_col"], g["coo_data"], U + I, U + I)
+    ei = graph_ref.bipartite_edge_index(g["u_idx"], g["i_idx"], U)
+    ours = graph_ref.coo_to_canonical_csr(ei[0], ei[1], None, U + I, U + I)
+    for a, b in zip(ref, ours):
+        assert np.array_equal(a, b)
+    assert np.array_equal(graph_ref.degrees(ei[0], U + I), graph_ref.degrees(g["coo_row"], U + I))
+
+
+def test_gcn_norm_equals_sym_normalisation(golden):
+    g = golden("selfcf_graph")
+    U, I = int(g["n_users"]), int(g["n_items"])
+    ei = graph_ref.bipartite_edge_index(g["u_idx"], g["i_idx"], U)
+    w, deg = graph_ref.gcn_norm_weights(ei, U + I)
+    assert np.array_equal(deg.astype(np.float32), g["rowsum"])
+    rp, ci, vals = graph_ref.coo_to_canonical_csr(ei[1], ei[0], w, U + I, U + I)  # M[col,row] = w, duplicates summed
+    np.testing.assert_allclose(vals, g["norm_data"], rtol=4 * ULP2, atol=0)
+
+
+def test_transpose_roundtrip():
+    rng = np.random.default_rng(0)
+    r, c = rng.integers(0, 30, 200), rng.integers(0, 45, 200)
+    rp, ci, v = graph_ref.coo_to_canonical_csr(r, c, rng.random(200).astype(np.float32), 30, 45)
+    t = graph_ref.csr_transpose(rp, ci, v, 30, 45)
+    tt = graph_ref.csr_transpose(*t, 45, 30)
+    for a, b in zip((rp, ci, v), tt):
+        assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------- propagation
+def _sym_csr(g):
+    U, I = int(g["n_users"]), int(g["n_items"])
+    return g["norm_indptr"], g["norm_indices"], g["norm_data"], U, I
+
+
+def test_propagate_mean_matches_selfcf_encoder(golden):
+    g, e = golden("selfcf_graph"), golden("selfcf_encoder")
+    rp, ci, v, U, I = _sym_csr(g)
+    x0 = np.concatenate([e["user_w"], e["item_w"]])
+    K = int(e["n_layers"])
+    _, final = graph_ref.propagate(rp, ci, v, x0, K, "mean")
+    np.testing.assert_allclose(final[:U], e["user_all"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(final[U:], e["item_all"], rtol=1e-5, atol=1e-6)
+    # backward: A symmetric => dL/dE0 = mean_k A^k proj
+    proj = np.concatenate([e["proj_u"], e["proj_i"]])
+    _, gfinal = graph_ref.propagate(rp, ci, v, proj, K, "mean")
+    np.testing.assert_allclose(gfinal[:U], e["grad_user_w"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(gfinal[U:], e["grad_item_w"], rtol=1e-4, atol=1e-5)
+
+
+def test_propagate_raw_matches_ncl_encoder(golden):
+    g, e = golden("ncl_graph"), golden("ncl_encoder")
+    U, I = int(g["n_users"]), int(g["n_items"])
+    rp, ci, v = graph_ref.coo_to_canonical_csr(g["coo_row"], g["coo_col"], g["coo_data"], U + I, U + I)
+    x0 = np.concatenate([e["user_w"], e["item_w"]])
+    K = int(e["n_layers"])
+    layers, final = graph_ref.propagate(rp, ci, v, x0, K, "mean")
+    np.testing.assert_allclose(final[:U], e["user_out"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(final[U:], e["item_out"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(np.stack(layers), e["all_emb"], rtol=1e-5, atol=1e-5)
+
+
+def test_lgconv_matches_selfcf_fixture(golden):
+    """The restated PyG LGConv (lightgcn.py cannot be imported) equals the importable reference encoder on the same
+    graph: sum over layers == (K+1) * mean over layers."""
+    g, e = golden("selfcf_graph"), golden("selfcf_encoder")
+    U, I = int(g["n_users"]), int(g["n_items"])
+    K = int(e["n_layers"])
+    ei = torch.from_numpy(graph_ref.bipartite_edge_index(g["u_idx"], g["i_idx"], U))
+    uw, iw = T(e["user_w"], True), T(e["item_w"], True)
+    ue, ie = lightgcn_ref.lightgcn_forward(uw, iw, ei, K)
+    np.testing.assert_allclose(ue.detach().numpy() / (K + 1), e["user_all"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ie.detach().numpy() / (K + 1), e["item_all"], rtol=1e-5, atol=1e-6)
+    loss = ((ue * T(e["proj_u"])).sum() + (ie * T(e["proj_i"])).sum()) / (K + 1)
+    loss.backward()
+    np.testing.assert_allclose(uw.grad.numpy(), e["grad_user_w"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(iw.grad.numpy(), e["grad_item_w"], rtol=1e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------- losses
+def _check(loss, params, want_loss, want_grads, rtol=1e-5, atol=1e-6):
+    np.testing.assert_allclose(loss.detach().numpy(), want_loss, rtol=rtol, atol=atol)
+    grads = torch.autograd.grad(loss, params, allow_unused=True)
+    for g, w in zip(grads, want_grads):
+        g = np.zeros_like(w) if g is None else g.numpy()
+        np.testing.assert_allclose(g, w, rtol=rtol * 10, atol=atol)
+
+
+def test_ncl_losses(golden):
+    z = golden("ncl_losses")
+    ue, pe, ne = T(z["ue"], True), T(z["pe"], True), T(z["ne"], True)
+    _check(losses_ref.bpr_log_eps_sigmoid(ue, pe, ne), (ue, pe, ne), z["bpr"], (z["g_bpr_u"], z["g_bpr_p"], z["g_bpr_n"]))
+    _check(losses_ref.l2_reg(1e-3, ue, pe, ne), (ue, pe, ne), z["reg"], (z["g_reg_u"], z["g_reg_p"], z["g_reg_n"]))
+    v1, v2 = T(z["v1"], True), T(z["v2"], True)
+    _check(losses_ref.info_nce(v1, v2, 0.2), (v1, v2), z["nce"], (z["g_nce_1"], z["g_nce_2"]))
+    _check(losses_ref.info_nce(v1 * 0.3, v2 * 0.3, 0.5, cos=False), (v1, v2), z["nce_nocos"], (z["g_nce_nocos_1"], z["g_nce_nocos_2"]))
+    ctx, ini = T(z["ctx"], True), T(z["ini"], True)
+    nU = int(z["n_users"])
+    l = losses_ref.ssl_layer_loss(ctx, ini, T(z["bu"]), T(z["bp"]), nU, float(z["ssl_temp"]), float(z["ssl_reg"]), float(z["alpha"]))
+    _check(l, (ctx, ini), z["ssl"], (z["g_ssl_ctx"], z["g_ssl_ini"]), rtol=1e-4, atol=1e-9)
+    l = losses_ref.proto_nce(ini, T(z["bu"]), T(z["bp"]), nU, T(z["user_centroids"]), T(z["user_2cluster"]), T(z["item_centroids"]),
+                             T(z["item_2cluster"]), float(z["ssl_temp"]), float(z["proto_reg"]), int(z["batch_size"]))
+    _check(l, (ini,), z["proto"], (z["g_proto_ini"],), rtol=1e-4, atol=1e-9)
+
+
+def test_directau_losses(golden):
+    z = golden("directau_losses")
+    xu, xp, xn = T(z["xu"], True), T(z["xp"], True), T(z["xn"], True)
+    gamma = float(z["gamma"])
+    _check(losses_ref.alignment(xu, xp), (xu, xp), z["align"], (z["g_align_u"], z["g_align_p"]))
+    _check(losses_ref.uniformity(xu), (xu,), z["unif"], (z["g_unif"],), rtol=1e-4)
+    _check(losses_ref.directau_loss(xu, xp, gamma), (xu, xp), z["calc"], (z["g_calc_u"], z["g_calc_p"]), rtol=1e-4)
+    train = (losses_ref.directau_loss(xu, xp, gamma) - losses_ref.directau_loss(xu, xn, gamma)
+             + losses_ref.l2_reg(float(z["reg"]), xu, xp, xn) / int(z["batch_size"]))
+    _check(train, (xu, xp, xn), z["train"], (z["g_train_u"], z["g_train_p"], z["g_train_n"]), rtol=1e-4)
+
+
+def test_ssl4rec_and_gcl_losses(golden):
+    z = golden("ssl4rec_losses")
+    a, b = T(z["a"], True), T(z["b"], True)
+    _check(losses_ref.batch_softmax(a, b, 0.2), (a, b), z["batch_softmax"], (z["g_bs_a"], z["g_bs_b"]))
+    _check(losses_ref.info_nce(a, b, 0.15), (a, b), z["nce"], (z["g_nce_a"], z["g_nce_b"]))
+    z = golden("gcl_losses")
+    z1, z2 = T(z["z1"], True), T(z["z2"], True)
+    _check(losses_ref.info_nce_symmetric(z1, z2, 0.2), (z1, z2), z["info_nce"], (z["g_z1"], z["g_z2"]))
+    ue, pe, ne = T(z["ue"], True), T(z["pe"], True), T(z["ne"], True)
+    _check(losses_ref.bpr_gcl(ue, pe, ne, float(z["reg_weight"])), (ue, pe, ne), z["bpr_reg"], (z["g_u"], z["g_p"], z["g_n"]))
+
+
+def test_selfcf_he(golden):
+    z = golden("selfcf_he")
+    g = golden("selfcf_graph")
+    rp, ci, v, U, I = _sym_csr(g)
+    uw, iw = T(z["user_w"], True), T(z["item_w"], True)
+    W, bias = T(z["pred_w"], True), T(z["pred_b"], True)
+    m = float(z["momentum"])
+    K = int(z["n_layers"])
+    # encoder through autograd: dense A (tiny graph)
+    A = torch.zeros(U + I, U + I)
+    row_of = np.repeat(np.arange(U + I), np.diff(rp))
+    A[torch.from_numpy(row_of), torch.from_numpy(ci.astype(np.int64))] = torch.from_numpy(v)
+    x = torch.cat([uw, iw]); layers = [x]
+    for _ in range(K):
+        layers.append(A @ layers[-1])
+    final = torch.stack(layers).mean(0)
+    uo, io = final[:U], final[U:]
+    users, items = T(z["users"]), T(z["items"])
+    t_u = T(z["his_u0"])[users] * m + uo[users].detach() * (1 - m)
+    t_i = T(z["his_i0"])[items] * m + io[items].detach() * (1 - m)
+    p_u, p_i = uo[users] @ W.T + bias, io[items] @ W.T + bias
+    for got, want in ((p_u, z["p_u"]), (t_u, z["t_u"]), (p_i, z["p_i"]), (t_i, z["t_i"])):
+        np.testing.assert_allclose(got.detach().numpy(), want, rtol=1e-5, atol=1e-6)
+    loss = losses_ref.selfcf_loss(p_u, t_u, p_i, t_i)
+    _check(loss, (uw, iw, W, bias), z["loss"], (z["g_user_w"], z["g_item_w"], z["g_pred_w"], z["g_pred_b"]), rtol=1e-4)
+    his_u1 = T(z["his_u0"]).clone(); his_u1[users] = uo[users].detach()
+    np.testing.assert_allclose(his_u1.numpy(), z["his_u1"], rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------- Philox
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    def run(c, k):
+        return [int(x) for x in philox_ref.philox4x32_10([np.uint32(v) for v in c], [np.uint32(v) for v in k])]
+    assert run([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert run([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert run([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == \
+        [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_sampler_oracle_properties():
+    n, n_items = 4000, 97
+    a = philox_ref.sample_negatives(5, 0, n, 1, n_items)
+    b = philox_ref.sample_negatives(5, 1, n, 1, n_items)
+    assert a.min() >= 0 and a.max() < n_items and not np.array_equal(a, b)
+    counts = np.bincount(a, minlength=n_items)
+    assert counts.min() > 0.4 * n / n_items and counts.max() < 1.8 * n / n_items  # roughly uniform
+    # rejection: every user rates all even items -> only odd items may come out
+    users = np.arange(n) % 10
+    pos_rp = np.arange(0, 11 * 49, 49)[:11].astype(np.int32)
+    pos_ci = np.tile(np.arange(0, 97, 2)[:49], 10).astype(np.int32)
+    c = philox_ref.sample_negatives(5, 0, n, 1, n_items, users, pos_rp, pos_ci, max_trials=64)
+    assert (c % 2 == 1).all()
+    unchanged = a % 2 == 1
+    assert np.array_equal(c[unchanged], a[unchanged])  # accepted first candidates are untouched
