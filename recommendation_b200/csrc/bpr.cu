@@ -27,11 +27,19 @@ __device__ __forceinline__ void load_row(const float* __restrict__ base, long lo
   }
 }
 
+// Reduce two per-lane partials (a, b) over a sub-warp of LPR lanes with log2(LPR) shuffles instead of
+// 2*log2(LPR): the first butterfly step trades one value for the other, so afterwards the lower half of
+// the sub-warp reduces `a` and the upper half reduces `b`.  Returns the lane's total (a for sl < LPR/2,
+// b otherwise).
 template <int LPR>
-__device__ __forceinline__ float group_sum(float v, unsigned mask) {
+__device__ __forceinline__ float pair_reduce(float a, float b, int sl, unsigned mask) {
+  const bool hi = (sl & (LPR / 2)) != 0;
+  float keep = hi ? b : a;
+  const float send = hi ? a : b;
+  keep += __shfl_xor_sync(mask, send, LPR / 2);
 #pragma unroll
-  for (int off = LPR / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off);
-  return v;
+  for (int off = LPR / 4; off > 0; off >>= 1) keep += __shfl_xor_sync(mask, keep, off);
+  return keep;
 }
 
 __device__ __forceinline__ void bpr_pointwise(int variant, float eps, float x, float& loss, float& dl) {
@@ -46,7 +54,9 @@ __device__ __forceinline__ void bpr_pointwise(int variant, float eps, float x, f
   }
 }
 
-template <int LPR, int VPL, bool GUARD>
+// BATCH triples are fetched together: all index loads first, then all 3*BATCH row gathers, then the math --
+// the dependent idx -> row chains of the batch overlap instead of running back to back.
+template <int LPR, int VPL, bool GUARD, int BATCH>
 __global__ void __launch_bounds__(kBprThreads)
 bpr_fwd_kernel(const float* __restrict__ uemb, long long ldu, const float* __restrict__ iemb, long long ldi, int dvec,
                const int64_t* __restrict__ u_idx, const int64_t* __restrict__ p_idx, const int64_t* __restrict__ n_idx,
@@ -59,51 +69,64 @@ bpr_fwd_kernel(const float* __restrict__ uemb, long long ldu, const float* __res
   const long long group = ((long long)blockIdx.x * (kBprThreads / 32) + (threadIdx.x >> 5)) * RPW + sub;
   const long long t0 = group * kRun;
   const float inv_negs = 1.f / (float)n_negs;
+  const bool x_lane = sl == 0, r_lane = sl == LPR / 2;  // pair_reduce leaves x in the low half, the reg term in the high half
 
   double local = 0.0;
-  long long cur_u = -1;
-  float4 ur[VPL];
-  float su = 0.f;
   if (t0 < n) {
     const long long t1 = min(t0 + (long long)kRun, n);
-#pragma unroll 2
-    for (long long t = t0; t < t1; ++t) {
-      const long long u = ld_stream_i64(u_idx + t);
-      const long long p = ld_stream_i64(p_idx + t);
-      float4 pr[VPL];
-      load_row<LPR, VPL, GUARD>(iemb, ldi, p, sl, dvec, pr);
-      if (u != cur_u) {
-        load_row<LPR, VPL, GUARD>(uemb, ldu, u, sl, dvec, ur);
-        cur_u = u;
-        su = 0.f;
+    for (long long tb = t0; tb < t1; tb += BATCH) {
+      long long u[BATCH], p[BATCH], q[BATCH];
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) su += f4_dot(ur[k], ur[k]);
-        su = group_sum<LPR>(su, mask);
+      for (int b = 0; b < BATCH; ++b) {
+        const long long t = min(tb + b, t1 - 1);  // ragged tail: replay the last triple, result discarded
+        u[b] = ld_stream_i64(u_idx + t);
+        p[b] = ld_stream_i64(p_idx + t);
+        q[b] = ld_stream_i64(n_idx + t * n_negs);
       }
-      float dp = 0.f, sp = 0.f, dn = 0.f, sn = 0.f;
+      float4 ur[BATCH][VPL], pr[BATCH][VPL], nr[BATCH][VPL];
 #pragma unroll
-      for (int k = 0; k < VPL; ++k) { dp += f4_dot(ur[k], pr[k]); sp += f4_dot(pr[k], pr[k]); }
-      for (int j = 0; j < n_negs; ++j) {
-        const long long q = ld_stream_i64(n_idx + t * n_negs + j);
-        float4 nr[VPL];
-        load_row<LPR, VPL, GUARD>(iemb, ldi, q, sl, dvec, nr);
-#pragma unroll
-        for (int k = 0; k < VPL; ++k) { dn += f4_dot(ur[k], nr[k]); sn += f4_dot(nr[k], nr[k]); }
+      for (int b = 0; b < BATCH; ++b) {
+        load_row<LPR, VPL, GUARD>(uemb, ldu, u[b], sl, dvec, ur[b]);
+        load_row<LPR, VPL, GUARD>(iemb, ldi, p[b], sl, dvec, pr[b]);
+        load_row<LPR, VPL, GUARD>(iemb, ldi, q[b], sl, dvec, nr[b]);
       }
-      dp = group_sum<LPR>(dp, mask);
-      dn = group_sum<LPR>(dn, mask);
-      sp = group_sum<LPR>(sp, mask);
-      sn = group_sum<LPR>(sn, mask);
-      const float x = dp - dn * inv_negs;
-      float loss, dl;
-      bpr_pointwise(variant, eps, x, loss, dl);
-      if (sl == 0) {
-        coef_out[t] = dl * w_loss;
-        local += (double)(loss * w_loss) + (double)(reg_u * su) + (double)(reg_p * sp) + (double)(reg_n * sn);
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b) {
+        const long long t = tb + b;
+        float xs = 0.f, dn = 0.f, rs = 0.f, sn = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          xs += f4_dot(ur[b][k], pr[b][k]);
+          dn += f4_dot(ur[b][k], nr[b][k]);
+          rs += reg_u * f4_dot(ur[b][k], ur[b][k]) + reg_p * f4_dot(pr[b][k], pr[b][k]);
+          sn += f4_dot(nr[b][k], nr[b][k]);
+        }
+        if (n_negs > 1 && t < t1) {  // rare path (lightgcn.py n_neg in {3,5}): remaining negatives one by one
+          for (int j = 1; j < n_negs; ++j) {
+            const long long qj = ld_stream_i64(n_idx + t * n_negs + j);
+            float4 nj[VPL];
+            load_row<LPR, VPL, GUARD>(iemb, ldi, qj, sl, dvec, nj);
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) { dn += f4_dot(ur[b][k], nj[k]); sn += f4_dot(nj[k], nj[k]); }
+          }
+        }
+        xs -= dn * inv_negs;
+        rs += reg_n * sn;
+        const float tot = pair_reduce<LPR>(xs, rs, sl, mask);
+        if (t < t1) {
+          if (x_lane) {
+            float loss, dl;
+            bpr_pointwise(variant, eps, tot, loss, dl);
+            coef_out[t] = dl * w_loss;
+            local += (double)(loss * w_loss);
+          } else if (r_lane) {
+            local += (double)tot;
+          }
+        }
       }
     }
   }
-  // block reduction of the double partials (only sub-warp leaders hold non-zero values)
+  // block reduction of the double partials
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
   __shared__ double warp_part[kBprThreads / 32];
@@ -148,7 +171,7 @@ __device__ __forceinline__ void red_row(float* __restrict__ base, long long ld, 
   }
 }
 
-template <int LPR, int VPL, bool GUARD>
+template <int LPR, int VPL, bool GUARD, int BATCH>
 __global__ void __launch_bounds__(kBprThreads)
 bpr_bwd_kernel(const float* __restrict__ uemb, long long ldu, const float* __restrict__ iemb, long long ldi, int dvec,
                const int64_t* __restrict__ u_idx, const int64_t* __restrict__ p_idx, const int64_t* __restrict__ n_idx,
@@ -167,46 +190,65 @@ bpr_bwd_kernel(const float* __restrict__ uemb, long long ldu, const float* __res
   const float ru2 = 2.f * reg_u * g, rp2 = 2.f * reg_p * g, rn2 = 2.f * reg_n * g;
 
   long long cur_u = -1;
-  float4 ur[VPL], gu[VPL];
+  float4 gu[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) gu[k] = f4_zero();
 
-#pragma unroll 2
-  for (long long t = t0; t < t1; ++t) {
-    const long long u = ld_stream_i64(u_idx + t);
-    const long long p = ld_stream_i64(p_idx + t);
-    const float c = ld_stream_f32(coef + t) * g;
-    float4 pr[VPL];
-    load_row<LPR, VPL, GUARD>(iemb, ldi, p, sl, dvec, pr);
-    if (u != cur_u) {
-      if (cur_u >= 0) red_row<LPR, VPL, GUARD>(g_user, ldgu, cur_u, sl, dvec, gu);
-      load_row<LPR, VPL, GUARD>(uemb, ldu, u, sl, dvec, ur);
-      cur_u = u;
+  for (long long tb = t0; tb < t1; tb += BATCH) {
+    long long u[BATCH], p[BATCH], q[BATCH];
+    float c[BATCH];
 #pragma unroll
-      for (int k = 0; k < VPL; ++k) gu[k] = f4_zero();
+    for (int b = 0; b < BATCH; ++b) {
+      const long long t = min(tb + b, t1 - 1);
+      u[b] = ld_stream_i64(u_idx + t);
+      p[b] = ld_stream_i64(p_idx + t);
+      q[b] = ld_stream_i64(n_idx + t * n_negs);
+      c[b] = ld_stream_f32(coef + t) * g;
     }
-    // d/du: c * (p - mean_j n_j) + 2 reg_u u ;  d/dp: c * u + 2 reg_p p ;  d/dn_j: -c/n_negs * u + 2 reg_n n_j
-    float4 gp[VPL];
+    float4 ur[BATCH][VPL], pr[BATCH][VPL], nr[BATCH][VPL];
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      gp[k] = make_float4(rp2 * pr[k].x, rp2 * pr[k].y, rp2 * pr[k].z, rp2 * pr[k].w);
-      f4_fma(gp[k], c, ur[k]);
-      f4_fma(gu[k], c, pr[k]);
-      f4_fma(gu[k], ru2, ur[k]);
+    for (int b = 0; b < BATCH; ++b) {
+      load_row<LPR, VPL, GUARD>(uemb, ldu, u[b], sl, dvec, ur[b]);
+      load_row<LPR, VPL, GUARD>(iemb, ldi, p[b], sl, dvec, pr[b]);
+      load_row<LPR, VPL, GUARD>(iemb, ldi, q[b], sl, dvec, nr[b]);
     }
-    red_row<LPR, VPL, GUARD>(g_item, ldgi, p, sl, dvec, gp);
-    const float cn = -c * inv_negs;
-    for (int j = 0; j < n_negs; ++j) {
-      const long long q = ld_stream_i64(n_idx + t * n_negs + j);
-      float4 nr[VPL], gn[VPL];
-      load_row<LPR, VPL, GUARD>(iemb, ldi, q, sl, dvec, nr);
+#pragma unroll
+    for (int b = 0; b < BATCH; ++b) {
+      const long long t = tb + b;
+      if (t >= t1) break;
+      if (u[b] != cur_u) {  // user changed: flush the register-accumulated user gradient
+        if (cur_u >= 0) red_row<LPR, VPL, GUARD>(g_user, ldgu, cur_u, sl, dvec, gu);
+        cur_u = u[b];
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) gu[k] = f4_zero();
+      }
+      // d/du: c * (p - mean_j n_j) + 2 reg_u u ;  d/dp: c * u + 2 reg_p p ;  d/dn_j: -c/n_negs * u + 2 reg_n n_j
+      const float cn = -c[b] * inv_negs;
+      float4 gp[VPL], gn[VPL];
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
-        gn[k] = make_float4(rn2 * nr[k].x, rn2 * nr[k].y, rn2 * nr[k].z, rn2 * nr[k].w);
-        f4_fma(gn[k], cn, ur[k]);
-        f4_fma(gu[k], cn, nr[k]);
+        gp[k] = make_float4(rp2 * pr[b][k].x, rp2 * pr[b][k].y, rp2 * pr[b][k].z, rp2 * pr[b][k].w);
+        f4_fma(gp[k], c[b], ur[b][k]);
+        gn[k] = make_float4(rn2 * nr[b][k].x, rn2 * nr[b][k].y, rn2 * nr[b][k].z, rn2 * nr[b][k].w);
+        f4_fma(gn[k], cn, ur[b][k]);
+        f4_fma(gu[k], c[b], pr[b][k]);
+        f4_fma(gu[k], cn, nr[b][k]);
+        f4_fma(gu[k], ru2, ur[b][k]);
       }
-      red_row<LPR, VPL, GUARD>(g_item, ldgi, q, sl, dvec, gn);
+      red_row<LPR, VPL, GUARD>(g_item, ldgi, p[b], sl, dvec, gp);
+      red_row<LPR, VPL, GUARD>(g_item, ldgi, q[b], sl, dvec, gn);
+      for (int j = 1; j < n_negs; ++j) {  // rare path: remaining negatives
+        const long long qj = ld_stream_i64(n_idx + t * n_negs + j);
+        float4 nj[VPL], gj[VPL];
+        load_row<LPR, VPL, GUARD>(iemb, ldi, qj, sl, dvec, nj);
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          gj[k] = make_float4(rn2 * nj[k].x, rn2 * nj[k].y, rn2 * nj[k].z, rn2 * nj[k].w);
+          f4_fma(gj[k], cn, ur[b][k]);
+          f4_fma(gu[k], cn, nj[k]);
+        }
+        red_row<LPR, VPL, GUARD>(g_item, ldgi, qj, sl, dvec, gj);
+      }
     }
   }
   if (cur_u >= 0) red_row<LPR, VPL, GUARD>(g_user, ldgu, cur_u, sl, dvec, gu);
@@ -241,16 +283,16 @@ extern "C" size_t gcf_bpr_workspace_bytes(int64_t n_triples) {
 #define GCF_BPR_DISPATCH(KERNEL, ...)                                                            \
   do {                                                                                           \
     switch (d) {                                                                                 \
-      case 16:  KERNEL<4, 1, false><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;           \
-      case 32:  KERNEL<8, 1, false><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;           \
-      case 64:  KERNEL<16, 1, false><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;          \
-      case 128: KERNEL<32, 1, false><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;          \
-      case 256: KERNEL<32, 2, false><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;          \
+      case 16:  KERNEL<4, 1, false, 4><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;        \
+      case 32:  KERNEL<8, 1, false, 4><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;        \
+      case 64:  KERNEL<16, 1, false, 4><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;       \
+      case 128: KERNEL<32, 1, false, 4><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;       \
+      case 256: KERNEL<32, 2, false, 2><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;       \
       default:                                                                                   \
-        if (d <= 128)      KERNEL<32, 1, true><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__);       \
-        else if (d <= 256) KERNEL<32, 2, true><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__);       \
-        else if (d <= 512) KERNEL<32, 4, true><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__);       \
-        else               KERNEL<32, 8, true><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__);       \
+        if (d <= 128)      KERNEL<32, 1, true, 4><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__);    \
+        else if (d <= 256) KERNEL<32, 2, true, 2><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__);    \
+        else if (d <= 512) KERNEL<32, 4, true, 1><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__);    \
+        else               KERNEL<32, 8, true, 1><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__);    \
     }                                                                                            \
   } while (0)
 

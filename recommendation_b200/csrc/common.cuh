@@ -55,19 +55,21 @@ struct Arena {
 // ---- device helpers --------------------------------------------------------------------
 namespace gcf {
 
+// Streaming loads of read-only index / value arrays: bypass L1 allocation, NOT volatile so that the
+// compiler may hoist them and overlap the dependent row gathers of consecutive iterations.
 __device__ __forceinline__ int ld_stream_i32(const int32_t* p) {
   int v;
-  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ float ld_stream_f32(const float* p) {
   float v;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ long long ld_stream_i64(const int64_t* p) {
   long long v;
-  asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
   return v;
 }
 // 128-bit vector reduction (sm_90+): one L2 atomic transaction per 16 bytes.

@@ -266,7 +266,7 @@ extern "C" int gcf_norm_values(int32_t mode, const int32_t* row_ptr, const int32
   GCF_REQUIRE(mode >= 0 && mode <= 2, "gcf_norm_values: mode must be 0 (none), 1 (sym) or 2 (row)");
   GCF_REQUIRE(mode != 1 || n_rows == n_cols, "gcf_norm_values: sym normalisation needs a square matrix");
   if (n_rows == 0) return GCF_OK;
-  GCF_REQUIRE(row_ptr && col_idx && vals_in && vals_out && dinv_out, "gcf_norm_values: null pointers");
+  GCF_REQUIRE(row_ptr && dinv_out, "gcf_norm_values: null row_ptr / dinv_out");  // col/val may be null when nnz == 0
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long blocks = cdiv(n_rows * 32, 256);
   GCF_REQUIRE(blocks < 2147483647LL, "gcf_norm_values: too many rows");

@@ -323,13 +323,13 @@ extern "C" int gcf_spmm_csr_f32(const gcf_csr_t* A, int32_t d, const float* X, i
     case 64:  // variants are tuning knobs (UNR loads in flight x resident blocks), same arithmetic
       if (variant == 1) return launch<16, 1, 4, false, 4>(A, X, ldx, dvec, ep, lp, st);
       if (variant == 2) return launch<16, 1, 16, false, 2>(A, X, ldx, dvec, ep, lp, st);
-      if (variant == 3) return launch<16, 1, 8, false, 4>(A, X, ldx, dvec, ep, lp, st);
-      return launch<16, 1, 8, false, 3>(A, X, ldx, dvec, ep, lp, st);
+      if (variant == 3) return launch<16, 1, 8, false, 3>(A, X, ldx, dvec, ep, lp, st);
+      return launch<16, 1, 8, false, 4>(A, X, ldx, dvec, ep, lp, st);  // measured best on cfg1 and cfg5
     case 128:
       if (variant == 1) return launch<32, 1, 4, false, 4>(A, X, ldx, dvec, ep, lp, st);
       if (variant == 2) return launch<32, 1, 16, false, 2>(A, X, ldx, dvec, ep, lp, st);
-      if (variant == 3) return launch<32, 1, 8, false, 4>(A, X, ldx, dvec, ep, lp, st);
-      return launch<32, 1, 8, false, 3>(A, X, ldx, dvec, ep, lp, st);
+      if (variant == 3) return launch<32, 1, 8, false, 3>(A, X, ldx, dvec, ep, lp, st);
+      return launch<32, 1, 8, false, 4>(A, X, ldx, dvec, ep, lp, st);
     case 256: return launch<32, 2, 4, false, 2>(A, X, ldx, dvec, ep, lp, st);
     default: break;
   }

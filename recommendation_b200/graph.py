@@ -135,8 +135,10 @@ class CSRGraph:
                                              _lib.ptr(ws), ws_bytes, stream), "gcf_coo_to_csr_stable")
         nnz = int(nnz_out.item())
         del ws
-        col_idx = col_idx[:nnz].clone() if nnz < col_idx.numel() else col_idx
-        out_vals = out_vals[:nnz].clone() if nnz < out_vals.numel() else out_vals
+        if 0 < nnz < col_idx.numel():  # duplicates were merged: release the slack
+            col_idx, out_vals = col_idx[:nnz].clone(), out_vals[:nnz].clone()
+        elif nnz == 0:                 # keep a non-null base pointer for empty operators
+            col_idx, out_vals = col_idx[:0], out_vals[:0]
         rowsum = torch.empty(n_rows, dtype=torch.float32, device=dev)
         dinv = torch.empty(n_rows, dtype=torch.float32, device=dev)
         normed = torch.empty_like(out_vals)

@@ -191,14 +191,21 @@ class FusedLightGCNTrainer:
         self.bpr_ws = torch.empty(self.bpr_ws_bytes, dtype=torch.uint8, device=dev)
         self.ws, self.ws_bytes = graph.workspace(self.d)
         self.step_count = 0
-        self.launches_per_step = 2 * n_layers + 6  # K fwd + K bwd SpMM, sampler, bpr fwd (2), memset, bpr bwd, adam
+        self.launches_per_step = 2 * n_layers + 5  # libgcf kernels only: K fwd + K bwd SpMM, sampler, bpr fwd + reduce, bpr bwd, adam
 
-    def step(self, neg_i: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def step(self, neg_i: Optional[torch.Tensor] = None, marks: Optional[list] = None) -> torch.Tensor:
+        """One optimisation step.  `marks` (optional list) receives (start_event, end_event, n_spmm_launches)
+        tuples bracketing the SpMM launches, so a caller can time the dominant kernel inside the step."""
         lib, st = self.lib, _lib.current_stream()
         g, d, u = self.graph, self.d, self.n_users
         self.step_count += 1
+        if marks is not None:
+            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            e0.record()
         _lib.check(lib.gcf_propagate_fwd(g.struct_ref(), d, self.k, _lib.ptr(self.table), _lib.ptr_array(self.layers),
                                          _lib.ptr(self.final), 1.0, _lib.ptr(self.ws), self.ws_bytes, st), "gcf_propagate_fwd")
+        if marks is not None:
+            e1.record()
         if neg_i is None:
             _lib.check(lib.gcf_sample_negatives(self.seed, self.step_count, None, self.n_triples, self.n_neg, self.n_items,
                                                 None, None, 1, _lib.ptr(self.neg), st), "gcf_sample_negatives")
@@ -215,9 +222,15 @@ class FusedLightGCNTrainer:
                                    _lib.ptr(neg), self.n_triples, self.n_neg, _lib.ptr(self.coef), None, self.reg, self.reg, 0.0,
                                    _lib.ptr(self.g_final[:u]), d, _lib.ptr(self.g_final[u:]), d, st), "gcf_bpr_bwd")
         gt = g.transpose()
+        if marks is not None:
+            e2.record()
         _lib.check(lib.gcf_propagate_bwd(gt.struct_ref(), d, self.k, _lib.ptr(self.g_final), None, 1.0, _lib.ptr(self.ping),
                                          _lib.ptr(self.pong), _lib.ptr(self.g_x0), _lib.ptr(self.ws), self.ws_bytes, st),
                    "gcf_propagate_bwd")
+        if marks is not None:
+            e3.record()
+            marks.append((e0, e1, self.k))
+            marks.append((e2, e3, self.k))
         _lib.check(lib.gcf_adam_step(_lib.ptr(self.table), _lib.ptr(self.g_x0), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
                                      self.table.numel(), self.lr, 0.9, 0.999, 1e-8, self.wd, 0, self.step_count, st),
                    "gcf_adam_step")
