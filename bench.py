@@ -55,7 +55,9 @@ def spmm_algorithmic_bytes(n_rows, n_cols, nnz, d):
 
 # ------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi sampled every 100 ms in a side process; samples are selected by wall-clock window."""
+
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -74,7 +76,10 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin: float, t_end: float):
+        """Summarise the samples taken in the wall-clock window [t_begin, t_end] (time.time() values)."""
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -83,28 +88,29 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        clocks, powers, reasons, mx = [], [], set(), None
+        clocks, reasons, mx = [], set(), None
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
             for line in Path(self.path).read_text().splitlines():
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
+                if len(f) < 10:
                     continue
                 try:
-                    clocks.append(float(f[1])); mx = float(f[2]); powers.append(float(f[3]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    clk = float(f[2]); mx_here = float(f[3])
                 except ValueError:
                     continue
-                for nm, val in zip(names, f[5:9]):
+                if ts < t_begin - 0.05 or ts > t_end + 0.05:
+                    continue
+                clocks.append(clk); mx = mx_here
+                for nm, val in zip(names, f[6:10]):
                     if val.lower().startswith("active"):
                         reasons.add(nm)
             os.unlink(self.path)
         except Exception:
             pass
         if clocks:
-            # "under load": samples whose power is in the upper half of the observed range
-            thr = (max(powers) + min(powers)) / 2 if powers else 0
-            loaded = [c for c, p in zip(clocks, powers) if p >= thr] or clocks
-            out = {"sm_mhz": statistics.median(loaded), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(clocks)}
+            out = {"sm_mhz": statistics.median(clocks), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(clocks)}
         return out
 
 
@@ -238,10 +244,11 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+        time.sleep(0.5)  # let nvidia-smi come up before the timed region
     step_ms, spmm_us = [], []
     ev = lambda: torch.cuda.Event(enable_timing=True)
     barrier()
-    wall0 = time.perf_counter()
+    wall0 = time.perf_counter(); clk_t0 = time.time()
     for _ in range(args.steps):
         if flush is not None:
             flush.zero_()
@@ -255,8 +262,23 @@ def run_ours(args):
         for (a, b, launches) in marks:  # (start event, end event, number of SpMM launches in between)
             spmm_us.append(a.elapsed_time(b) * 1e3 / launches)
     barrier()
-    wall = time.perf_counter() - wall0
-    clk = clocks.stop() if rank == 0 else None
+    wall = time.perf_counter() - wall0; clk_t1 = time.time()
+    clk_note = "sampled during the timed region"
+    if wall < 1.0:
+        # the timed region is shorter than a few sampler periods: keep the identical step loop running (untimed)
+        # for ~1 s right after it and sample the clocks over that window instead
+        t_end = time.perf_counter() + 1.0
+        while time.perf_counter() < t_end:
+            for _ in range(10):
+                if flush is not None:
+                    flush.zero_()
+                trainer.step()
+            torch.cuda.synchronize()
+        clk_t1 = time.time()
+        clk_note = f"timed region {wall * 1e3:.1f} ms is shorter than the sampler period; sampled over it plus 1 s of the identical step loop run right after"
+    clk = clocks.stop(clk_t0, clk_t1) if rank == 0 else None
+    if clk is not None:
+        clk["note"] = clk_note
 
     total_ms = sum(step_ms)
     if world > 1:
