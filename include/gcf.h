@@ -77,6 +77,12 @@ int gcf_norm_values(int32_t mode, const int32_t* row_ptr, const int32_t* col_idx
                     int64_t n_rows, int64_t n_cols, float* vals_out, float* rowsum_out, float* dinv_out,
                     gcf_stream_t stream);
 
+/* vals_out[j] = (row_scale[r] * vals_in[j]) * col_scale[col_idx[j]]  -- the same two-multiply order as mode 1 above,
+ * with the scaling vectors supplied by the caller.  Used for the row blocks of a row-sharded adjacency, where
+ * dinv of remote column nodes comes from the global degree vector.  Either vector may be NULL (= 1). */
+int gcf_scale_csr_values(const int32_t* row_ptr, const int32_t* col_idx, const float* vals_in, int64_t n_rows,
+                         const float* row_scale, const float* col_scale, float* vals_out, gcf_stream_t stream);
+
 /* CSR -> CSR of the transpose (stable: rows ascending inside each output row).
  * Needed for the backward of non-symmetric operators (mhcn.py:440-456 R / R^T,
  * diffnet.py:1127,1131 S and A).  nnz is the exact entry count. */

@@ -46,6 +46,7 @@ _SIGNATURES = {
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gcf_norm_values": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gcf_scale_csr_values": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gcf_csr_transpose_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "gcf_csr_transpose": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

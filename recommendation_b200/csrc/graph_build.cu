@@ -124,6 +124,22 @@ scale_values_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col
 }
 
 __global__ void __launch_bounds__(256)
+scale_given_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx, const float* __restrict__ vals_in,
+                   long long n_rows, const float* __restrict__ row_scale, const float* __restrict__ col_scale,
+                   float* __restrict__ vals_out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_rows) return;
+  const int s = row_ptr[row], e = row_ptr[row + 1];
+  const float dr = row_scale != nullptr ? row_scale[row] : 1.f;
+  for (int j = s + lane; j < e; j += 32) {
+    float v = dr * vals_in[j];
+    if (col_scale != nullptr) v = v * col_scale[col_idx[j]];
+    vals_out[j] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
 col_hist_kernel(const int* __restrict__ col_idx, long long nnz, int* __restrict__ cnt, uint32_t* __restrict__ keys) {
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += (long long)gridDim.x * blockDim.x) {
     const int c = col_idx[j];
@@ -274,6 +290,20 @@ extern "C" int gcf_norm_values(int32_t mode, const int32_t* row_ptr, const int32
   GCF_LAUNCH_CHECK("rowsum_kernel");
   scale_values_kernel<<<(unsigned)blocks, 256, 0, st>>>(row_ptr, col_idx, vals_in, n_rows, mode, dinv_out, vals_out);
   GCF_LAUNCH_CHECK("scale_values_kernel");
+  return GCF_OK;
+}
+
+extern "C" int gcf_scale_csr_values(const int32_t* row_ptr, const int32_t* col_idx, const float* vals_in, int64_t n_rows,
+                                    const float* row_scale, const float* col_scale, float* vals_out,
+                                    gcf_stream_t stream) {
+  GCF_REQUIRE(n_rows >= 0, "gcf_scale_csr_values: negative n_rows");
+  if (n_rows == 0) return GCF_OK;
+  GCF_REQUIRE(row_ptr != nullptr, "gcf_scale_csr_values: null row_ptr");
+  const long long blocks = cdiv(n_rows * 32, 256);
+  GCF_REQUIRE(blocks < 2147483647LL, "gcf_scale_csr_values: too many rows");
+  scale_given_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(row_ptr, col_idx, vals_in, n_rows,
+                                                                                    row_scale, col_scale, vals_out);
+  GCF_LAUNCH_CHECK("scale_given_kernel");
   return GCF_OK;
 }
 

@@ -1,0 +1,282 @@
+"""Row-sharded LightGCN training over G GPUs of one NVSwitch box (north star "2/4/8-GPU runs").
+
+One process per GPU (torch.distributed, NCCL).  The reference has no distributed code at all; this is the
+scaling path of the same step as lightgcn.FusedLightGCNTrainer:
+
+  * node v (user u -> v = u, item i -> v = U + i) is owned by rank v % G at local row v // G (cyclic: the
+    power-law hubs, which have the lowest ids in the synthetic graphs and arbitrary ids in real data, spread
+    evenly).  Rank r keeps rows {v : v % G == r} of the embedding table, of the Adam state and of the
+    normalised adjacency; column ids of its CSR block are "gathered positions" pos(v) = (v % G) * n_loc + v // G,
+    i.e. the row of v inside an all-gathered [G * n_loc, d] buffer.
+  * forward : per layer ONE all-gather of the [n_loc, d] fp32 shards (in place, the local SpMM writes straight
+    into the rank's slot of the next gather buffer), then the local row-block SpMM; the layer sum is folded into
+    the last SpMM's epilogue; one more all-gather publishes the final embeddings for the loss.
+  * loss    : training triples are sharded by edge (E/G per rank); fused gather+BPR on the gathered final
+    embeddings; the [G * n_loc, d] gradient partials are combined with ONE reduce-scatter.
+  * backward: A is symmetric, so rank r's row block applied to the all-gathered G(k+1) yields its rows of
+    A^T G(k+1): K more all-gathers.  Adam runs on the local shard.
+
+Communication volume per step: (2K+1) all-gathers + 1 reduce-scatter of N*d*4 bytes each (3.84 GB at cfg 5);
+the data path has no other collective.  ShardPlan is pure index arithmetic (CPU-testable with gloo).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .graph import CSRGraph
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    """Cyclic node partition over `world` ranks."""
+
+    n_users: int
+    n_items: int
+    world: int
+
+    @property
+    def n_nodes(self) -> int:
+        return self.n_users + self.n_items
+
+    @property
+    def n_loc(self) -> int:
+        """Rows per rank (the last ranks may carry one padding row)."""
+        return -(-self.n_nodes // self.world)
+
+    @property
+    def n_padded(self) -> int:
+        return self.n_loc * self.world
+
+    def owner(self, v):
+        return v % self.world
+
+    def local_row(self, v):
+        return v // self.world
+
+    def gathered_pos(self, v):
+        """Row of node v inside an all-gathered [world * n_loc, d] buffer."""
+        return (v % self.world) * self.n_loc + v // self.world
+
+    def node_of_pos(self, pos):
+        """Inverse of gathered_pos (padding rows map to ids >= n_nodes)."""
+        return (pos % self.n_loc) * self.world + pos // self.n_loc
+
+    def local_nodes(self, rank: int, device=None) -> torch.Tensor:
+        return torch.arange(rank, self.n_nodes, self.world, dtype=torch.int64, device=device)
+
+    def local_block_coo(self, users: torch.Tensor, items: torch.Tensor, rank: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Rows of the bidirectional adjacency [[0,R],[R^T,0]] owned by `rank`:
+        (local row ids, gathered-position column ids), duplicates kept."""
+        u = users.to(torch.int64)
+        i = items.to(torch.int64) + self.n_users
+        mu = (u % self.world) == rank          # user rows owned here: entries (u, i)
+        mi = (i % self.world) == rank          # item rows owned here: entries (i, u)
+        rows = torch.cat([u[mu] // self.world, i[mi] // self.world])
+        cols = torch.cat([self.gathered_pos(i[mu]), self.gathered_pos(u[mi])])
+        return rows, cols
+
+    def triple_range(self, n_triples: int, rank: int) -> Tuple[int, int]:
+        """Contiguous slice of the training triples handled by `rank` (balanced to within one)."""
+        base, rem = divmod(n_triples, self.world)
+        lo = rank * base + min(rank, rem)
+        return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_table(full: torch.Tensor, plan: ShardPlan, rank: int) -> torch.Tensor:
+    """[N, d] -> this rank's [n_loc, d] rows (zero padded)."""
+    out = torch.zeros(plan.n_loc, full.shape[1], dtype=full.dtype, device=full.device)
+    rows = full[rank::plan.world]
+    out[: rows.shape[0]] = rows
+    return out
+
+
+def unshard_table(gathered: torch.Tensor, plan: ShardPlan) -> torch.Tensor:
+    """All-gathered [world * n_loc, d] buffer -> [N, d] in node order."""
+    pos = plan.gathered_pos(torch.arange(plan.n_nodes, dtype=torch.int64, device=gathered.device))
+    return gathered[pos]
+
+
+class ShardedLightGCNTrainer:
+    """Full-batch LightGCN step (lightgcn.py:83-120), row-sharded over the default process group."""
+
+    def __init__(self, users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int, *, d: int = 64,
+                 n_layers: int = 3, lr: float = 0.01, reg_weight: float = 1e-4, seed: int = 0,
+                 init_table: Optional[torch.Tensor] = None):
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedLightGCNTrainer needs an initialised torch.distributed process group")
+        self.lib = _lib.load()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        dev = users.device
+        if not users.is_cuda:
+            raise RuntimeError("ShardedLightGCNTrainer: tensors must be on the rank's CUDA device")
+        self.dev = dev
+        self.plan = plan = ShardPlan(n_users, n_items, self.world)
+        self.n_users, self.n_items, self.d, self.k = n_users, n_items, d, n_layers
+        self.lr, self.reg, self.seed = lr, reg_weight, seed
+        n_loc, n_pad = plan.n_loc, plan.n_padded
+        self.rows_per_rank = n_loc
+        self.n_edges = int(users.numel())
+
+        # ---- local row block of D^-1/2 A D^-1/2 (values from the GLOBAL degree vector) ----
+        lib, st = self.lib, _lib.current_stream()
+        ei_rows = torch.cat([users, items + n_users]).contiguous()
+        deg = torch.empty(plan.n_nodes, dtype=torch.int32, device=dev)
+        _lib.check(lib.gcf_degree_count(_lib.ptr(ei_rows), ei_rows.numel(), _lib.ptr(deg), plan.n_nodes, st), "gcf_degree_count")
+        del ei_rows
+        dinv = deg.to(torch.float32).sqrt_().reciprocal_()
+        dinv[torch.isinf(dinv)] = 0.0                       # inf -> 0 (selfcf.py:246)
+        dinv_pos = torch.zeros(n_pad, dtype=torch.float32, device=dev)   # indexed by gathered position
+        dinv_pos[plan.gathered_pos(torch.arange(plan.n_nodes, device=dev))] = dinv
+        rows, cols = plan.local_block_coo(users, items, self.rank)
+        block = CSRGraph.from_coo(rows, cols, None, n_loc, n_pad, norm="none")
+        del rows, cols
+        row_scale = dinv_pos[self.rank * n_loc:(self.rank + 1) * n_loc].contiguous()
+        _lib.check(lib.gcf_scale_csr_values(_lib.ptr(block.row_ptr), _lib.ptr(block.col_idx), _lib.ptr(block.vals), n_loc,
+                                            _lib.ptr(row_scale), _lib.ptr(dinv_pos), _lib.ptr(block.vals), st),
+                   "gcf_scale_csr_values")
+        self.block = block
+        self.local_nnz = block.nnz
+        self.ws, self.ws_bytes = block.workspace(d)
+
+        # ---- parameters / optimiser state: local rows only ----
+        if init_table is not None:
+            self.table = shard_table(init_table.to(dev), plan, self.rank).contiguous()
+        else:
+            gen = torch.Generator(device=dev); gen.manual_seed(seed + 17)
+            bound_u = (6.0 / (n_users + d)) ** 0.5   # xavier_uniform_ bounds of the two reference tables
+            bound_i = (6.0 / (n_items + d)) ** 0.5
+            nodes = plan.local_nodes(self.rank, dev)
+            t = (torch.rand(n_loc, d, device=dev, generator=gen) * 2 - 1)
+            scale = torch.where(nodes < n_users, bound_u, bound_i).to(torch.float32)
+            t[: nodes.numel()] *= scale[:, None]
+            t[nodes.numel():] = 0
+            self.table = t
+        self.exp_avg = torch.zeros_like(self.table)
+        self.exp_avg_sq = torch.zeros_like(self.table)
+
+        # ---- gather buffers: E0..E(K-1) gathered, final gathered, gradient gathered ----
+        self.full = [torch.zeros(n_pad, d, device=dev) for _ in range(n_layers)]
+        self.final_full = torch.zeros(n_pad, d, device=dev)
+        self.g_full = torch.zeros(n_pad, d, device=dev)
+        self.g_loc = torch.zeros(n_loc, d, device=dev)
+        self.gk_full = [torch.zeros(n_pad, d, device=dev) for _ in range(2)]
+        self.g_x0 = torch.zeros(n_loc, d, device=dev)
+
+        # ---- this rank's triples, in gathered-position space ----
+        lo, hi = plan.triple_range(self.n_edges, self.rank)
+        self.n_triples = hi - lo
+        self.pos_u = plan.gathered_pos(users[lo:hi].to(torch.int64)).contiguous()
+        self.pos_i = plan.gathered_pos(items[lo:hi].to(torch.int64) + n_users).contiguous()
+        self.neg_raw = torch.empty(max(self.n_triples, 1), dtype=torch.int64, device=dev)
+        self.coef = torch.empty(max(self.n_triples, 1), dtype=torch.float32, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.bpr_ws_bytes = lib.gcf_bpr_workspace_bytes(self.n_triples)
+        self.bpr_ws = torch.empty(self.bpr_ws_bytes, dtype=torch.uint8, device=dev)
+        self.triple_offset = lo
+        self.step_count = 0
+        self.launches_per_step = 2 * n_layers + 5
+        self.collectives_per_step = 2 * n_layers + 2
+
+    # -------------------------------------------------------------------------------------------------
+    def _slot(self, buf: torch.Tensor) -> torch.Tensor:
+        return buf[self.rank * self.plan.n_loc:(self.rank + 1) * self.plan.n_loc]
+
+    def _spmm(self, x_full, y, out, alpha, post, addends, betas):
+        lib = self.lib
+        _lib.check(lib.gcf_spmm_csr_f32(self.block.struct_ref(), self.d, _lib.ptr(x_full), self.d,
+                                        _lib.ptr(y), self.d if y is not None else 0,
+                                        _lib.ptr(out), self.d if out is not None else 0,
+                                        _lib.EPILOGUE_NONE, alpha, post, len(addends), _lib.ptr_array(list(addends)),
+                                        _lib.float_array(list(betas)), _lib.ptr(self.ws), self.ws_bytes, 0,
+                                        _lib.current_stream()), "gcf_spmm_csr_f32")
+
+    def step(self, neg_items: Optional[torch.Tensor] = None, marks: Optional[list] = None) -> torch.Tensor:
+        """One optimisation step; returns the (global) loss.  neg_items: optional pre-drawn raw item ids for this
+        rank's triples (parity tests); otherwise Philox negatives keyed by the GLOBAL triple index, so the draw is
+        independent of the number of ranks."""
+        lib, st, plan, d, K = self.lib, _lib.current_stream(), self.plan, self.d, self.k
+        self.step_count += 1
+        ev = (lambda: torch.cuda.Event(enable_timing=True)) if marks is not None else None
+        spmm_marks: List = []
+
+        def timed_spmm(*a):
+            if ev is None:
+                return self._spmm(*a)
+            e0, e1 = ev(), ev()
+            e0.record(); self._spmm(*a); e1.record()
+            spmm_marks.append((e0, e1, 1))
+
+        # ---- forward: E0 gathered, then K SpMM with K-1 more gathers ----
+        self._slot(self.full[0]).copy_(self.table)
+        dist.all_gather_into_tensor(self.full[0], self._slot(self.full[0]))
+        final_loc = self._slot(self.final_full)
+        for k in range(1, K + 1):
+            if k < K:
+                y = self._slot(self.full[k])
+                timed_spmm(self.full[k - 1], y, None, 1.0, 1.0, [], [])
+                dist.all_gather_into_tensor(self.full[k], y)
+            else:  # last layer: final = sum_k E(k) (lightgcn.py:26), E(K) itself is not stored
+                adds = [self._slot(self.full[q]) for q in range(K)]
+                timed_spmm(self.full[K - 1], None, final_loc, 1.0, 1.0, adds, [1.0] * K)
+        dist.all_gather_into_tensor(self.final_full, final_loc)
+
+        # ---- loss on this rank's triples ----
+        if neg_items is None:
+            # one Philox stream per (seed, rank, step): rank in the high word of `offset` (it perturbs the key),
+            # step in the low word (a counter word)
+            _lib.check(lib.gcf_sample_negatives(self.seed, (self.rank << 32) | self.step_count, None, self.n_triples, 1,
+                                                self.n_items, None, None, 1, _lib.ptr(self.neg_raw), st),
+                       "gcf_sample_negatives")
+            neg_raw = self.neg_raw[: self.n_triples]
+        else:
+            neg_raw = neg_items.to(torch.int64)
+        neg = plan.gathered_pos(neg_raw + self.n_users).contiguous()
+        w = 1.0 / self.n_edges
+        # per-rank partial of the global mean: reduction = sum with coefficients pre-scaled by 1/E
+        _lib.check(lib.gcf_bpr_fwd(_lib.ptr(self.final_full), d, _lib.ptr(self.final_full), d, d, _lib.ptr(self.pos_u),
+                                   _lib.ptr(self.pos_i), _lib.ptr(neg), self.n_triples, 1, _lib.BPR_SOFTPLUS, 0.0,
+                                   _lib.REDUCE_SUM, self.reg / w, self.reg / w, 0.0, _lib.ptr(self.loss), _lib.ptr(self.coef),
+                                   _lib.ptr(self.bpr_ws), self.bpr_ws_bytes, st), "gcf_bpr_fwd")
+        self.g_full.zero_()
+        gscale = torch.full((), w, dtype=torch.float32, device=self.dev)
+        _lib.check(lib.gcf_bpr_bwd(_lib.ptr(self.final_full), d, _lib.ptr(self.final_full), d, d, _lib.ptr(self.pos_u),
+                                   _lib.ptr(self.pos_i), _lib.ptr(neg), self.n_triples, 1, _lib.ptr(self.coef), _lib.ptr(gscale),
+                                   self.reg / w, self.reg / w, 0.0, _lib.ptr(self.g_full), d, _lib.ptr(self.g_full), d, st),
+                   "gcf_bpr_bwd")
+        dist.reduce_scatter_tensor(self.g_loc, self.g_full, op=dist.ReduceOp.SUM)
+
+        # ---- backward propagation: G(k) = A G(k+1) + g,  G(K) = g  (scale 1: 'sum' combination) ----
+        cur_full = self.gk_full[0]
+        self._slot(cur_full).copy_(self.g_loc)
+        dist.all_gather_into_tensor(cur_full, self._slot(cur_full))
+        which = 1
+        for k in range(K - 1, -1, -1):
+            if k > 0:
+                nxt = self.gk_full[which]
+                out = self._slot(nxt)
+                timed_spmm(cur_full, None, out, 1.0, 1.0, [self.g_loc], [1.0])
+                dist.all_gather_into_tensor(nxt, out)
+                cur_full = nxt
+                which ^= 1
+            else:
+                timed_spmm(cur_full, None, self.g_x0, 1.0, 1.0, [self.g_loc], [1.0])
+
+        _lib.check(lib.gcf_adam_step(_lib.ptr(self.table), _lib.ptr(self.g_x0), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                                     self.table.numel(), self.lr, 0.9, 0.999, 1e-8, 0.0, 0, self.step_count, st), "gcf_adam_step")
+        loss = self.loss * w
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+        if marks is not None:
+            marks.extend(spmm_marks)
+        return loss
+
+    def gathered_table(self) -> torch.Tensor:
+        """[N, d] table in node order on every rank (for checks / evaluation)."""
+        buf = torch.zeros(self.plan.n_padded, self.d, device=self.dev)
+        self._slot(buf).copy_(self.table)
+        dist.all_gather_into_tensor(buf, self._slot(buf))
+        return unshard_table(buf, self.plan)

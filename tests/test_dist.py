@@ -1,0 +1,148 @@
+"""Multi-rank path.  CPU: world_size-2 gloo run of the sharding choreography (ShardPlan index arithmetic + real
+collectives, with the oracle's numpy SpMM standing in for the CUDA kernel).  GPU: 2-rank NCCL run of
+ShardedLightGCNTrainer against the single-GPU trainer (needs >= 2 devices; skipped otherwise)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from recommendation_b200 import synth
+from recommendation_b200.dist import ShardPlan, shard_table, unshard_table
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_shard_plan_arithmetic():
+    plan = ShardPlan(10, 7, 4)
+    v = torch.arange(plan.n_nodes)
+    pos = plan.gathered_pos(v)
+    assert plan.n_loc == 5 and plan.n_padded == 20
+    assert len(set(pos.tolist())) == plan.n_nodes and pos.max() < plan.n_padded
+    assert torch.equal(plan.node_of_pos(pos), v)
+    for r in range(4):
+        nodes = plan.local_nodes(r)
+        assert torch.equal(nodes % 4, torch.full_like(nodes, r))
+        assert torch.equal(pos[nodes], r * plan.n_loc + torch.arange(nodes.numel()))
+    spans = [plan.triple_range(23, r) for r in range(4)]
+    assert spans[0][0] == 0 and spans[-1][1] == 23 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    full = torch.randn(plan.n_nodes, 3)
+    gathered = torch.cat([shard_table(full, plan, r) for r in range(4)])
+    assert torch.equal(unshard_table(gathered, plan), full)
+
+
+def _gloo_worker(rank, world, port, n_users, n_items, users, items, x0, k, out_q):
+    from oracle import graph_ref
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plan = ShardPlan(n_users, n_items, world)
+        users_t, items_t = torch.from_numpy(users), torch.from_numpy(items)
+        rows, cols = plan.local_block_coo(users_t, items_t, rank)
+        deg = np.bincount(np.concatenate([users, items + n_users]), minlength=plan.n_nodes).astype(np.float32)
+        with np.errstate(divide="ignore"):
+            dinv = 1.0 / np.sqrt(deg)
+        dinv[np.isinf(dinv)] = 0
+        dinv_pos = np.zeros(plan.n_padded, np.float32)
+        dinv_pos[plan.gathered_pos(torch.arange(plan.n_nodes)).numpy()] = dinv
+        rp, ci, mult = graph_ref.coo_to_canonical_csr(rows.numpy(), cols.numpy(), None, plan.n_loc, plan.n_padded)
+        row_of = np.repeat(np.arange(plan.n_loc), np.diff(rp))
+        vals = (dinv_pos[rank * plan.n_loc + row_of] * mult) * dinv_pos[ci]
+        local = shard_table(torch.from_numpy(x0), plan, rank)
+        layers = [local]
+        for _ in range(k):
+            full = torch.zeros(plan.n_padded, x0.shape[1], dtype=torch.float64)
+            dist.all_gather_into_tensor(full, layers[-1].double().contiguous())   # one all-gather per layer
+            layers.append(torch.from_numpy(graph_ref.spmm_csr(rp, ci, vals, full.numpy())))
+        final = torch.stack([l.double() for l in layers]).sum(0)
+        gathered = torch.zeros(plan.n_padded, x0.shape[1], dtype=torch.float64)
+        dist.all_gather_into_tensor(gathered, final.contiguous())
+        if rank == 0:
+            out_q.put(unshard_table(gathered, plan).numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_propagation_gloo_world2():
+    from oracle import graph_ref
+
+    inter = synth.power_law_bipartite(60, 90, 700, seed=4)
+    U, I, k, d = 60, 90, 3, 8
+    x0 = np.random.default_rng(0).standard_normal((U + I, d)).astype(np.float32)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, U, I, inter.users, inter.items, x0, k, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ei = graph_ref.bipartite_edge_index(inter.users, inter.items, U)
+    rp, ci, mult = graph_ref.coo_to_canonical_csr(ei[0], ei[1], None, U + I, U + I)
+    vals, _, _ = graph_ref.normalize_csr(rp, ci, mult, U + I, U + I, "sym")
+    _, want = graph_ref.propagate(rp, ci, vals, x0, k, "sum")
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------- GPU, 2 ranks
+def _nccl_worker(rank, world, port, n_users, n_items, users, items, table0, negs, k, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from recommendation_b200.dist import ShardedLightGCNTrainer
+
+        users_t, items_t = torch.from_numpy(users).to(dev), torch.from_numpy(items).to(dev)
+        tr = ShardedLightGCNTrainer(users_t, items_t, n_users, n_items, d=table0.shape[1], n_layers=k, lr=0.01,
+                                    reg_weight=1e-4, init_table=torch.from_numpy(table0))
+        lo, hi = tr.plan.triple_range(users.shape[0], rank)
+        losses = []
+        for s in range(negs.shape[0]):
+            losses.append(float(tr.step(neg_items=torch.from_numpy(negs[s, lo:hi]).to(dev)).item()))
+        table = tr.gathered_table().cpu().numpy()
+        if rank == 0:
+            out_q.put((losses, table))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_trainer_matches_single_gpu():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 CUDA devices")
+    from recommendation_b200.graph import CSRGraph
+    from recommendation_b200.lightgcn import FusedLightGCNTrainer
+
+    inter = synth.power_law_bipartite(3000, 4000, 100000, seed=6)
+    U, I, d, k, steps = 3000, 4000, 64, 3, 3
+    rng = np.random.default_rng(1)
+    table0 = (rng.standard_normal((U + I, d)) * 0.05).astype(np.float32)
+    negs = rng.integers(0, I, (steps, inter.n_edges))
+    dev = torch.device("cuda", 0)
+    users_t, items_t = torch.from_numpy(inter.users).to(dev), torch.from_numpy(inter.items).to(dev)
+    g = CSRGraph.from_pairs(users_t, items_t, U, I, norm="sym")
+    ref = FusedLightGCNTrainer(g, U, I, torch.from_numpy(table0).to(dev), users_t, items_t, n_layers=k, lr=0.01, reg_weight=1e-4)
+    want_losses = [float(ref.step(neg_i=torch.from_numpy(negs[s]).to(dev)).item()) for s in range(steps)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, U, I, inter.users, inter.items, table0, negs, k, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got_losses, got_table = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    np.testing.assert_allclose(got_losses, want_losses, rtol=1e-4)
+    np.testing.assert_allclose(got_table, ref.table.cpu().numpy(), rtol=1e-3, atol=2e-5)
