@@ -318,3 +318,30 @@ def adam_step_(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, e
     _lib.check(lib.gcf_adam_step(_lib.ptr(param), _lib.ptr(grad), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq), param.numel(),
                                  lr, betas[0], betas[1], eps, weight_decay, 1 if decoupled else 0, int(step),
                                  _lib.current_stream()), "gcf_adam_step")
+
+
+# =========================================================================================
+# InfoNCE family (tcgen05 tensor cores)
+# =========================================================================================
+def infonce_stats_raw(q: torch.Tensor, k: torch.Tensor, tau: float, *, cos: bool = True, pos_idx: Optional[torch.Tensor] = None,
+                      want_row: bool = True, want_col: bool = False, want_pos: bool = True):
+    """(row_lse[M], col_lse[N] | None, pos[M]) of S = q^ k^T / tau without materialising S (gcf_infonce_fwd)."""
+    lib = _lib.load()
+    q, ldq = _rows_view(q, "q")
+    k, ldk = _rows_view(k, "k")
+    m, d = q.shape
+    n = k.shape[0]
+    if k.shape[1] != d:
+        raise ValueError("q and k must have the same width")
+    dev = q.device
+    row = torch.empty(m, dtype=torch.float32, device=dev) if want_row else None
+    col = torch.empty(n, dtype=torch.float32, device=dev) if want_col else None
+    pos = torch.empty(m, dtype=torch.float32, device=dev) if want_pos else None
+    ws_bytes = lib.gcf_infonce_workspace_bytes(m, n, d)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if pos_idx is not None:
+        pos_idx = _idx(pos_idx, dev, "pos_idx")
+    _lib.check(lib.gcf_infonce_fwd(_lib.ptr(q), ldq, m, _lib.ptr(k), ldk, n, d, 1 if cos else 0, float(tau), _lib.ptr(pos_idx),
+                                   _lib.ptr(row), _lib.ptr(col), _lib.ptr(pos), _lib.ptr(ws), ws_bytes, _lib.current_stream()),
+               "gcf_infonce_fwd")
+    return row, col, pos
