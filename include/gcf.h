@@ -208,11 +208,26 @@ int gcf_bpr_bwd(const float* user_emb, int64_t ld_user, const float* item_emb, i
                 const float* coef, const float* grad_out, float reg_u, float reg_p, float reg_n,
                 float* g_user, int64_t ldg_user, float* g_item, int64_t ldg_item, gcf_stream_t stream);
 
+/* Forward and backward in ONE pass (the three row gathers are done once): the loss is a scalar, so its upstream
+ * gradient is known before the backward starts (lightgcn.py:119 `loss.backward()`: 1) and is passed as the host
+ * scalar grad_scale.  Accumulates grad_scale * dloss/d(rows) into g_user / g_item exactly like gcf_bpr_bwd and
+ * writes the loss like gcf_bpr_fwd; coef_out is optional (NULL = not kept). */
+int gcf_bpr_fwd_bwd(const float* user_emb, int64_t ld_user, const float* item_emb, int64_t ld_item, int32_t d,
+                    const int64_t* u_idx, const int64_t* p_idx, const int64_t* n_idx, int64_t n_triples, int32_t n_negs,
+                    int32_t variant, float eps, int32_t reduction, float reg_u, float reg_p, float reg_n,
+                    float grad_scale, float* loss_out, float* coef_out,
+                    float* g_user, int64_t ldg_user, float* g_item, int64_t ldg_item,
+                    void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+
 /* Fused dense Adam / AdamW step (torch.optim.Adam semantics, ncl.py:305, lightgcn.py:80).
  * step = 1-based step count. */
 int gcf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t decoupled,
                   int64_t step, gcf_stream_t stream);
+
+/* x[0..n) *= *g (device scalar); returns without touching memory when *g == 1.  Used to apply the upstream
+ * gradient to tables whose gradient was produced in the forward pass (gcf_bpr_fwd_bwd). */
+int gcf_scale_by_device_scalar(float* x, int64_t n, const float* g, gcf_stream_t stream);
 
 /* ---- InfoNCE family on tcgen05 tensor cores (bf16 operands, fp32 accumulate + LSE) ----
  *

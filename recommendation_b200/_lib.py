@@ -71,6 +71,10 @@ _SIGNATURES = {
                               c_void_p, c_size_t, c_void_p]),
     "gcf_bpr_bwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                               c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "gcf_bpr_fwd_bwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                  c_int32, c_float, c_int32, c_float, c_float, c_float, c_float, c_void_p, c_void_p,
+                                  c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "gcf_scale_by_device_scalar": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gcf_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                 c_float, c_int32, c_int64, c_void_p]),
     "gcf_infonce_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),

@@ -32,3 +32,4 @@ int sm_count() {
 
 extern "C" const char* gcf_version(void) { return "gcf-b200 0.1.0 (sm_100a)"; }
 extern "C" const char* gcf_last_error(void) { return gcf::g_err; }
+

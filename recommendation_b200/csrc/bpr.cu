@@ -261,6 +261,158 @@ bpr_bwd_kernel(const float* __restrict__ uemb, long long ldu, const float* __res
   if (cur_u >= 0) red_row<LPR, VPL, GUARD>(g_user, ldgu, cur_u, sl, dvec, gu);
 }
 
+template <int LPR, int VPL, bool GUARD>
+__device__ __forceinline__ void red_row_hint(float* __restrict__ base, long long ld, long long row, int sl, int dvec,
+                                             const float4 (&v)[VPL], uint64_t pol) {
+  float* p = base + row * ld;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int idx = sl + k * LPR;
+    if (!GUARD || idx < dvec)
+      asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p + 4 * idx), "f"(v[k].x),
+                   "f"(v[k].y), "f"(v[k].z), "f"(v[k].w), "l"(pol));
+  }
+}
+
+template <int LPR, int VPL, bool GUARD>
+__device__ __forceinline__ void load_row_stream(const float* __restrict__ base, long long ld, long long row, int sl, int dvec,
+                                                float4 (&r)[VPL], uint64_t pol) {
+  const float4* p = reinterpret_cast<const float4*>(base + row * ld);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int idx = sl + k * LPR;
+    r[k] = (!GUARD || idx < dvec) ? ldg_f4_stream(p + idx, pol) : f4_zero();
+  }
+}
+
+// Forward AND backward in one pass over the triples: the three row gathers are done once, the loss derivative is
+// applied on the spot (dL/dloss = grad_scale is known up front: a scalar loss, lightgcn.py:119 `loss.backward()`),
+// and the gradients leave as red.global.add.v4.f32 -- the user gradient once per run of equal users.  Halves the
+// gather traffic of the separate fwd + bwd kernels, which is what bounds them once the tables outgrow the L2.
+// Negative rows are uniformly random (no reuse): gathered and reduced with L2 evict_first so they do not push the
+// popular positive rows out of the cache.
+template <int LPR, int VPL, bool GUARD, int BATCH>
+__global__ void __launch_bounds__(kBprThreads)
+bpr_fused_kernel(const float* __restrict__ uemb, long long ldu, const float* __restrict__ iemb, long long ldi, int dvec,
+                 const int64_t* __restrict__ u_idx, const int64_t* __restrict__ p_idx, const int64_t* __restrict__ n_idx,
+                 long long n, int n_negs, int variant, float eps, float w_loss, float reg_u, float reg_p, float reg_n,
+                 float grad_scale, float* __restrict__ coef_out, double* __restrict__ block_partials,
+                 float* __restrict__ g_user, long long ldgu, float* __restrict__ g_item, long long ldgi) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const long long group = ((long long)blockIdx.x * (kBprThreads / 32) + (threadIdx.x >> 5)) * RPW + sub;
+  const long long t0 = group * kRun;
+  const float inv_negs = 1.f / (float)n_negs;
+  const float ru2 = 2.f * reg_u * grad_scale, rp2 = 2.f * reg_p * grad_scale, rn2 = 2.f * reg_n * grad_scale;
+  const uint64_t pol_first = l2_policy_evict_first();
+
+  double local = 0.0;
+  if (t0 < n) {
+    const long long t1 = min(t0 + (long long)kRun, n);
+    long long cur_u = -1;
+    float4 gu[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) gu[k] = f4_zero();
+    float reg_part = 0.f;  // this lane's slice of the squared-norm regulariser
+    for (long long tb = t0; tb < t1; tb += BATCH) {
+      long long u[BATCH], p[BATCH], q[BATCH];
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b) {
+        const long long t = min(tb + b, t1 - 1);
+        u[b] = ld_stream_i64(u_idx + t);
+        p[b] = ld_stream_i64(p_idx + t);
+        q[b] = ld_stream_i64(n_idx + t * n_negs);
+      }
+      float4 ur[BATCH][VPL], pr[BATCH][VPL], nr[BATCH][VPL];
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b) {
+        load_row<LPR, VPL, GUARD>(uemb, ldu, u[b], sl, dvec, ur[b]);
+        load_row<LPR, VPL, GUARD>(iemb, ldi, p[b], sl, dvec, pr[b]);
+        load_row_stream<LPR, VPL, GUARD>(iemb, ldi, q[b], sl, dvec, nr[b], pol_first);
+      }
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b) {
+        const long long t = tb + b;
+        if (t >= t1) break;
+        float xs = 0.f, dn = 0.f, rs = 0.f, sn = 0.f;
+        float4 nsum[VPL];  // sum of the negative rows (for the user gradient)
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          xs += f4_dot(ur[b][k], pr[b][k]);
+          dn += f4_dot(ur[b][k], nr[b][k]);
+          rs += reg_u * f4_dot(ur[b][k], ur[b][k]) + reg_p * f4_dot(pr[b][k], pr[b][k]);
+          sn += f4_dot(nr[b][k], nr[b][k]);
+          nsum[k] = nr[b][k];
+        }
+        for (int j = 1; j < n_negs; ++j) {  // rare path (lightgcn.py n_neg in {3,5})
+          const long long qj = ld_stream_i64(n_idx + t * n_negs + j);
+          float4 nj[VPL];
+          load_row_stream<LPR, VPL, GUARD>(iemb, ldi, qj, sl, dvec, nj, pol_first);
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) { dn += f4_dot(ur[b][k], nj[k]); sn += f4_dot(nj[k], nj[k]); f4_add(nsum[k], nj[k]); }
+        }
+        float x = xs - dn * inv_negs;
+#pragma unroll
+        for (int off = LPR / 2; off > 0; off >>= 1) x += __shfl_xor_sync(mask, x, off);  // every lane gets the score
+        reg_part += rs + reg_n * sn;
+        float loss, dl;
+        bpr_pointwise(variant, eps, x, loss, dl);
+        const float cf = dl * w_loss;
+        if (sl == 0) {
+          if (coef_out != nullptr) coef_out[t] = cf;
+          local += (double)(loss * w_loss);
+        }
+        const float c = cf * grad_scale, cn = -c * inv_negs;
+        if (u[b] != cur_u) {
+          if (cur_u >= 0) red_row<LPR, VPL, GUARD>(g_user, ldgu, cur_u, sl, dvec, gu);
+          cur_u = u[b];
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) gu[k] = f4_zero();
+        }
+        float4 gp[VPL], gn[VPL];
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          gp[k] = make_float4(rp2 * pr[b][k].x, rp2 * pr[b][k].y, rp2 * pr[b][k].z, rp2 * pr[b][k].w);
+          f4_fma(gp[k], c, ur[b][k]);
+          gn[k] = make_float4(rn2 * nr[b][k].x, rn2 * nr[b][k].y, rn2 * nr[b][k].z, rn2 * nr[b][k].w);
+          f4_fma(gn[k], cn, ur[b][k]);
+          f4_fma(gu[k], c, pr[b][k]);
+          f4_fma(gu[k], cn, nsum[k]);
+          f4_fma(gu[k], ru2, ur[b][k]);
+        }
+        red_row<LPR, VPL, GUARD>(g_item, ldgi, p[b], sl, dvec, gp);
+        red_row_hint<LPR, VPL, GUARD>(g_item, ldgi, q[b], sl, dvec, gn, pol_first);
+        for (int j = 1; j < n_negs; ++j) {
+          const long long qj = ld_stream_i64(n_idx + t * n_negs + j);
+          float4 nj[VPL], gj[VPL];
+          load_row_stream<LPR, VPL, GUARD>(iemb, ldi, qj, sl, dvec, nj, pol_first);
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) {
+            gj[k] = make_float4(rn2 * nj[k].x, rn2 * nj[k].y, rn2 * nj[k].z, rn2 * nj[k].w);
+            f4_fma(gj[k], cn, ur[b][k]);
+          }
+          red_row_hint<LPR, VPL, GUARD>(g_item, ldgi, qj, sl, dvec, gj, pol_first);
+        }
+      }
+    }
+    if (cur_u >= 0) red_row<LPR, VPL, GUARD>(g_user, ldgu, cur_u, sl, dvec, gu);
+    local += (double)reg_part;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+  __shared__ double warp_part[kBprThreads / 32];
+  if (lane == 0) warp_part[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kBprThreads / 32; ++w) s += warp_part[w];
+    block_partials[blockIdx.x] = s;
+  }
+}
+
 static inline long long bpr_blocks(long long n, int lpr) {
   const long long groups_per_block = (long long)(kBprThreads / 32) * (32 / lpr);
   return cdiv(cdiv(n, kRun), groups_per_block);
@@ -374,5 +526,54 @@ extern "C" int gcf_bpr_bwd(const float* user_emb, int64_t ld_user, const float* 
     GCF_BPR_DISPATCH(bpr_bwd_kernel, user_emb, ld_user, item_emb, ld_item, dvec, u_idx, p_idx, n_idx, n_triples, n_negs,
                      coef, grad_out, reg_u, reg_p, reg_n, g_user, ldg_user, g_item, ldg_item);
   GCF_LAUNCH_CHECK("bpr_bwd_kernel");
+  return GCF_OK;
+}
+
+extern "C" int gcf_bpr_fwd_bwd(const float* user_emb, int64_t ld_user, const float* item_emb, int64_t ld_item, int32_t d,
+                               const int64_t* u_idx, const int64_t* p_idx, const int64_t* n_idx, int64_t n_triples,
+                               int32_t n_negs, int32_t variant, float eps, int32_t reduction, float reg_u, float reg_p,
+                               float reg_n, float grad_scale, float* loss_out, float* coef_out, float* g_user,
+                               int64_t ldg_user, float* g_item, int64_t ldg_item, void* workspace, size_t workspace_bytes,
+                               gcf_stream_t stream) {
+  int rc = bpr_check("gcf_bpr_fwd_bwd", user_emb, ld_user, item_emb, ld_item, d, u_idx, p_idx, n_idx, n_triples, n_negs);
+  if (rc != GCF_OK) return rc;
+  GCF_REQUIRE(loss_out != nullptr, "gcf_bpr_fwd_bwd: null loss_out");
+  GCF_REQUIRE(variant == GCF_BPR_LOG_EPS_SIGMOID || variant == GCF_BPR_SOFTPLUS, "gcf_bpr_fwd_bwd: bad variant");
+  GCF_REQUIRE(reduction == GCF_REDUCE_MEAN || reduction == GCF_REDUCE_SUM, "gcf_bpr_fwd_bwd: bad reduction");
+  GCF_REQUIRE(g_user && g_item && aligned16(g_user) && aligned16(g_item), "gcf_bpr_fwd_bwd: null/misaligned gradient tables");
+  GCF_REQUIRE(ldg_user >= d && ldg_item >= d && (ldg_user & 3) == 0 && (ldg_item & 3) == 0, "gcf_bpr_fwd_bwd: bad gradient leading dims");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_triples == 0) {
+    GCF_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+    return GCF_OK;
+  }
+  const long long grid = bpr_blocks(n_triples, lpr_for(d));
+  GCF_REQUIRE(grid < 2147483647LL, "gcf_bpr_fwd_bwd: too many triples for one launch");
+  const size_t need = align_up((size_t)grid * sizeof(double));
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("gcf_bpr_fwd_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return GCF_EWORKSPACE;
+  }
+  double* partials = static_cast<double*>(workspace);
+  const float w_loss = (reduction == GCF_REDUCE_MEAN) ? (1.f / (float)n_triples) : 1.f;
+  const int dvec = d / 4;
+#define GCF_BPR_FUSED_ARGS user_emb, ld_user, item_emb, ld_item, dvec, u_idx, p_idx, n_idx, n_triples, n_negs, variant, eps, \
+                           w_loss, reg_u, reg_p, reg_n, grad_scale, coef_out, partials, g_user, ldg_user, g_item, ldg_item
+  switch (d) {
+    case 16:  bpr_fused_kernel<4, 1, false, 2><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
+    case 32:  bpr_fused_kernel<8, 1, false, 2><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
+    case 64:  bpr_fused_kernel<16, 1, false, 2><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
+    case 128: bpr_fused_kernel<32, 1, false, 2><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
+    case 256: bpr_fused_kernel<32, 2, false, 1><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
+    default:
+      if (d <= 128)      bpr_fused_kernel<32, 1, true, 2><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS);
+      else if (d <= 256) bpr_fused_kernel<32, 2, true, 1><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS);
+      else if (d <= 512) bpr_fused_kernel<32, 4, true, 1><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS);
+      else               bpr_fused_kernel<32, 8, true, 1><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS);
+  }
+#undef GCF_BPR_FUSED_ARGS
+  GCF_LAUNCH_CHECK("bpr_fused_kernel");
+  bpr_reduce_kernel<<<1, 256, 0, st>>>(partials, grid, loss_out);
+  GCF_LAUNCH_CHECK("bpr_reduce_kernel");
   return GCF_OK;
 }

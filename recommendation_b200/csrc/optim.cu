@@ -44,6 +44,20 @@ adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __
   for (long long i = (n4 << 2) + tid; i < n; i += nth) adam_update(param[i], grad[i], m[i], v[i], a);
 }
 
+// x *= *g, skipped entirely (no traffic) when *g == 1 -- the usual `loss.backward()` seed.
+__global__ void __launch_bounds__(256)
+scale_by_device_scalar_kernel(float4* __restrict__ x, long long n4, float* __restrict__ tail, int n_tail,
+                              const float* __restrict__ g) {
+  const float s = __ldg(g);
+  if (s == 1.f) return;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = x[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    x[i] = v;
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) tail[threadIdx.x] *= s;
+}
+
 }  // namespace gcf
 
 using namespace gcf;
@@ -71,5 +85,18 @@ extern "C" int gcf_adam_step(float* param, const float* grad, float* exp_avg, fl
   const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(n / 4 + 1, 256), (long long)sm_count() * 16));
   adam_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, a);
   GCF_LAUNCH_CHECK("adam_kernel");
+  return GCF_OK;
+}
+
+extern "C" int gcf_scale_by_device_scalar(float* x, int64_t n, const float* g, gcf_stream_t stream) {
+  GCF_REQUIRE(n >= 0, "gcf_scale_by_device_scalar: negative n");
+  if (n == 0) return GCF_OK;
+  GCF_REQUIRE(x != nullptr && g != nullptr, "gcf_scale_by_device_scalar: null pointers");
+  GCF_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0, "gcf_scale_by_device_scalar: x must be 16B aligned");
+  const long long n4 = n / 4;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(gcf::cdiv(std::max<long long>(n4, 1), 256), (long long)gcf::sm_count() * 8));
+  gcf::scale_by_device_scalar_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<float4*>(x), n4, x + n4 * 4, (int)(n - n4 * 4), g);
+  GCF_LAUNCH_CHECK("scale_by_device_scalar_kernel");
   return GCF_OK;
 }

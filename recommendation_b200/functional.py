@@ -243,40 +243,88 @@ def sample_negatives(n: int, n_items: int, *, seed: int, offset: int = 0, n_negs
 # fused BPR
 # =========================================================================================
 class _BprFused(torch.autograd.Function):
+    """Fused gather + BPR.  When a gradient is needed the backward is computed IN the forward launch
+    (gcf_bpr_fwd_bwd: one pass over the triples, rows gathered once) with an upstream gradient of 1; backward()
+    then only applies the actual upstream scalar, which is a no-op launch for `loss.backward()`."""
+
     @staticmethod
-    def forward(ctx, user_emb, item_emb, u_idx, p_idx, n_idx, n_negs, variant, eps, reduction, reg_u, reg_p, reg_n):
+    def forward(ctx, user_emb, item_emb, u_idx, p_idx, n_idx, n_negs, variant, eps, reduction, reg_u, reg_p, reg_n, split=0):
         lib = _lib.load()
-        user_emb, ldu = _rows_view(user_emb, "user_emb")
-        item_emb, ldi = _rows_view(item_emb, "item_emb")
+        joint = item_emb is None  # user_emb is the joint [U+I, d] table: users = rows [0, split), items = the rest
+        if joint:
+            table = _f32c(user_emb, "table")
+            user_emb, item_emb = table[:split], table[split:]
+            ldu = ldi = table.shape[1]
+        else:
+            user_emb, ldu = _rows_view(user_emb, "user_emb")
+            item_emb, ldi = _rows_view(item_emb, "item_emb")
         d = user_emb.shape[1]
         if item_emb.shape[1] != d:
             raise ValueError("user/item embedding widths differ")
         n = u_idx.numel()
         dev = user_emb.device
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        coef = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
         ws_bytes = lib.gcf_bpr_workspace_bytes(n)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _lib.check(lib.gcf_bpr_fwd(_lib.ptr(user_emb), ldu, _lib.ptr(item_emb), ldi, d, _lib.ptr(u_idx), _lib.ptr(p_idx),
-                                   _lib.ptr(n_idx), n, n_negs, variant, eps, reduction, reg_u, reg_p, reg_n,
-                                   _lib.ptr(loss), _lib.ptr(coef), _lib.ptr(ws), ws_bytes, _lib.current_stream()),
-                   "gcf_bpr_fwd")
-        ctx.save_for_backward(user_emb, item_emb, u_idx, p_idx, n_idx, coef)
-        ctx.args = (ldu, ldi, d, n, n_negs, reg_u, reg_p, reg_n)
+        need_grad = ctx.needs_input_grad[0] or (not joint and ctx.needs_input_grad[1])
+        ctx.joint = joint
+        ctx.consumed = False
+        if need_grad:
+            if joint:
+                g_table = torch.zeros(table.shape, dtype=torch.float32, device=dev)
+                g_user, g_item = g_table[:split], g_table[split:]
+            else:
+                g_user = torch.zeros(user_emb.shape, dtype=torch.float32, device=dev)
+                g_item = torch.zeros(item_emb.shape, dtype=torch.float32, device=dev)
+            _lib.check(lib.gcf_bpr_fwd_bwd(_lib.ptr(user_emb), ldu, _lib.ptr(item_emb), ldi, d, _lib.ptr(u_idx),
+                                           _lib.ptr(p_idx), _lib.ptr(n_idx), n, n_negs, variant, eps, reduction,
+                                           reg_u, reg_p, reg_n, 1.0, _lib.ptr(loss), None, _lib.ptr(g_user), d,
+                                           _lib.ptr(g_item), d, _lib.ptr(ws), ws_bytes, _lib.current_stream()),
+                       "gcf_bpr_fwd_bwd")
+            ctx.grads = (g_table, None) if joint else (g_user, g_item)
+        else:
+            coef = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+            _lib.check(lib.gcf_bpr_fwd(_lib.ptr(user_emb), ldu, _lib.ptr(item_emb), ldi, d, _lib.ptr(u_idx), _lib.ptr(p_idx),
+                                       _lib.ptr(n_idx), n, n_negs, variant, eps, reduction, reg_u, reg_p, reg_n,
+                                       _lib.ptr(loss), _lib.ptr(coef), _lib.ptr(ws), ws_bytes, _lib.current_stream()),
+                       "gcf_bpr_fwd")
+            ctx.grads = None
         return loss
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         lib = _lib.load()
-        user_emb, item_emb, u_idx, p_idx, n_idx, coef = ctx.saved_tensors
-        ldu, ldi, d, n, n_negs, reg_u, reg_p, reg_n = ctx.args
+        if ctx.grads is None:
+            return (None,) * 13
+        if ctx.consumed:
+            raise RuntimeError("fused BPR gradients were already consumed (backward through this loss twice)")
+        ctx.consumed = True
         g = g.contiguous().to(torch.float32)
-        g_user = torch.zeros(user_emb.shape, dtype=torch.float32, device=user_emb.device)
-        g_item = torch.zeros(item_emb.shape, dtype=torch.float32, device=item_emb.device)
-        _lib.check(lib.gcf_bpr_bwd(_lib.ptr(user_emb), ldu, _lib.ptr(item_emb), ldi, d, _lib.ptr(u_idx), _lib.ptr(p_idx),
-                                   _lib.ptr(n_idx), n, n_negs, _lib.ptr(coef), _lib.ptr(g), reg_u, reg_p, reg_n,
-                                   _lib.ptr(g_user), d, _lib.ptr(g_item), d, _lib.current_stream()), "gcf_bpr_bwd")
-        return (g_user, g_item) + (None,) * 10
+        g_user, g_item = ctx.grads
+        ctx.grads = None
+        for t in (g_user, g_item):
+            if t is not None:
+                _lib.check(lib.gcf_scale_by_device_scalar(_lib.ptr(t), t.numel(), _lib.ptr(g), _lib.current_stream()),
+                           "gcf_scale_by_device_scalar")
+        return (g_user, g_item) + (None,) * 11
+
+
+def _adjacent_views(a: torch.Tensor, b: torch.Tensor) -> Optional[torch.Tensor]:
+    """If a = base[:U] and b = base[U:] of one contiguous [U+I, d] autograd tensor, return that base -- the
+    (x[:U], x[U:]) pair LightGCN.forward returns (lightgcn.py:27).  Using the base directly keeps the gradient
+    in one [U+I, d] buffer instead of two slice-backward zero-fills + copies."""
+    base = a._base
+    if base is None or b._base is not base or base.dim() != 2 or not base.is_contiguous():
+        return None
+    d = base.shape[1]
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != d or b.shape[1] != d or not (a.is_contiguous() and b.is_contiguous()):
+        return None
+    if a.data_ptr() != base.data_ptr() or b.data_ptr() != base.data_ptr() + a.shape[0] * d * 4:
+        return None
+    if a.shape[0] + b.shape[0] != base.shape[0]:
+        return None
+    return base
 
 
 def bpr_loss_gather(user_emb: torch.Tensor, item_emb: torch.Tensor, u_idx, p_idx, n_idx, *,
@@ -292,6 +340,10 @@ def bpr_loss_gather(user_emb: torch.Tensor, item_emb: torch.Tensor, u_idx, p_idx
     n_negs = n_idx.numel() // n if n else 1
     var = {"log_eps_sigmoid": _lib.BPR_LOG_EPS_SIGMOID, "softplus": _lib.BPR_SOFTPLUS}[variant]
     red = {"mean": _lib.REDUCE_MEAN, "sum": _lib.REDUCE_SUM}[reduction]
+    base = _adjacent_views(user_emb, item_emb)
+    if base is not None:  # one joint table: a single [U+I, d] gradient buffer is produced
+        return _BprFused.apply(base, None, u_idx, p_idx, n_idx.reshape(-1), n_negs, var, float(eps), red,
+                               float(reg_u), float(reg_p), float(reg_n), int(user_emb.shape[0]))
     return _BprFused.apply(user_emb, item_emb, u_idx, p_idx, n_idx.reshape(-1), n_negs, var, float(eps), red,
                            float(reg_u), float(reg_p), float(reg_n))
 

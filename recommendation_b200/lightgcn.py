@@ -166,14 +166,25 @@ class FusedLightGCNTrainer:
 
     def __init__(self, graph: CSRGraph, n_users: int, n_items: int, table: torch.Tensor, pos_u: torch.Tensor,
                  pos_i: torch.Tensor, *, n_layers: int = 3, lr: float = 0.01, reg_weight: float = 1e-4,
-                 weight_decay: float = 0.0, n_neg: int = 1, seed: int = 0):
+                 weight_decay: float = 0.0, n_neg: int = 1, seed: int = 0, sort_triples: bool = True,
+                 fused_bpr: bool = True):
         self.lib = _lib.load()
+        self.fused_bpr = fused_bpr
+        self.order = None
         self.graph, self.n_users, self.n_items = graph, n_users, n_items
         self.table = table
         self.n, self.d = table.shape
         dev = table.device
-        self.pos_u = pos_u.to(dev, torch.int64).contiguous()
-        self.pos_i = pos_i.to(dev, torch.int64).contiguous()
+        pos_u = pos_u.to(dev, torch.int64)
+        pos_i = pos_i.to(dev, torch.int64)
+        if sort_triples and pos_u.numel() > 1:
+            # full batch: the order of the interactions is free (the loss is a mean over all of them, lightgcn.py:86-88).
+            # User-major order lets the fused kernel keep the user row and its gradient in registers over a run.
+            order = torch.argsort(pos_u * n_items + pos_i)
+            pos_u, pos_i = pos_u[order], pos_i[order]
+            self.order = order  # externally supplied negatives (parity runs) are permuted the same way
+        self.pos_u = pos_u.contiguous()
+        self.pos_i = pos_i.contiguous()
         self.n_triples = self.pos_u.numel()
         self.k, self.lr, self.reg, self.wd, self.n_neg, self.seed = n_layers, lr, reg_weight, weight_decay, n_neg, seed
         self.layers = [torch.empty_like(table) for _ in range(n_layers - 1)] + [None]
@@ -191,7 +202,8 @@ class FusedLightGCNTrainer:
         self.bpr_ws = torch.empty(self.bpr_ws_bytes, dtype=torch.uint8, device=dev)
         self.ws, self.ws_bytes = graph.workspace(self.d)
         self.step_count = 0
-        self.launches_per_step = 2 * n_layers + 5  # libgcf kernels only: K fwd + K bwd SpMM, sampler, bpr fwd + reduce, bpr bwd, adam
+        # libgcf kernels only: K fwd + K bwd SpMM, sampler, bpr (fused fwd+bwd | fwd, bwd) + reduce, adam
+        self.launches_per_step = 2 * n_layers + (4 if fused_bpr else 5)
 
     def step(self, neg_i: Optional[torch.Tensor] = None, marks: Optional[list] = None) -> torch.Tensor:
         """One optimisation step.  `marks` (optional list) receives (start_event, end_event, n_spmm_launches)
@@ -211,16 +223,27 @@ class FusedLightGCNTrainer:
                                                 None, None, 1, _lib.ptr(self.neg), st), "gcf_sample_negatives")
             neg = self.neg
         else:
-            neg = neg_i.reshape(-1)
+            neg = neg_i.reshape(self.n_triples, -1)
+            if self.order is not None:
+                neg = neg[self.order]
+            neg = neg.reshape(-1).contiguous()
         user_emb, item_emb = self.final[:u], self.final[u:]
-        _lib.check(lib.gcf_bpr_fwd(_lib.ptr(user_emb), d, _lib.ptr(item_emb), d, d, _lib.ptr(self.pos_u), _lib.ptr(self.pos_i),
-                                   _lib.ptr(neg), self.n_triples, self.n_neg, _lib.BPR_SOFTPLUS, 0.0, _lib.REDUCE_MEAN,
-                                   self.reg, self.reg, 0.0, _lib.ptr(self.loss), _lib.ptr(self.coef), _lib.ptr(self.bpr_ws),
-                                   self.bpr_ws_bytes, st), "gcf_bpr_fwd")
-        self.g_final.zero_()
-        _lib.check(lib.gcf_bpr_bwd(_lib.ptr(user_emb), d, _lib.ptr(item_emb), d, d, _lib.ptr(self.pos_u), _lib.ptr(self.pos_i),
-                                   _lib.ptr(neg), self.n_triples, self.n_neg, _lib.ptr(self.coef), None, self.reg, self.reg, 0.0,
-                                   _lib.ptr(self.g_final[:u]), d, _lib.ptr(self.g_final[u:]), d, st), "gcf_bpr_bwd")
+        if self.fused_bpr:
+            self.g_final.zero_()
+            _lib.check(lib.gcf_bpr_fwd_bwd(_lib.ptr(user_emb), d, _lib.ptr(item_emb), d, d, _lib.ptr(self.pos_u), _lib.ptr(self.pos_i),
+                                           _lib.ptr(neg), self.n_triples, self.n_neg, _lib.BPR_SOFTPLUS, 0.0, _lib.REDUCE_MEAN,
+                                           self.reg, self.reg, 0.0, 1.0, _lib.ptr(self.loss), None,
+                                           _lib.ptr(self.g_final[:u]), d, _lib.ptr(self.g_final[u:]), d, _lib.ptr(self.bpr_ws),
+                                           self.bpr_ws_bytes, st), "gcf_bpr_fwd_bwd")
+        else:
+            _lib.check(lib.gcf_bpr_fwd(_lib.ptr(user_emb), d, _lib.ptr(item_emb), d, d, _lib.ptr(self.pos_u), _lib.ptr(self.pos_i),
+                                       _lib.ptr(neg), self.n_triples, self.n_neg, _lib.BPR_SOFTPLUS, 0.0, _lib.REDUCE_MEAN,
+                                       self.reg, self.reg, 0.0, _lib.ptr(self.loss), _lib.ptr(self.coef), _lib.ptr(self.bpr_ws),
+                                       self.bpr_ws_bytes, st), "gcf_bpr_fwd")
+            self.g_final.zero_()
+            _lib.check(lib.gcf_bpr_bwd(_lib.ptr(user_emb), d, _lib.ptr(item_emb), d, d, _lib.ptr(self.pos_u), _lib.ptr(self.pos_i),
+                                       _lib.ptr(neg), self.n_triples, self.n_neg, _lib.ptr(self.coef), None, self.reg, self.reg, 0.0,
+                                       _lib.ptr(self.g_final[:u]), d, _lib.ptr(self.g_final[u:]), d, st), "gcf_bpr_bwd")
         gt = g.transpose()
         if marks is not None:
             e2.record()

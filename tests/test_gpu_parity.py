@@ -453,3 +453,47 @@ def test_cfg1_size_properties(cuda):
     for r in rows:
         want = (v[rp[r]:rp[r + 1], None].astype(np.float64) * xc[ci[rp[r]:rp[r + 1]]]).sum(0)
         np.testing.assert_allclose(ax[r].cpu().numpy(), want, rtol=1e-4, atol=1e-5)
+
+
+# ====================================================================== fused BPR forward+backward
+def test_fused_bpr_equals_separate_forward_backward(cuda):
+    rng = np.random.default_rng(11)
+    U, I, T, d = 500, 700, 20011, 64
+    lib = _lib.load(); st = _lib.current_stream()
+    ue = torch.randn(U, d, device=cuda) * 0.3; ie = torch.randn(I, d, device=cuda) * 0.3
+    pu = dev_t(np.sort(rng.integers(0, U, T)), cuda); pi = dev_t(rng.integers(0, I, T), cuda); ni = dev_t(rng.integers(0, I, T), cuda)
+    ws_bytes = lib.gcf_bpr_workspace_bytes(T); ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cuda)
+    loss_a = torch.empty((), device=cuda); coef = torch.empty(T, device=cuda)
+    gu_a, gi_a = torch.zeros_like(ue), torch.zeros_like(ie)
+    _lib.check(lib.gcf_bpr_fwd(_lib.ptr(ue), d, _lib.ptr(ie), d, d, _lib.ptr(pu), _lib.ptr(pi), _lib.ptr(ni), T, 1, 1, 0.0, 0,
+                               1e-3, 1e-3, 2e-3, _lib.ptr(loss_a), _lib.ptr(coef), _lib.ptr(ws), ws_bytes, st), "fwd")
+    g = torch.tensor(0.5, device=cuda)
+    _lib.check(lib.gcf_bpr_bwd(_lib.ptr(ue), d, _lib.ptr(ie), d, d, _lib.ptr(pu), _lib.ptr(pi), _lib.ptr(ni), T, 1, _lib.ptr(coef),
+                               _lib.ptr(g), 1e-3, 1e-3, 2e-3, _lib.ptr(gu_a), d, _lib.ptr(gi_a), d, st), "bwd")
+    loss_b = torch.empty((), device=cuda); coef_b = torch.empty(T, device=cuda)
+    gu_b, gi_b = torch.zeros_like(ue), torch.zeros_like(ie)
+    _lib.check(lib.gcf_bpr_fwd_bwd(_lib.ptr(ue), d, _lib.ptr(ie), d, d, _lib.ptr(pu), _lib.ptr(pi), _lib.ptr(ni), T, 1, 1, 0.0, 0,
+                                   1e-3, 1e-3, 2e-3, 0.5, _lib.ptr(loss_b), _lib.ptr(coef_b), _lib.ptr(gu_b), d, _lib.ptr(gi_b), d,
+                                   _lib.ptr(ws), ws_bytes, st), "fwd_bwd")
+    np.testing.assert_allclose(loss_b.item(), loss_a.item(), rtol=1e-6)
+    torch.testing.assert_close(coef_b, coef, rtol=1e-6, atol=1e-12)
+    torch.testing.assert_close(gu_b, gu_a, rtol=1e-4, atol=1e-8)
+    torch.testing.assert_close(gi_b, gi_a, rtol=1e-4, atol=1e-8)
+
+
+def test_fused_bpr_applies_upstream_gradient(cuda):
+    """(3 * loss).backward(): the gradients computed in the forward launch are scaled by the upstream scalar."""
+    rng = np.random.default_rng(12)
+    U, I, T, d = 200, 300, 4001, 32
+    ue = torch.randn(U, d) * 0.3; ie = torch.randn(I, d) * 0.3
+    pu = rng.integers(0, U, T); pi = rng.integers(0, I, T); ni = rng.integers(0, I, T)
+    ue_c, ie_c = ue.clone().requires_grad_(True), ie.clone().requires_grad_(True)
+    (3.0 * losses_ref.bpr_lightgcn(ue_c.double(), ie_c.double(), torch.from_numpy(pu), torch.from_numpy(pi), torch.from_numpy(ni), 1e-3)).backward()
+    ue_g, ie_g = ue.to(cuda).requires_grad_(True), ie.to(cuda).requires_grad_(True)
+    loss = bpr_step_loss(ue_g, ie_g, dev_t(pu, cuda), dev_t(pi, cuda), dev_t(ni, cuda), 1e-3)
+    (3.0 * loss).backward()
+    np.testing.assert_allclose(ue_g.grad.cpu().numpy(), ue_c.grad.numpy(), rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(ie_g.grad.cpu().numpy(), ie_c.grad.numpy(), rtol=RTOL, atol=1e-7)
+    with torch.no_grad():   # no gradient requested: plain forward kernel, same value
+        loss2 = bpr_step_loss(ue_g.detach(), ie_g.detach(), dev_t(pu, cuda), dev_t(pi, cuda), dev_t(ni, cuda), 1e-3)
+    np.testing.assert_allclose(loss2.item(), loss.item(), rtol=1e-6)
