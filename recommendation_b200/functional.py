@@ -397,3 +397,135 @@ def infonce_stats_raw(q: torch.Tensor, k: torch.Tensor, tau: float, *, cos: bool
                                    _lib.ptr(row), _lib.ptr(col), _lib.ptr(pos), _lib.ptr(ws), ws_bytes, _lib.current_stream()),
                "gcf_infonce_fwd")
     return row, col, pos
+
+
+class _InfoNCEStats(torch.autograd.Function):
+    """(row_lse, col_lse, pos) of S = q^ k^T / tau, differentiable w.r.t. q and k (gcf_infonce_fwd / _bwd).
+    The B x N logits exist only as tensor-core tiles in TMEM; the backward recomputes them tile by tile."""
+
+    @staticmethod
+    def forward(ctx, q, k, tau, cos, pos_idx, want_col):
+        q, _ = _rows_view(q, "q")
+        k, _ = _rows_view(k, "k")
+        row, col, pos = infonce_stats_raw(q, k, tau, cos=cos, pos_idx=pos_idx, want_col=want_col)
+        ctx.save_for_backward(q, k, row, col if want_col else None, pos_idx)
+        ctx.tau, ctx.cos, ctx.want_col = float(tau), bool(cos), bool(want_col)
+        if not want_col:
+            col = row.new_zeros(0)
+        ctx.set_materialize_grads(False)
+        return row, col, pos
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_row, g_col, g_pos):
+        lib = _lib.load()
+        q, k, row, col, pos_idx = ctx.saved_tensors
+        if not ctx.want_col:
+            g_col = None
+        if g_row is None and g_col is None and g_pos is None:
+            return (None,) * 6
+        m, d = q.shape
+        n = k.shape[0]
+        dev = q.device
+        f = lambda t: None if t is None else t.contiguous().to(torch.float32)
+        g_row, g_col, g_pos = f(g_row), f(g_col), f(g_pos)
+        need_q, need_k = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gq = torch.empty_like(q) if need_q else None
+        gk = torch.empty_like(k) if need_k else None
+        ws_bytes = lib.gcf_infonce_workspace_bytes(m, n, d)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.gcf_infonce_bwd(_lib.ptr(q), q.stride(0), m, _lib.ptr(k), k.stride(0), n, d, 1 if ctx.cos else 0, ctx.tau,
+                                       _lib.ptr(pos_idx), _lib.ptr(row if g_row is not None else None),
+                                       _lib.ptr(col if g_col is not None else None), _lib.ptr(g_row), _lib.ptr(g_col),
+                                       _lib.ptr(g_pos), _lib.ptr(gq), d, _lib.ptr(gk), d, _lib.ptr(ws), ws_bytes,
+                                       _lib.current_stream()), "gcf_infonce_bwd")
+        return gq, gk, None, None, None, None
+
+
+def infonce_stats(q: torch.Tensor, k: torch.Tensor, tau: float, *, cos: bool = True, pos_idx=None, want_col: bool = False):
+    """Differentiable (row_lse[M], col_lse[N] | None, pos[M]); every InfoNCE-family loss below is a few vector ops on these."""
+    if pos_idx is not None:
+        pos_idx = _idx(pos_idx, q.device, "pos_idx")
+    row, col, pos = _InfoNCEStats.apply(q, k, float(tau), bool(cos), pos_idx, bool(want_col))
+    return row, (col if want_col else None), pos
+
+
+def info_nce(view1: torch.Tensor, view2: torch.Tensor, temperature: float, b_cos: bool = True) -> torch.Tensor:
+    """InfoNCE(view1, view2, temperature, b_cos) of ncl.py:125-130 / ssl4rec.py:19-23:
+    -mean(diag(log_softmax(v1^ v2^T / tau, dim=1)))."""
+    row, _, pos = infonce_stats(view1, view2, temperature, cos=b_cos)
+    return (row - pos).mean()
+
+
+def ssl_layer_side(context_rows: torch.Tensor, all_rows: torch.Tensor, idx, tau: float) -> torch.Tensor:
+    """One side of NCLModel.ssl_layer_loss (ncl.py:358-367): sum_b [ log sum_{all} exp(c^_b z^_./tau) - c^_b z^_{idx_b}/tau ]
+    with the denominator over ALL rows of `all_rows` (B x U or B x I logits, never materialised)."""
+    row, _, pos = infonce_stats(context_rows, all_rows, tau, cos=True, pos_idx=idx)
+    return (row - pos).sum()
+
+
+def batch_softmax(user_emb: torch.Tensor, item_emb: torch.Tensor, temperature: float) -> torch.Tensor:
+    """batch_softmax_loss of ssl4rec.py:25-30: -mean log( exp(s_ii) / sum_j exp(s_ij) + 1e-6 )."""
+    row, _, pos = infonce_stats(user_emb, item_emb, temperature, cos=True)
+    return -torch.log(torch.exp(pos - row) + 1e-6).mean()
+
+
+def info_nce_symmetric(z1: torch.Tensor, z2: torch.Tensor, temp: float = 0.2) -> torch.Tensor:
+    """info_nce_loss of gcl.py:28-35: (CE(S, arange) + CE(S^T, arange)) / 2 over the full N x N logits."""
+    row, col, pos = infonce_stats(z1, z2, temp, cos=True, want_col=True)
+    return ((row - pos).mean() + (col - pos).mean()) / 2
+
+
+class _DirectAU(torch.autograd.Function):
+    """(align, unif(x), unif(y)) of directau.py:240-251 (gcf_directau_fwd / _bwd; Gram matrices on tensor cores)."""
+
+    @staticmethod
+    def forward(ctx, x, y, t):
+        lib = _lib.load()
+        x, ldx = _rows_view(x, "x")
+        y, ldy = _rows_view(y, "y")
+        b, d = x.shape
+        if y.shape != x.shape:
+            raise ValueError("x and y must have the same shape")
+        out3 = torch.empty(3, dtype=torch.float32, device=x.device)
+        ws_bytes = lib.gcf_directau_workspace_bytes(b, d)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        _lib.check(lib.gcf_directau_fwd(_lib.ptr(x), ldx, _lib.ptr(y), ldy, b, d, float(t), _lib.ptr(out3), _lib.ptr(ws), ws_bytes,
+                                        _lib.current_stream()), "gcf_directau_fwd")
+        ctx.save_for_backward(x, y, out3)
+        ctx.t = float(t)
+        return out3
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g3):
+        lib = _lib.load()
+        x, y, out3 = ctx.saved_tensors
+        b, d = x.shape
+        g3 = g3.contiguous().to(torch.float32)
+        gx, gy = torch.empty_like(x), torch.empty_like(y)
+        ws_bytes = lib.gcf_directau_workspace_bytes(b, d)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        _lib.check(lib.gcf_directau_bwd(_lib.ptr(x), x.stride(0), _lib.ptr(y), y.stride(0), b, d, ctx.t, _lib.ptr(out3), _lib.ptr(g3),
+                                        _lib.ptr(gx), d, _lib.ptr(gy), d, _lib.ptr(ws), ws_bytes, _lib.current_stream()),
+                   "gcf_directau_bwd")
+        return gx, gy, None
+
+
+def directau_terms(x: torch.Tensor, y: torch.Tensor, t: float = 2.0) -> torch.Tensor:
+    """[alignment(x, y), uniformity(x), uniformity(y)] (directau.py:245-251) in one fused evaluation.
+    Fewer than two rows: uniformity is 0 by the reference's `pdist.numel() > 0` guard."""
+    if x.shape[0] < 2:
+        xn = torch.nn.functional.normalize(x, dim=-1); yn = torch.nn.functional.normalize(y, dim=-1)
+        align = (xn - yn).pow(2).sum(1).mean()
+        zero = align.new_zeros(())
+        return torch.stack([align, zero, zero])
+    return _DirectAU.apply(x, y, float(t))
+
+
+def l2_reg_loss(reg: float, *args: torch.Tensor) -> torch.Tensor:
+    """ncl.py:122-123 / directau.py:35 / ssl4rec.py:16: reg * sum_x |x|_F / rows(x)   (norm NOT squared)."""
+    emb_loss = 0
+    for emb in args:
+        emb_loss = emb_loss + torch.norm(emb, p=2) / emb.shape[0]
+    return emb_loss * reg
