@@ -24,6 +24,7 @@ import torch.nn as nn
 from . import _lib
 from . import functional as F_
 from .graph import CSRGraph
+from .tables import JoinTables as _JoinTables, join_parameters
 
 
 def build_edge_index(users: torch.Tensor, items: torch.Tensor, num_users: int) -> torch.Tensor:
@@ -40,27 +41,6 @@ def build_edge_index(users: torch.Tensor, items: torch.Tensor, num_users: int) -
                    "gcf_bipartite_edge_index")
         return out
     return torch.stack([torch.cat([users, items + num_users]), torch.cat([items + num_users, users])])
-
-
-class _JoinTables(torch.autograd.Function):
-    """cat([user_w, item_w]) without the copy when both weights are adjacent slices of one allocation."""
-
-    @staticmethod
-    def forward(ctx, user_w: torch.Tensor, item_w: torch.Tensor):
-        u, d = user_w.shape
-        i = item_w.shape[0]
-        ctx.split = (u, i)
-        adjacent = (user_w.is_contiguous() and item_w.is_contiguous()
-                    and user_w.untyped_storage().data_ptr() == item_w.untyped_storage().data_ptr()
-                    and user_w.data_ptr() + u * d * 4 == item_w.data_ptr())
-        if adjacent:
-            return torch.as_strided(user_w.detach(), (u + i, d), (d, 1))
-        return torch.cat([user_w, item_w], dim=0)
-
-    @staticmethod
-    def backward(ctx, g):
-        u, i = ctx.split
-        return g[:u], g[u:]
 
 
 class LGConv(nn.Module):
@@ -83,14 +63,7 @@ class LightGCN(nn.Module):
 
     # -- one allocation for both tables ------------------------------------------------------
     def _join(self) -> None:
-        uw, iw = self.user_embedding.weight, self.item_embedding.weight
-        table = torch.empty(uw.shape[0] + iw.shape[0], uw.shape[1], dtype=uw.dtype, device=uw.device)
-        with torch.no_grad():
-            table[: uw.shape[0]].copy_(uw)
-            table[uw.shape[0]:].copy_(iw)
-            uw.data = table[: uw.shape[0]]
-            iw.data = table[uw.shape[0]:]
-        self._table = table
+        self._table = join_parameters(self.user_embedding.weight, self.item_embedding.weight)
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)

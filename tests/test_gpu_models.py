@@ -1,0 +1,186 @@
+"""GPU parity of the drop-in model classes against fixtures produced by the reference's own classes
+(tests/golden/make_golden.py): same parameters in, same outputs / losses / gradients out."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from recommendation_b200 import encoders, losses, sampling
+from recommendation_b200.graph import CSRGraph
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-3
+
+
+def _close(got, want, rtol=RTOL, atol=1e-6):
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want, rtol=rtol, atol=atol)
+
+
+def _selfcf_data(g):
+    U, I = int(g["n_users"]), int(g["n_items"])
+    norm = sp.csr_matrix((g["norm_data"], g["norm_indices"], g["norm_indptr"]), shape=(U + I, U + I))
+    return SimpleNamespace(user_num=U, item_num=I, norm_adj=norm)
+
+
+def _ncl_data(g):
+    U, I = int(g["n_users"]), int(g["n_items"])
+    raw = sp.coo_matrix((g["coo_data"], (g["coo_row"], g["coo_col"])), shape=(U + I, U + I))  # duplicates kept (ncl.py:76-85)
+    return SimpleNamespace(user_num=U, item_num=I, norm_adj=raw)
+
+
+def _load(enc, z, cuda):
+    sd = {"embedding_dict.user_emb": torch.from_numpy(z["user_w"]), "embedding_dict.item_emb": torch.from_numpy(z["item_w"])}
+    assert sorted(enc.state_dict().keys()) == sorted(sd.keys())   # state_dict keys are part of the interface
+    enc.load_state_dict(sd)
+    return enc.embedding_dict["user_emb"], enc.embedding_dict["item_emb"]
+
+
+def test_lgcn_encoder_selfcf_fixture(cuda, golden):
+    z, data = golden("selfcf_encoder"), _selfcf_data(golden("selfcf_graph"))
+    enc = encoders.LGCN_Encoder(data, z["user_w"].shape[1], int(z["n_layers"]))
+    uw, iw = _load(enc, z, cuda)
+    ua, ia = enc()
+    _close(ua, z["user_all"]); _close(ia, z["item_all"])
+    ((ua * torch.from_numpy(z["proj_u"]).to(cuda)).sum() + (ia * torch.from_numpy(z["proj_i"]).to(cuda)).sum()).backward()
+    _close(uw.grad, z["grad_user_w"]); _close(iw.grad, z["grad_item_w"])
+
+
+def test_lgcn_encoder_ncl_fixture(cuda, golden):
+    z, data = golden("ncl_encoder"), _ncl_data(golden("ncl_graph"))
+    enc = encoders.LGCNEncoder(data, z["user_w"].shape[1], int(z["n_layers"]))
+    uw, iw = _load(enc, z, cuda)
+    ru, ri, all_emb = enc()
+    assert len(all_emb) == int(z["n_layers"]) + 1
+    _close(ru, z["user_out"], atol=1e-5); _close(ri, z["item_out"], atol=1e-5)
+    for k, e in enumerate(all_emb):
+        _close(e, z["all_emb"][k], atol=1e-5 * max(1.0, np.abs(z["all_emb"][k]).max()))
+    proj = torch.from_numpy(z["proj_layers"]).to(cuda)
+    loss = (ru * torch.from_numpy(z["proj_u"]).to(cuda)).sum() + (ri * torch.from_numpy(z["proj_i"]).to(cuda)).sum()
+    loss = loss + sum((e * proj[k]).sum() for k, e in enumerate(all_emb))
+    loss.backward()
+    _close(uw.grad, z["grad_user_w"], atol=1e-4); _close(iw.grad, z["grad_item_w"], atol=1e-4)
+
+
+def test_selfcf_he_fixture(cuda, golden):
+    z, data = golden("selfcf_he"), _selfcf_data(golden("selfcf_graph"))
+    he = encoders.SelfCF_HE(data, z["user_w"].shape[1], float(z["momentum"]), int(z["n_layers"]))
+    want_keys = ["online_encoder.embedding_dict.item_emb", "online_encoder.embedding_dict.user_emb", "predictor.bias", "predictor.weight"]
+    assert sorted(he.state_dict().keys()) == want_keys          # history buffers are NOT in the state_dict
+    he.load_state_dict({"online_encoder.embedding_dict.user_emb": torch.from_numpy(z["user_w"]),
+                        "online_encoder.embedding_dict.item_emb": torch.from_numpy(z["item_w"]),
+                        "predictor.weight": torch.from_numpy(z["pred_w"]), "predictor.bias": torch.from_numpy(z["pred_b"])})
+    he.u_target_his = torch.from_numpy(z["his_u0"]).to(cuda); he.i_target_his = torch.from_numpy(z["his_i0"]).to(cuda)
+    out = he({"user": z["users"].tolist(), "item": z["items"].tolist()})      # Python lists, as the reference passes
+    for got, key in zip(out, ("p_u", "t_u", "p_i", "t_i")):
+        _close(got, z[key], atol=1e-5)
+    loss = he.get_loss(out)
+    _close(loss, z["loss"], rtol=1e-4)
+    loss.backward()
+    enc = he.online_encoder
+    _close(enc.embedding_dict["user_emb"].grad, z["g_user_w"], atol=1e-6); _close(enc.embedding_dict["item_emb"].grad, z["g_item_w"], atol=1e-6)
+    _close(he.predictor.weight.grad, z["g_pred_w"], atol=1e-6); _close(he.predictor.bias.grad, z["g_pred_b"], atol=1e-6)
+    _close(he.u_target_his, z["his_u1"], atol=1e-5); _close(he.i_target_his, z["his_i1"], atol=1e-5)
+    pu, uo, pi, io = he.get_embedding()
+    assert pu.shape == uo.shape == (data.user_num, z["user_w"].shape[1]) and not pu.requires_grad
+
+
+def test_reference_named_losses(cuda, golden):
+    z = golden("ncl_losses")
+    T = lambda a: torch.from_numpy(np.asarray(a)).to(cuda)
+    L = lambda a: T(a).float().requires_grad_(True)
+    ue, pe, ne = L(z["ue"]), L(z["pe"]), L(z["ne"])
+    loss = losses.bpr_loss(ue, pe, ne)
+    _close(loss, z["bpr"], rtol=1e-4)
+    loss.backward()
+    _close(ue.grad, z["g_bpr_u"], atol=1e-7); _close(pe.grad, z["g_bpr_p"], atol=1e-7); _close(ne.grad, z["g_bpr_n"], atol=1e-7)
+    ue, pe, ne = L(z["ue"]), L(z["pe"]), L(z["ne"])
+    reg = losses.l2_reg_loss(1e-3, ue, pe, ne)
+    _close(reg, z["reg"], rtol=1e-5)
+    ncl = losses.NCLLosses(int(z["n_users"]), int(z["n_items"]), float(z["ssl_temp"]), float(z["ssl_reg"]), float(z["alpha"]),
+                           float(z["proto_reg"]), int(z["batch_size"]))
+    ctx, ini = L(z["ctx"]), L(z["ini"])
+    l = ncl.ssl_layer_loss(ctx, ini, z["bu"].tolist(), z["bp"].tolist())
+    np.testing.assert_allclose(l.item(), z["ssl"], rtol=2e-2)
+    ncl.user_centroids, ncl.item_centroids = T(z["user_centroids"]), T(z["item_centroids"])
+    ncl.user_2cluster, ncl.item_2cluster = T(z["user_2cluster"]), T(z["item_2cluster"])
+    ini2 = L(z["ini"])
+    l = ncl.ProtoNCE_loss(ini2, z["bu"].tolist(), z["bp"].tolist())
+    np.testing.assert_allclose(l.item(), z["proto"], rtol=2e-2)
+    l.backward()
+    want = z["g_proto_ini"]
+    np.testing.assert_allclose(ini2.grad.cpu().numpy(), want, rtol=2e-2, atol=2e-2 * np.abs(want).max())
+    zd = golden("directau_losses")
+    dau = losses.DirectAULosses(float(zd["gamma"]))
+    xu, xp, xn = L(zd["xu"]), L(zd["xp"]), L(zd["xn"])
+    train = dau.calculate_loss(xu, xp) - dau.calculate_loss(xu, xn) + losses.l2_reg_loss(float(zd["reg"]), xu, xp, xn) / int(zd["batch_size"])
+    np.testing.assert_allclose(train.item(), zd["train"], rtol=2e-2, atol=2e-3)
+    train.backward()
+    for t, k in ((xu, "g_train_u"), (xp, "g_train_p"), (xn, "g_train_n")):
+        np.testing.assert_allclose(t.grad.cpu().numpy(), zd[k], rtol=2e-2, atol=2e-2 * np.abs(zd[k]).max())
+    np.testing.assert_allclose(dau.alignment(xu, xp).item(), zd["align"], rtol=1e-4)
+    np.testing.assert_allclose(dau.uniformity(xu).item(), zd["unif"], rtol=2e-2)
+
+
+def test_dnn_encoder_and_grace_interfaces(cuda):
+    data = SimpleNamespace(user_num=50, item_num=70)
+    torch.manual_seed(0)
+    m = encoders.DNNEncoder(data, 32, 0.1, 0.2, 2)
+    keys = sorted(m.state_dict().keys())
+    assert keys == sorted(["initial_user", "initial_item", "user_net.0.weight", "user_net.0.bias", "user_net.2.weight", "user_net.2.bias",
+                           "item_net.0.weight", "item_net.0.bias", "item_net.2.weight", "item_net.2.bias"])
+    u, i = [1, 2, 3, 3], [5, 6, 7, 7]
+    a, b = m(u, i)
+    assert a.shape == b.shape == (4, 128)
+    m.eval()
+    cl = m.cal_cl_loss(i)           # eval mode: both dropout views are identical -> InfoNCE of a batch with itself
+    emb = m.item_net(m.initial_item[torch.tensor(i, device=cuda)])
+    en = torch.nn.functional.normalize(emb.double(), dim=1)
+    want = -torch.diag(torch.log_softmax(en @ en.T / 0.2, dim=1)).mean()
+    np.testing.assert_allclose(cl.item(), want.item(), rtol=2e-2)
+    (cl + losses.batch_softmax_loss(a, b, 0.2)).backward()
+    assert m.initial_item.grad is not None and m.initial_user.grad is not None
+    g = encoders.GRACEModel(50, 70, emb_size=32, num_layers=2, proj_dim=16).to(cuda)
+    assert "convs.1.weight" in g.state_dict() and "proj_head.2.bias" in g.state_dict() and "user_emb.weight" in g.state_dict()
+    ei = torch.randint(0, 120, (2, 400), device=cuda)
+    aug = encoders.EdgeRemoving(0.5)(ei)
+    assert aug.shape[0] == 2 and 100 < aug.shape[1] < 300
+    z1, z2 = g(aug, encoders.EdgeRemoving(0.5)(ei))
+    loss = losses.info_nce_loss(z1[:50], z2[:50]) + losses.info_nce_loss(z1[50:], z2[50:])
+    zd1, zd2 = z1.detach().double(), z2.detach().double()
+
+    def ref(a, b, temp=0.2):
+        a, b = torch.nn.functional.normalize(a, dim=1), torch.nn.functional.normalize(b, dim=1)
+        s = a @ b.T / temp
+        lab = torch.arange(a.shape[0], device=a.device)
+        return (torch.nn.functional.cross_entropy(s, lab) + torch.nn.functional.cross_entropy(s.T, lab)) / 2
+    np.testing.assert_allclose(loss.item(), (ref(zd1[:50], zd2[:50]) + ref(zd1[50:], zd2[50:])).item(), rtol=2e-2)
+    loss.backward()
+    assert g.user_emb.weight.grad is not None
+
+
+def test_next_batch_pairwise_semantics(cuda):
+    rng = np.random.default_rng(0)
+    U, I, E = 40, 60, 700
+    u = rng.integers(0, U, E); i = rng.integers(0, I, E)
+    data = SimpleNamespace(user_num=U, item_num=I, training_data=[[f"u{a}", f"i{b}", 1.0] for a, b in zip(u, i)],
+                           user={f"u{a}": a for a in range(U)}, item={f"i{b}": b for b in range(I)})
+    pos = {a: set() for a in range(U)}
+    for a, b in zip(u, i):
+        pos[int(a)].add(int(b))
+    seen = []
+    sizes = []
+    for bu, bi, bj in sampling.next_batch_pairwise(data, 128):
+        bu, bi, bj = bu.cpu().numpy(), bi.cpu().numpy(), bj.cpu().numpy()
+        sizes.append(len(bu))
+        assert len(bu) == len(bi) == len(bj)
+        assert ((bj >= 0) & (bj < I)).all()
+        assert all(int(j) not in pos[int(a)] for a, j in zip(bu, bj))     # negatives are never training positives
+        seen += list(zip(bu.tolist(), bi.tolist()))
+    assert sizes == [128] * 5 + [60]
+    assert sorted(seen) == sorted(zip(u.tolist(), i.tolist()))             # one epoch = every training pair exactly once
+    first = next(iter(sampling.next_batch_pairwise(data, 128)))[0].cpu().numpy()
+    assert not np.array_equal(first, np.array([p[0] for p in seen[:128]]))  # reshuffled per epoch
+    negs = np.concatenate([b[2].cpu().numpy() for b in data._gcf_sampler.batches(700, n_negs=1)])
+    assert len(np.unique(negs)) > I // 2                                    # spread over the item set
