@@ -48,6 +48,17 @@ def measured_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload: str):
+    """DRAM bytes per SpMM launch from the committed `ncu --set full` capture of this workload (profiles/traffic.json),
+    or None when no capture exists for it."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        rec = json.loads(p.read_text())[workload]["spmm_csr_kernel"]
+        return float(rec["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def spmm_algorithmic_bytes(n_rows, n_cols, nnz, d):
     """nnz*(4+4) + (N_r+1)*4 + N_c*d*4 + N_r*d*4 per SpMM launch (compulsory traffic)."""
     return nnz * 8 + (n_rows + 1) * 4 + n_cols * d * 4 + n_rows * d * 4
@@ -115,7 +126,19 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_step_rate(sample_cfg: str, steps: int, warmup: int):
+def cpu_sample_shape(workload: str):
+    """Bounded CPU sample of a workload: the graph itself when it has <= 2.1 M edges, otherwise the same generator at
+    1/k scale (same users:items:edges proportions, hence the same average degrees), k chosen so that E ~ 2 M."""
+    from recommendation_b200 import synth
+
+    U, I, E, d, K = synth.CONFIGS[workload]
+    if E <= 2_100_000:
+        return U, I, E, d, K, f"the {workload} graph"
+    k = max(1, round(E / 2_000_000))
+    return U // k, I // k, E // k, d, K, f"a 1/{k}-scale {workload} graph (same generator and degree law)"
+
+
+def cpu_reference_step_rate(workload: str, steps: int, warmup: int):
     """Time the oracle's restatement of lightgcn.py's epoch iteration on the host cores (bounded sample)."""
     import torch
     from oracle import lightgcn_ref
@@ -124,7 +147,7 @@ def cpu_reference_step_rate(sample_cfg: str, steps: int, warmup: int):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    U, I, E, d, K = synth.CONFIGS[sample_cfg]
+    U, I, E, d, K, what = cpu_sample_shape(workload)
     inter = synth.power_law_bipartite(U, I, E, seed=1001)
     pu, pi = torch.from_numpy(inter.users), torch.from_numpy(inter.items)
     ei = build_edge_index(pu, pi, U)
@@ -144,17 +167,16 @@ def cpu_reference_step_rate(sample_cfg: str, steps: int, warmup: int):
         if s >= warmup:
             times.append(dt)
     per_step = sum(times) / len(times)
-    return E / per_step, per_step, cores, (f"{steps} full step(s) of lightgcn.py's epoch loop (PyG LGConv restated, oracle/lightgcn_ref.py) on the "
-                                           f"{sample_cfg} graph: U={U} I={I} E={E} d={d} K={K}, torch CPU fp32, {cores} threads")
+    return E / per_step, per_step, cores, (f"{steps} full step(s) of lightgcn.py's epoch loop (PyG LGConv restated, oracle/lightgcn_ref.py) on "
+                                           f"{what}: U={U} I={I} E={E} d={d} K={K}, torch CPU fp32, {cores} threads")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_cfg = "cfg1"
     steps, warmup = max(1, min(args.steps, 3)), 1
-    value, per_step, cores, sample = cpu_reference_step_rate(sample_cfg, steps, warmup)
+    value, per_step, cores, sample = cpu_reference_step_rate(args.workload, steps, warmup)
     U, I, E, d, K = __import__("recommendation_b200.synth", fromlist=["CONFIGS"]).CONFIGS[args.workload]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
@@ -281,6 +303,7 @@ def run_ours(args):
         clk["note"] = clk_note
 
     total_ms = sum(step_ms)
+    launches_per_step = trainer.launches_per_step
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -293,31 +316,49 @@ def run_ours(args):
     # ---- e2e through the reference-facing API with host buffers (rank-local at N>1 is not defined: N=1 only) ----
     e2e = None
     if world == 1 and not args.no_e2e:
+        from recommendation_b200 import functional as F_
+        from recommendation_b200.lightgcn import bpr_step_loss
+
+        del trainer  # free the device-resident arm's buffers (cfg5: ~35 GB) before the public-API arm allocates its own
+        torch.cuda.empty_cache()
         torch.manual_seed(1)
         model = LightGCN(U, I, d, K).to(dev)
-        opt = torch.optim.Adam(model.parameters(), lr=0.01)
+        opt = torch.optim.Adam(model.parameters(), lr=0.01, fused=True)
         ei = build_edge_index(users, items, U)
-        cfg = {"n_neg": 1, "reg_weight": 1e-4, "loss_type": "bpr"}
         pu_h, pi_h = users.cpu().pin_memory(), items.cpu().pin_memory()
         loss_h = torch.empty((), dtype=torch.float32).pin_memory()
         model(ei)  # builds + caches the CSR (the reference normalises on every call; here once)
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
         e2e_steps = max(1, min(args.steps, 10))
         for it in range(2 + e2e_steps):
             if it == 2:
                 torch.cuda.synchronize(); t0 = time.perf_counter()
-            pu_d = pu_h.to(dev, non_blocking=True); pi_d = pi_h.to(dev, non_blocking=True)
-            loss = train_step(model, opt, ei, pu_d, pi_d, I, cfg, seed=1234, step=it)
+            # the step's index tensors come from pinned host memory on a copy stream; the propagation (which does not
+            # need them) runs on the main stream meanwhile
+            with torch.cuda.stream(copy_stream):
+                pu_d = pu_h.to(dev, non_blocking=True); pi_d = pi_h.to(dev, non_blocking=True)
+                copied = torch.cuda.Event(); copied.record(copy_stream)
+            opt.zero_grad(set_to_none=True)
+            user_emb, item_emb = model(ei)
+            neg = F_.sample_negatives(E, I, seed=1234, offset=it, device=dev)
+            main.wait_event(copied)
+            pu_d.record_stream(main); pi_d.record_stream(main)
+            loss = bpr_step_loss(user_emb, item_emb, pu_d, pi_d, neg, 1e-4)
+            loss.backward()
+            opt.step()
             loss_h.copy_(loss.detach(), non_blocking=True)
             torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / e2e_steps
         e2e = {"value": E / dt, "unit": UNIT, "h2d_bytes_per_step": int(pu_h.numel() * 8 * 2), "d2h_bytes_per_step": 4,
                "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "api": "LightGCN.forward(edge_index) + bpr_step_loss + loss.backward() + torch.optim.Adam.step()"}
+               "api": "LightGCN.forward(edge_index) + sample_negatives + bpr_step_loss + loss.backward() + torch.optim.Adam(fused=True).step(); "
+                      "index tensors copied from pinned host memory on a side stream every step, loss read back to the host"}
         del model, opt
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, per_step, cores, sample = cpu_reference_step_rate("cfg1", 2, 1)
+        v, per_step, cores, sample = cpu_reference_step_rate(args.workload, 2, 1)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step": per_step * 1e3}
 
     if rank == 0:
@@ -333,9 +374,11 @@ def run_ours(args):
                        "wall_s_timed_region": wall},
             "clocks": clk,
             "e2e": e2e,
-            "gpu_launches": int(trainer.launches_per_step * args.steps),
+            "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "hbm", "kernel": "spmm_csr_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic(args.workload) if world == 1 else None,
+                         "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": spmm_avg_us,
                          "launches_timed": len(spmm_us) * K},
             "cpu_baseline": cpu_baseline,

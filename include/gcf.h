@@ -186,6 +186,9 @@ int gcf_sample_negatives(uint64_t seed, uint64_t offset, const int64_t* users, i
 
 #define GCF_BPR_LOG_EPS_SIGMOID 0 /* -log(eps + sigmoid(x))      ncl.py:116-120, mhcn.py:35-39 */
 #define GCF_BPR_SOFTPLUS        1 /* -log(sigmoid(x))            lightgcn.py:108, gcl.py:221   */
+#define GCF_BPR_RAW_SCORE       2 /* gcf_bpr_fwd only: coef_out[t] = x_t (the score itself), loss_out = the reg terms.
+                                     For tables sharded along the feature dimension: every rank holds d/G columns, the
+                                     partial scores are summed across ranks and gcf_bpr_coef_from_scores applies the loss. */
 #define GCF_REDUCE_MEAN 0
 #define GCF_REDUCE_SUM  1         /* diffnet.py:1113 */
 
@@ -207,6 +210,12 @@ int gcf_bpr_bwd(const float* user_emb, int64_t ld_user, const float* item_emb, i
                 const int64_t* u_idx, const int64_t* p_idx, const int64_t* n_idx, int64_t n_triples, int32_t n_negs,
                 const float* coef, const float* grad_out, float reg_u, float reg_p, float reg_n,
                 float* g_user, int64_t ldg_user, float* g_item, int64_t ldg_item, gcf_stream_t stream);
+
+/* loss = reduce_t l(x_t), coef[t] = dl/dx_t (already divided by n for the mean) from complete scores x[n]:
+ * the pointwise half of gcf_bpr_fwd, used after the partial scores of feature-sharded tables were all-reduced. */
+int gcf_bpr_coef_from_scores(const float* x, int64_t n_triples, int32_t variant, float eps, int32_t reduction,
+                             float* loss_out, float* coef_out, void* workspace, size_t workspace_bytes,
+                             gcf_stream_t stream);
 
 /* Forward and backward in ONE pass (the three row gathers are done once): the loss is a scalar, so its upstream
  * gradient is known before the backward starts (lightgcn.py:119 `loss.backward()`: 1) and is passed as the host

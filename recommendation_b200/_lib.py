@@ -16,7 +16,7 @@ LIB_PATH = Path(__file__).with_name("libgcf.so")
 MAX_ADDENDS = 8
 EPILOGUE_NONE, EPILOGUE_L2NORM = 0, 1
 NORM_NONE, NORM_SYM, NORM_ROW = 0, 1, 2
-BPR_LOG_EPS_SIGMOID, BPR_SOFTPLUS = 0, 1
+BPR_LOG_EPS_SIGMOID, BPR_SOFTPLUS, BPR_RAW_SCORE = 0, 1, 2
 REDUCE_MEAN, REDUCE_SUM = 0, 1
 
 
@@ -71,6 +71,8 @@ _SIGNATURES = {
                               c_void_p, c_size_t, c_void_p]),
     "gcf_bpr_bwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                               c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "gcf_bpr_coef_from_scores": (c_int32, [c_void_p, c_int64, c_int32, c_float, c_int32, c_void_p, c_void_p, c_void_p, c_size_t,
+                                           c_void_p]),
     "gcf_bpr_fwd_bwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                   c_int32, c_float, c_int32, c_float, c_float, c_float, c_float, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),

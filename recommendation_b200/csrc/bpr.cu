@@ -10,6 +10,7 @@
 // backward, accumulate the user gradient in registers: one red.global.add.v4.f32 per run instead of
 // one per triple.  The [T, d] gathered tensors of the reference are never materialised.
 #include "common.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace gcf {
@@ -47,7 +48,10 @@ __device__ __forceinline__ float pair_reduce(float a, float b, int sl, unsigned 
 // term, far inside the 1e-3 parity tolerance, and ~5x fewer instructions than expf/logf/log1pf -- the forward
 // kernel was issue-bound on the libm sequences (ncu r01: 102 M instructions for 1.03 M triples).
 __device__ __forceinline__ void bpr_pointwise(int variant, float eps, float x, float& loss, float& dl) {
-  if (variant == GCF_BPR_LOG_EPS_SIGMOID) {
+  if (variant == GCF_BPR_RAW_SCORE) {  // feature-sharded tables: emit the partial score, the loss is applied after the all-reduce
+    loss = 0.f;
+    dl = x;
+  } else if (variant == GCF_BPR_LOG_EPS_SIGMOID) {
     const float sg = __fdividef(1.f, 1.f + __expf(-x));
     loss = -__logf(eps + sg);
     dl = -__fdividef(sg * (1.f - sg), eps + sg);
@@ -160,6 +164,30 @@ __global__ void __launch_bounds__(256) bpr_reduce_kernel(const double* __restric
     __syncthreads();
   }
   if (threadIdx.x == 0) *loss_out = (float)sh[0];
+}
+
+// coef[t] = w * l'(x[t]),  block partial of sum_t w * l(x[t])   (x = complete scores, e.g. after an all-reduce of the
+// per-feature-slice partial scores)
+__global__ void __launch_bounds__(256)
+bpr_coef_kernel(const float* __restrict__ x, long long n, int variant, float eps, float w_loss, float* __restrict__ coef,
+                double* __restrict__ block_partials) {
+  double local = 0.0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    float loss, dl;
+    bpr_pointwise(variant, eps, x[t], loss, dl);
+    coef[t] = dl * w_loss;
+    local += (double)(loss * w_loss);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+  __shared__ double warp_part[8];
+  if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += warp_part[w];
+    block_partials[blockIdx.x] = s;
+  }
 }
 
 template <int LPR, int VPL, bool GUARD>
@@ -420,6 +448,7 @@ static inline long long bpr_blocks(long long n, int lpr) {
 
 static inline int lpr_for(int d) {
   switch (d) {
+    case 8: return 2;
     case 16: return 4;
     case 32: return 8;
     case 64: return 16;
@@ -442,6 +471,7 @@ extern "C" size_t gcf_bpr_workspace_bytes(int64_t n_triples) {
 #define GCF_BPR_DISPATCH(KERNEL, ...)                                                            \
   do {                                                                                           \
     switch (d) {                                                                                 \
+      case 8:   KERNEL<2, 1, false, 4><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;        \
       case 16:  KERNEL<4, 1, false, 4><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;        \
       case 32:  KERNEL<8, 1, false, 4><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;        \
       case 64:  KERNEL<16, 1, false, 4><<<grid, kBprThreads, 0, st>>>(__VA_ARGS__); break;       \
@@ -477,7 +507,9 @@ extern "C" int gcf_bpr_fwd(const float* user_emb, int64_t ld_user, const float* 
   int rc = bpr_check("gcf_bpr_fwd", user_emb, ld_user, item_emb, ld_item, d, u_idx, p_idx, n_idx, n_triples, n_negs);
   if (rc != GCF_OK) return rc;
   GCF_REQUIRE(loss_out != nullptr && (n_triples == 0 || coef_out != nullptr), "gcf_bpr_fwd: null outputs");
-  GCF_REQUIRE(variant == GCF_BPR_LOG_EPS_SIGMOID || variant == GCF_BPR_SOFTPLUS, "gcf_bpr_fwd: bad variant");
+  GCF_REQUIRE(variant == GCF_BPR_LOG_EPS_SIGMOID || variant == GCF_BPR_SOFTPLUS || variant == GCF_BPR_RAW_SCORE,
+              "gcf_bpr_fwd: bad variant");
+  GCF_REQUIRE(variant != GCF_BPR_RAW_SCORE || reduction == GCF_REDUCE_SUM, "gcf_bpr_fwd: raw scores need reduction = sum");
   GCF_REQUIRE(reduction == GCF_REDUCE_MEAN || reduction == GCF_REDUCE_SUM, "gcf_bpr_fwd: bad reduction");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n_triples == 0) {
@@ -560,6 +592,7 @@ extern "C" int gcf_bpr_fwd_bwd(const float* user_emb, int64_t ld_user, const flo
 #define GCF_BPR_FUSED_ARGS user_emb, ld_user, item_emb, ld_item, dvec, u_idx, p_idx, n_idx, n_triples, n_negs, variant, eps, \
                            w_loss, reg_u, reg_p, reg_n, grad_scale, coef_out, partials, g_user, ldg_user, g_item, ldg_item
   switch (d) {
+    case 8:   bpr_fused_kernel<2, 1, false, 2><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
     case 16:  bpr_fused_kernel<4, 1, false, 2><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
     case 32:  bpr_fused_kernel<8, 1, false, 2><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
     case 64:  bpr_fused_kernel<16, 1, false, 2><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
@@ -574,6 +607,33 @@ extern "C" int gcf_bpr_fwd_bwd(const float* user_emb, int64_t ld_user, const flo
 #undef GCF_BPR_FUSED_ARGS
   GCF_LAUNCH_CHECK("bpr_fused_kernel");
   bpr_reduce_kernel<<<1, 256, 0, st>>>(partials, grid, loss_out);
+  GCF_LAUNCH_CHECK("bpr_reduce_kernel");
+  return GCF_OK;
+}
+
+extern "C" int gcf_bpr_coef_from_scores(const float* x, int64_t n_triples, int32_t variant, float eps, int32_t reduction,
+                                        float* loss_out, float* coef_out, void* workspace, size_t workspace_bytes,
+                                        gcf_stream_t stream) {
+  GCF_REQUIRE(n_triples >= 0, "gcf_bpr_coef_from_scores: negative n_triples");
+  GCF_REQUIRE(loss_out != nullptr, "gcf_bpr_coef_from_scores: null loss_out");
+  GCF_REQUIRE(variant == GCF_BPR_LOG_EPS_SIGMOID || variant == GCF_BPR_SOFTPLUS, "gcf_bpr_coef_from_scores: bad variant");
+  GCF_REQUIRE(reduction == GCF_REDUCE_MEAN || reduction == GCF_REDUCE_SUM, "gcf_bpr_coef_from_scores: bad reduction");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_triples == 0) {
+    GCF_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+    return GCF_OK;
+  }
+  GCF_REQUIRE(x != nullptr && coef_out != nullptr, "gcf_bpr_coef_from_scores: null arrays");
+  const long long grid = std::max<long long>(1, std::min<long long>(cdiv(n_triples, 256), (long long)sm_count() * 8));
+  const size_t need = align_up((size_t)grid * sizeof(double));
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("gcf_bpr_coef_from_scores: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return GCF_EWORKSPACE;
+  }
+  const float w_loss = (reduction == GCF_REDUCE_MEAN) ? (1.f / (float)n_triples) : 1.f;
+  bpr_coef_kernel<<<(unsigned)grid, 256, 0, st>>>(x, n_triples, variant, eps, w_loss, coef_out, static_cast<double*>(workspace));
+  GCF_LAUNCH_CHECK("bpr_coef_kernel");
+  bpr_reduce_kernel<<<1, 256, 0, st>>>(static_cast<double*>(workspace), grid, loss_out);
   GCF_LAUNCH_CHECK("bpr_reduce_kernel");
   return GCF_OK;
 }

@@ -318,6 +318,7 @@ extern "C" int gcf_spmm_csr_f32(const gcf_csr_t* A, int32_t d, const float* X, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int dvec = d / 4;
   switch (d) {
+    case 8:  return launch<2, 1, 2, false, 4>(A, X, ldx, dvec, ep, lp, st);  // feature-sharded slices (d / 8 GPUs)
     case 16: return launch<4, 1, 4, false, 4>(A, X, ldx, dvec, ep, lp, st);
     case 32: return launch<8, 1, 8, false, 3>(A, X, ldx, dvec, ep, lp, st);
     case 64:  // variants are tuning knobs (UNR loads in flight x resident blocks), same arithmetic

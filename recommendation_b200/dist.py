@@ -170,16 +170,21 @@ class ShardedLightGCNTrainer:
         # ---- this rank's triples, in gathered-position space ----
         lo, hi = plan.triple_range(self.n_edges, self.rank)
         self.n_triples = hi - lo
-        self.pos_u = plan.gathered_pos(users[lo:hi].to(torch.int64)).contiguous()
-        self.pos_i = plan.gathered_pos(items[lo:hi].to(torch.int64) + n_users).contiguous()
+        pos_u = plan.gathered_pos(users[lo:hi].to(torch.int64))
+        pos_i = plan.gathered_pos(items[lo:hi].to(torch.int64) + n_users)
+        # user-major order inside the rank's slice: the fused BPR kernel keeps the user row / gradient in registers
+        # over a run (the order of the triples is free: the loss is a mean over all of them)
+        self.order = torch.argsort(pos_u * plan.n_padded + pos_i) if self.n_triples > 1 else None
+        if self.order is not None:
+            pos_u, pos_i = pos_u[self.order], pos_i[self.order]
+        self.pos_u, self.pos_i = pos_u.contiguous(), pos_i.contiguous()
         self.neg_raw = torch.empty(max(self.n_triples, 1), dtype=torch.int64, device=dev)
-        self.coef = torch.empty(max(self.n_triples, 1), dtype=torch.float32, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.bpr_ws_bytes = lib.gcf_bpr_workspace_bytes(self.n_triples)
         self.bpr_ws = torch.empty(self.bpr_ws_bytes, dtype=torch.uint8, device=dev)
         self.triple_offset = lo
         self.step_count = 0
-        self.launches_per_step = 2 * n_layers + 5
+        self.launches_per_step = 2 * n_layers + 4
         self.collectives_per_step = 2 * n_layers + 2
 
     # -------------------------------------------------------------------------------------------------
@@ -235,19 +240,18 @@ class ShardedLightGCNTrainer:
             neg_raw = self.neg_raw[: self.n_triples]
         else:
             neg_raw = neg_items.to(torch.int64)
+            if self.order is not None:
+                neg_raw = neg_raw[self.order]
         neg = plan.gathered_pos(neg_raw + self.n_users).contiguous()
         w = 1.0 / self.n_edges
-        # per-rank partial of the global mean: reduction = sum with coefficients pre-scaled by 1/E
-        _lib.check(lib.gcf_bpr_fwd(_lib.ptr(self.final_full), d, _lib.ptr(self.final_full), d, d, _lib.ptr(self.pos_u),
-                                   _lib.ptr(self.pos_i), _lib.ptr(neg), self.n_triples, 1, _lib.BPR_SOFTPLUS, 0.0,
-                                   _lib.REDUCE_SUM, self.reg / w, self.reg / w, 0.0, _lib.ptr(self.loss), _lib.ptr(self.coef),
-                                   _lib.ptr(self.bpr_ws), self.bpr_ws_bytes, st), "gcf_bpr_fwd")
+        # per-rank partial of the global mean: reduction = sum, loss and gradients scaled by 1/E afterwards / inside;
+        # forward and backward in one pass over the triples (rows gathered once)
         self.g_full.zero_()
-        gscale = torch.full((), w, dtype=torch.float32, device=self.dev)
-        _lib.check(lib.gcf_bpr_bwd(_lib.ptr(self.final_full), d, _lib.ptr(self.final_full), d, d, _lib.ptr(self.pos_u),
-                                   _lib.ptr(self.pos_i), _lib.ptr(neg), self.n_triples, 1, _lib.ptr(self.coef), _lib.ptr(gscale),
-                                   self.reg / w, self.reg / w, 0.0, _lib.ptr(self.g_full), d, _lib.ptr(self.g_full), d, st),
-                   "gcf_bpr_bwd")
+        _lib.check(lib.gcf_bpr_fwd_bwd(_lib.ptr(self.final_full), d, _lib.ptr(self.final_full), d, d, _lib.ptr(self.pos_u),
+                                       _lib.ptr(self.pos_i), _lib.ptr(neg), self.n_triples, 1, _lib.BPR_SOFTPLUS, 0.0,
+                                       _lib.REDUCE_SUM, self.reg / w, self.reg / w, 0.0, w, _lib.ptr(self.loss), None,
+                                       _lib.ptr(self.g_full), d, _lib.ptr(self.g_full), d, _lib.ptr(self.bpr_ws),
+                                       self.bpr_ws_bytes, st), "gcf_bpr_fwd_bwd")
         dist.reduce_scatter_tensor(self.g_loc, self.g_full, op=dist.ReduceOp.SUM)
 
         # ---- backward propagation: G(k) = A G(k+1) + g,  G(K) = g  (scale 1: 'sum' combination) ----
