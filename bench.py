@@ -243,15 +243,35 @@ def run_ours(args):
         table = torch.empty(n, d, device=dev)
         torch.nn.init.xavier_uniform_(table[:U]); torch.nn.init.xavier_uniform_(table[U:])
         trainer = FusedLightGCNTrainer(graph, U, I, table, users, items, n_layers=K, lr=0.01, reg_weight=1e-4, seed=1234)
-        nnz, spmm_rows = graph.nnz, n
+        nnz, spmm_rows, spmm_d = graph.nnz, n, d
         parallelism = "single GPU"
         scaling = "weak"
     else:
-        from recommendation_b200.dist import ShardedLightGCNTrainer
+        from recommendation_b200.dist import FeatureShardedLightGCNTrainer, ShardedLightGCNTrainer
 
-        trainer = ShardedLightGCNTrainer(users, items, U, I, d=d, n_layers=K, lr=0.01, reg_weight=1e-4, seed=1234)
-        nnz, spmm_rows = trainer.local_nnz, trainer.rows_per_rank
-        parallelism = f"row-sharded tables + adjacency rows over {world} GPUs, one NCCL all-gather per layer"
+        # layout: F feature shards x R = G / F row shards.  F = G: no collective in the propagation at all (one all-reduce
+        # of E floats per step); F = 1: the row-sharded layout (one all-gather of d-wide rows per layer); in between: the
+        # all-gathers run inside row groups on d/F-wide rows.  Default picked from the measured r01 sweep.
+        F = args.feature_shards
+        if F <= 0:
+            F = {2: 2, 4: 2, 8: 4}.get(world, 1)
+        while F > 1 and (world % F != 0 or d % F != 0 or (d // F) % 4 != 0 or d // F < 8):
+            F //= 2
+        if F == world:
+            trainer = FeatureShardedLightGCNTrainer(users, items, U, I, d=d, n_layers=K, lr=0.01, reg_weight=1e-4, seed=1234)
+            nnz, spmm_rows, spmm_d = trainer.local_nnz, n, trainer.dg
+            parallelism = (f"feature-sharded over {world} GPUs: every rank owns d/G = {trainer.dg} columns of all [N, d] tables, "
+                           f"propagation / Adam without any collective, ONE NCCL all-reduce of E fp32 partial scores per step")
+        else:
+            trainer = ShardedLightGCNTrainer(users, items, U, I, d=d, n_layers=K, lr=0.01, reg_weight=1e-4, seed=1234,
+                                             feature_shards=F)
+            nnz, spmm_rows, spmm_d = trainer.local_nnz, trainer.rows_per_rank, trainer.d
+            if F == 1:
+                parallelism = f"row-sharded tables + adjacency rows over {world} GPUs, one NCCL all-gather per propagation layer"
+            else:
+                parallelism = (f"2-D: {world // F} row shards x {F} feature shards; tables + adjacency rows row-sharded inside each row "
+                               f"group (one NCCL all-gather of d/{F}-wide rows per propagation layer), BPR scores completed by one "
+                               f"all-reduce of E/{world // F} floats inside each feature group")
         scaling = "strong"
 
     def barrier():
@@ -310,7 +330,7 @@ def run_ours(args):
         total_ms = float(t.item())
     value = E * args.steps / (total_ms * 1e-3)
     spmm_avg_us = sum(spmm_us) / max(len(spmm_us), 1)
-    alg_bytes = spmm_algorithmic_bytes(spmm_rows, n, nnz, d)
+    alg_bytes = spmm_algorithmic_bytes(spmm_rows, n, nnz, spmm_d)  # per launch on ONE rank
     achieved = alg_bytes / (spmm_avg_us * 1e-6) / 1e9 if spmm_avg_us > 0 else 0.0
 
     # ---- e2e through the reference-facing API with host buffers (rank-local at N>1 is not defined: N=1 only) ----
@@ -395,6 +415,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", default=os.environ.get("GCF_BENCH_WORKLOAD", "cfg5"))
+    ap.add_argument("--feature-shards", type=int, default=int(os.environ.get("GCF_BENCH_FEATURE_SHARDS", "0")),
+                    help="N > 1 only: F feature shards x N/F row shards (1 = row-sharded, N = feature-sharded, 0 = measured default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

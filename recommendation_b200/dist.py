@@ -1,4 +1,6 @@
-"""Row-sharded LightGCN training over G GPUs of one NVSwitch box (north star "2/4/8-GPU runs").
+"""LightGCN training over G GPUs of one NVSwitch box (north star "2/4/8-GPU runs"): the row-sharded
+layout the north star describes (ShardedLightGCNTrainer, below) and a feature-sharded layout that needs no collective
+in the propagation at all (FeatureShardedLightGCNTrainer, end of file; measured comparison in DESIGN.md section 6).
 
 One process per GPU (torch.distributed, NCCL).  The reference has no distributed code at all; this is the
 scaling path of the same step as lightgcn.FusedLightGCNTrainer:
@@ -106,11 +108,34 @@ class ShardedLightGCNTrainer:
 
     def __init__(self, users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int, *, d: int = 64,
                  n_layers: int = 3, lr: float = 0.01, reg_weight: float = 1e-4, seed: int = 0,
-                 init_table: Optional[torch.Tensor] = None):
+                 init_table: Optional[torch.Tensor] = None, feature_shards: int = 1):
+        """feature_shards = F > 1 gives the 2-D layout: the G ranks form R = G / F row groups x F feature groups; a rank
+        owns N/R rows x d/F columns.  All-gathers / reduce-scatters run inside a row group (ranks with the same feature
+        slice) on d/F-wide rows -- F times less volume -- and the BPR scores are completed by one all-reduce of E/R floats
+        inside the feature group (see FeatureShardedLightGCNTrainer for that half)."""
         if not dist.is_initialized():
             raise RuntimeError("ShardedLightGCNTrainer needs an initialised torch.distributed process group")
         self.lib = _lib.load()
-        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        g_rank, g_world = dist.get_rank(), dist.get_world_size()
+        if feature_shards < 1 or g_world % feature_shards != 0:
+            raise ValueError(f"feature_shards={feature_shards} must divide the world size {g_world}")
+        self.fs = F = feature_shards
+        self.world = R = g_world // F          # size of a row group: the sharding factor of the node dimension
+        self.rank = g_rank // F                # this rank's row shard
+        self.feat_rank = g_rank % F
+        self.row_group = self.feat_group = None
+        if F > 1:  # every rank creates every group, in the same order
+            for f in range(F):
+                grp = dist.new_group([r * F + f for r in range(R)])
+                if f == self.feat_rank:
+                    self.row_group = grp
+            for r in range(R):
+                grp = dist.new_group([r * F + f for f in range(F)])
+                if r == self.rank:
+                    self.feat_group = grp
+        d_full = d
+        lo_c, hi_c = feature_slice(d_full, F, self.feat_rank)
+        d = hi_c - lo_c                        # local width: everything below works on [*, d/F] matrices
         dev = users.device
         if not users.is_cuda:
             raise RuntimeError("ShardedLightGCNTrainer: tensors must be on the rank's CUDA device")
@@ -145,11 +170,11 @@ class ShardedLightGCNTrainer:
 
         # ---- parameters / optimiser state: local rows only ----
         if init_table is not None:
-            self.table = shard_table(init_table.to(dev), plan, self.rank).contiguous()
+            self.table = shard_table(init_table.to(dev)[:, lo_c:hi_c].contiguous(), plan, self.rank).contiguous()
         else:
-            gen = torch.Generator(device=dev); gen.manual_seed(seed + 17)
-            bound_u = (6.0 / (n_users + d)) ** 0.5   # xavier_uniform_ bounds of the two reference tables
-            bound_i = (6.0 / (n_items + d)) ** 0.5
+            gen = torch.Generator(device=dev); gen.manual_seed(seed + 17 + 1000 * self.feat_rank)
+            bound_u = (6.0 / (n_users + d_full)) ** 0.5   # xavier_uniform_ bounds of the two reference tables
+            bound_i = (6.0 / (n_items + d_full)) ** 0.5
             nodes = plan.local_nodes(self.rank, dev)
             t = (torch.rand(n_loc, d, device=dev, generator=gen) * 2 - 1)
             scale = torch.where(nodes < n_users, bound_u, bound_i).to(torch.float32)
@@ -184,8 +209,11 @@ class ShardedLightGCNTrainer:
         self.bpr_ws = torch.empty(self.bpr_ws_bytes, dtype=torch.uint8, device=dev)
         self.triple_offset = lo
         self.step_count = 0
-        self.launches_per_step = 2 * n_layers + 4
-        self.collectives_per_step = 2 * n_layers + 2
+        self.scores = torch.empty(max(self.n_triples, 1), dtype=torch.float32, device=dev) if F > 1 else None
+        self.coef = torch.empty(max(self.n_triples, 1), dtype=torch.float32, device=dev) if F > 1 else None
+        self.loss_reg = torch.zeros((), dtype=torch.float32, device=dev)
+        self.launches_per_step = 2 * n_layers + (4 if F == 1 else 7)
+        self.collectives_per_step = 2 * n_layers + 2 + (1 if F > 1 else 0)
 
     # -------------------------------------------------------------------------------------------------
     def _slot(self, buf: torch.Tensor) -> torch.Tensor:
@@ -217,23 +245,25 @@ class ShardedLightGCNTrainer:
             spmm_marks.append((e0, e1, 1))
 
         # ---- forward: E0 gathered, then K SpMM with K-1 more gathers ----
+        rg = self.row_group
         self._slot(self.full[0]).copy_(self.table)
-        dist.all_gather_into_tensor(self.full[0], self._slot(self.full[0]))
+        dist.all_gather_into_tensor(self.full[0], self._slot(self.full[0]), group=rg)
         final_loc = self._slot(self.final_full)
         for k in range(1, K + 1):
             if k < K:
                 y = self._slot(self.full[k])
                 timed_spmm(self.full[k - 1], y, None, 1.0, 1.0, [], [])
-                dist.all_gather_into_tensor(self.full[k], y)
+                dist.all_gather_into_tensor(self.full[k], y, group=rg)
             else:  # last layer: final = sum_k E(k) (lightgcn.py:26), E(K) itself is not stored
                 adds = [self._slot(self.full[q]) for q in range(K)]
                 timed_spmm(self.full[K - 1], None, final_loc, 1.0, 1.0, adds, [1.0] * K)
-        dist.all_gather_into_tensor(self.final_full, final_loc)
+        dist.all_gather_into_tensor(self.final_full, final_loc, group=rg)
 
         # ---- loss on this rank's triples ----
         if neg_items is None:
             # one Philox stream per (seed, rank, step): rank in the high word of `offset` (it perturbs the key),
             # step in the low word (a counter word)
+            # (self.rank = the row shard: identical for the ranks of a feature group, which share the triples)
             _lib.check(lib.gcf_sample_negatives(self.seed, (self.rank << 32) | self.step_count, None, self.n_triples, 1,
                                                 self.n_items, None, None, 1, _lib.ptr(self.neg_raw), st),
                        "gcf_sample_negatives")
@@ -244,27 +274,43 @@ class ShardedLightGCNTrainer:
                 neg_raw = neg_raw[self.order]
         neg = plan.gathered_pos(neg_raw + self.n_users).contiguous()
         w = 1.0 / self.n_edges
-        # per-rank partial of the global mean: reduction = sum, loss and gradients scaled by 1/E afterwards / inside;
-        # forward and backward in one pass over the triples (rows gathered once)
+        # per-rank partial of the global mean: reduction = sum, loss and gradients scaled by 1/E afterwards / inside
         self.g_full.zero_()
-        _lib.check(lib.gcf_bpr_fwd_bwd(_lib.ptr(self.final_full), d, _lib.ptr(self.final_full), d, d, _lib.ptr(self.pos_u),
-                                       _lib.ptr(self.pos_i), _lib.ptr(neg), self.n_triples, 1, _lib.BPR_SOFTPLUS, 0.0,
-                                       _lib.REDUCE_SUM, self.reg / w, self.reg / w, 0.0, w, _lib.ptr(self.loss), None,
-                                       _lib.ptr(self.g_full), d, _lib.ptr(self.g_full), d, _lib.ptr(self.bpr_ws),
-                                       self.bpr_ws_bytes, st), "gcf_bpr_fwd_bwd")
-        dist.reduce_scatter_tensor(self.g_loc, self.g_full, op=dist.ReduceOp.SUM)
+        tables = (_lib.ptr(self.final_full), d, _lib.ptr(self.final_full), d, d, _lib.ptr(self.pos_u), _lib.ptr(self.pos_i),
+                  _lib.ptr(neg), self.n_triples, 1)
+        if self.fs == 1:
+            # forward and backward in one pass over the triples (rows gathered once)
+            _lib.check(lib.gcf_bpr_fwd_bwd(*tables, _lib.BPR_SOFTPLUS, 0.0, _lib.REDUCE_SUM, self.reg / w, self.reg / w, 0.0, w,
+                                           _lib.ptr(self.loss), None, _lib.ptr(self.g_full), d, _lib.ptr(self.g_full), d,
+                                           _lib.ptr(self.bpr_ws), self.bpr_ws_bytes, st), "gcf_bpr_fwd_bwd")
+            loss_local = self.loss * w
+        else:
+            # partial scores on the local columns -> all-reduce inside the feature group -> loss -> local gradients
+            _lib.check(lib.gcf_bpr_fwd(*tables, _lib.BPR_RAW_SCORE, 0.0, _lib.REDUCE_SUM, self.reg / w, self.reg / w, 0.0,
+                                       _lib.ptr(self.loss_reg), _lib.ptr(self.scores), _lib.ptr(self.bpr_ws), self.bpr_ws_bytes, st),
+                       "gcf_bpr_fwd")
+            dist.all_reduce(self.scores, op=dist.ReduceOp.SUM, group=self.feat_group)
+            _lib.check(lib.gcf_bpr_coef_from_scores(_lib.ptr(self.scores), self.n_triples, _lib.BPR_SOFTPLUS, 0.0, _lib.REDUCE_SUM,
+                                                    _lib.ptr(self.loss), _lib.ptr(self.coef), _lib.ptr(self.bpr_ws),
+                                                    self.bpr_ws_bytes, st), "gcf_bpr_coef_from_scores")
+            gscale = torch.full((), w, dtype=torch.float32, device=self.dev)
+            _lib.check(lib.gcf_bpr_bwd(*tables, _lib.ptr(self.coef), _lib.ptr(gscale), self.reg / w, self.reg / w, 0.0,
+                                       _lib.ptr(self.g_full), d, _lib.ptr(self.g_full), d, st), "gcf_bpr_bwd")
+            # the pointwise part is replicated inside the feature group: count it once
+            loss_local = (self.loss / self.fs + self.loss_reg) * w
+        dist.reduce_scatter_tensor(self.g_loc, self.g_full, op=dist.ReduceOp.SUM, group=rg)
 
         # ---- backward propagation: G(k) = A G(k+1) + g,  G(K) = g  (scale 1: 'sum' combination) ----
         cur_full = self.gk_full[0]
         self._slot(cur_full).copy_(self.g_loc)
-        dist.all_gather_into_tensor(cur_full, self._slot(cur_full))
+        dist.all_gather_into_tensor(cur_full, self._slot(cur_full), group=rg)
         which = 1
         for k in range(K - 1, -1, -1):
             if k > 0:
                 nxt = self.gk_full[which]
                 out = self._slot(nxt)
                 timed_spmm(cur_full, None, out, 1.0, 1.0, [self.g_loc], [1.0])
-                dist.all_gather_into_tensor(nxt, out)
+                dist.all_gather_into_tensor(nxt, out, group=rg)
                 cur_full = nxt
                 which ^= 1
             else:
@@ -272,7 +318,7 @@ class ShardedLightGCNTrainer:
 
         _lib.check(lib.gcf_adam_step(_lib.ptr(self.table), _lib.ptr(self.g_x0), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
                                      self.table.numel(), self.lr, 0.9, 0.999, 1e-8, 0.0, 0, self.step_count, st), "gcf_adam_step")
-        loss = self.loss * w
+        loss = loss_local.clone()
         dist.all_reduce(loss, op=dist.ReduceOp.SUM)
         if marks is not None:
             marks.extend(spmm_marks)
@@ -282,5 +328,149 @@ class ShardedLightGCNTrainer:
         """[N, d] table in node order on every rank (for checks / evaluation)."""
         buf = torch.zeros(self.plan.n_padded, self.d, device=self.dev)
         self._slot(buf).copy_(self.table)
-        dist.all_gather_into_tensor(buf, self._slot(buf))
-        return unshard_table(buf, self.plan)
+        dist.all_gather_into_tensor(buf, self._slot(buf), group=self.row_group)
+        rows = unshard_table(buf, self.plan).contiguous()
+        if self.fs == 1:
+            return rows
+        parts = [torch.empty_like(rows) for _ in range(self.fs)]
+        dist.all_gather(parts, rows, group=self.feat_group)
+        return torch.cat(parts, dim=1)
+
+
+# =====================================================================================================
+# Feature-sharded layout: every rank holds ALL N rows but only d/G columns of every [N, d] matrix.
+# =====================================================================================================
+def feature_slice(d: int, world: int, rank: int) -> Tuple[int, int]:
+    """Columns [lo, hi) of the embedding dimension owned by `rank` (d must split into multiples of 4 floats)."""
+    if d % world != 0 or (d // world) % 4 != 0:
+        raise ValueError(f"feature sharding needs d/G to be a multiple of 4 (d={d}, G={world})")
+    dg = d // world
+    return rank * dg, (rank + 1) * dg
+
+
+class FeatureShardedLightGCNTrainer:
+    """The same full-batch step, parallelised over the embedding dimension.
+
+    The propagation is linear and acts on every feature column independently: E(k+1)[:, c] = A E(k)[:, c].  A rank
+    that owns columns [lo, hi) of the tables therefore runs all K layers forward and backward, and Adam, on its
+    [N, d/G] slice WITHOUT any exchange -- against (2K+1) all-gathers + 1 reduce-scatter of N*d*4 bytes in the
+    row-sharded layout.  The only coupling is the BPR score <u, p - n>, a sum over all d columns:
+
+        partial scores on the local columns (gcf_bpr_fwd, GCF_BPR_RAW_SCORE)      [E floats]
+        -> ONE all-reduce of E floats per step (0.4 GB at cfg 5, vs 30.7 GB above)
+        -> loss / dl/dx on the complete scores (gcf_bpr_coef_from_scores), identical on every rank
+        -> gradients w.r.t. the local columns (gcf_bpr_bwd), transpose propagation, Adam: local.
+
+    Costs: the CSR (int32 structure + fp32 values, 1.6 GB at cfg 5) and the triple index arrays are replicated, every
+    rank walks all nnz / all triples (with d/G-wide rows: 32 B at d = 64, G = 8), and the three row gathers of the loss
+    are done twice (score pass, gradient pass).  Negatives are drawn with the same Philox (seed, step) on every rank.
+    """
+
+    def __init__(self, users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int, *, d: int = 64,
+                 n_layers: int = 3, lr: float = 0.01, reg_weight: float = 1e-4, seed: int = 0,
+                 init_table: Optional[torch.Tensor] = None):
+        if not dist.is_initialized():
+            raise RuntimeError("FeatureShardedLightGCNTrainer needs an initialised torch.distributed process group")
+        if not users.is_cuda:
+            raise RuntimeError("FeatureShardedLightGCNTrainer: tensors must be on the rank's CUDA device")
+        self.lib = _lib.load()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.lo, self.hi = feature_slice(d, self.world, self.rank)
+        self.dg = self.hi - self.lo
+        dev = users.device
+        self.dev, self.d_full = dev, d
+        self.n_users, self.n_items, self.n = n_users, n_items, n_users + n_items
+        self.k, self.lr, self.reg, self.seed = n_layers, lr, reg_weight, seed
+        self.graph = CSRGraph.from_pairs(users, items, n_users, n_items, norm="sym")  # replicated operator
+        self.local_nnz = self.graph.nnz
+        self.rows_per_rank = self.n
+        n, dg = self.n, self.dg
+        if init_table is not None:
+            self.table = init_table.to(dev)[:, self.lo:self.hi].contiguous()
+        else:
+            gen = torch.Generator(device=dev); gen.manual_seed(seed * 1000 + 17 + self.rank)
+            t = torch.rand(n, dg, device=dev, generator=gen) * 2 - 1
+            t[:n_users] *= (6.0 / (n_users + d)) ** 0.5      # xavier_uniform_ bounds of the reference's two tables
+            t[n_users:] *= (6.0 / (n_items + d)) ** 0.5
+            self.table = t
+        pos_u, pos_i = users.to(torch.int64), items.to(torch.int64)
+        self.n_edges = self.n_triples = int(pos_u.numel())
+        self.order = torch.argsort(pos_u * n_items + pos_i) if self.n_triples > 1 else None  # user-major (see lightgcn.py)
+        if self.order is not None:
+            pos_u, pos_i = pos_u[self.order], pos_i[self.order]
+        self.pos_u, self.pos_i = pos_u.contiguous(), pos_i.contiguous()
+        new = lambda: torch.empty(n, dg, device=dev)
+        self.layers = [new() for _ in range(n_layers - 1)] + [None]
+        self.final, self.g_final, self.g_x0 = new(), new(), new()
+        self.ping = new() if n_layers > 1 else None
+        self.pong = new() if n_layers > 1 else None
+        self.exp_avg, self.exp_avg_sq = torch.zeros(n, dg, device=dev), torch.zeros(n, dg, device=dev)
+        self.neg = torch.empty(max(self.n_triples, 1), dtype=torch.int64, device=dev)
+        self.scores = torch.empty(max(self.n_triples, 1), dtype=torch.float32, device=dev)
+        self.coef = torch.empty(max(self.n_triples, 1), dtype=torch.float32, device=dev)
+        self.loss_reg = torch.zeros((), dtype=torch.float32, device=dev)
+        self.loss_pt = torch.zeros((), dtype=torch.float32, device=dev)
+        self.bpr_ws_bytes = self.lib.gcf_bpr_workspace_bytes(self.n_triples)
+        self.bpr_ws = torch.empty(self.bpr_ws_bytes, dtype=torch.uint8, device=dev)
+        self.ws, self.ws_bytes = self.graph.workspace(dg)
+        self.step_count = 0
+        # K fwd + K bwd SpMM, sampler, score pass + reduce, coef + reduce, gradient pass, adam
+        self.launches_per_step = 2 * n_layers + 7
+        self.collectives_per_step = 2  # E-float score all-reduce + scalar loss all-reduce
+
+    def step(self, neg_items: Optional[torch.Tensor] = None, marks: Optional[list] = None) -> torch.Tensor:
+        """One optimisation step; returns the (global) loss.  neg_items: optional pre-drawn item ids for ALL triples in
+        their original order (parity tests), identical on every rank."""
+        lib, st, g, dg, K, u = self.lib, _lib.current_stream(), self.graph, self.dg, self.k, self.n_users
+        self.step_count += 1
+        if marks is not None:
+            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            e0.record()
+        _lib.check(lib.gcf_propagate_fwd(g.struct_ref(), dg, K, _lib.ptr(self.table), _lib.ptr_array(self.layers),
+                                         _lib.ptr(self.final), 1.0, _lib.ptr(self.ws), self.ws_bytes, st), "gcf_propagate_fwd")
+        if marks is not None:
+            e1.record()
+        if neg_items is None:
+            _lib.check(lib.gcf_sample_negatives(self.seed, self.step_count, None, self.n_triples, 1, self.n_items, None, None, 1,
+                                                _lib.ptr(self.neg), st), "gcf_sample_negatives")
+            neg = self.neg
+        else:
+            neg = neg_items.to(torch.int64).reshape(-1)
+            if self.order is not None:
+                neg = neg[self.order]
+            neg = neg.contiguous()
+        ue, ie = self.final[:u], self.final[u:]
+        args = (_lib.ptr(ue), dg, _lib.ptr(ie), dg, dg, _lib.ptr(self.pos_u), _lib.ptr(self.pos_i), _lib.ptr(neg), self.n_triples, 1)
+        # 1. partial scores over the local columns (+ the local part of the squared-norm regulariser)
+        _lib.check(lib.gcf_bpr_fwd(*args, _lib.BPR_RAW_SCORE, 0.0, _lib.REDUCE_SUM, self.reg, self.reg, 0.0, _lib.ptr(self.loss_reg),
+                                   _lib.ptr(self.scores), _lib.ptr(self.bpr_ws), self.bpr_ws_bytes, st), "gcf_bpr_fwd")
+        # 2. the one data-path collective of the step
+        dist.all_reduce(self.scores, op=dist.ReduceOp.SUM)
+        # 3. pointwise loss on the complete scores (redundantly on every rank: E floats)
+        _lib.check(lib.gcf_bpr_coef_from_scores(_lib.ptr(self.scores), self.n_triples, _lib.BPR_SOFTPLUS, 0.0, _lib.REDUCE_MEAN,
+                                                _lib.ptr(self.loss_pt), _lib.ptr(self.coef), _lib.ptr(self.bpr_ws),
+                                                self.bpr_ws_bytes, st), "gcf_bpr_coef_from_scores")
+        # 4. gradients w.r.t. the local columns
+        self.g_final.zero_()
+        _lib.check(lib.gcf_bpr_bwd(*args, _lib.ptr(self.coef), None, self.reg, self.reg, 0.0, _lib.ptr(self.g_final[:u]), dg,
+                                   _lib.ptr(self.g_final[u:]), dg, st), "gcf_bpr_bwd")
+        if marks is not None:
+            e2.record()
+        _lib.check(lib.gcf_propagate_bwd(g.struct_ref(), dg, K, _lib.ptr(self.g_final), None, 1.0, _lib.ptr(self.ping),
+                                         _lib.ptr(self.pong), _lib.ptr(self.g_x0), _lib.ptr(self.ws), self.ws_bytes, st),
+                   "gcf_propagate_bwd")
+        if marks is not None:
+            e3.record()
+            marks.append((e0, e1, K))
+            marks.append((e2, e3, K))
+        _lib.check(lib.gcf_adam_step(_lib.ptr(self.table), _lib.ptr(self.g_x0), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                                     self.table.numel(), self.lr, 0.9, 0.999, 1e-8, 0.0, 0, self.step_count, st), "gcf_adam_step")
+        reg = self.loss_reg.clone()
+        dist.all_reduce(reg, op=dist.ReduceOp.SUM)
+        return self.loss_pt + reg
+
+    def gathered_table(self) -> torch.Tensor:
+        """[N, d] table on every rank (for checks / evaluation)."""
+        parts = [torch.empty_like(self.table) for _ in range(self.world)]
+        dist.all_gather(parts, self.table)
+        return torch.cat(parts, dim=1)
