@@ -28,7 +28,7 @@ constexpr int kTileM = 128;      // rows of the stationary operand per CTA (= TM
 constexpr int kTileN = 256;      // rows of the streamed operand per MMA tile (= TMEM columns per stage)
 constexpr int kChunkK = 64;      // bf16 elements per 128-byte swizzled row
 constexpr int kLseStages = 4;    // TMA ring depth (one stage = one [kTileN x 64] chunk = 32 KB)
-constexpr int kLseThreads = 192; // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int kLseThreads = 320; // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue (two per TMEM lane quadrant)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -105,7 +105,10 @@ struct LseSmem {
   static constexpr int kBBytesPerStage = kTileN * 128;  // 32 KB
 };
 
-template <int KC>  // number of 64-wide K chunks (d_pad = 64 * KC)
+// BOUNDED: the operands are L2-normalised, so |S2| <= log2e / tau is known up front; when that bound is small enough for fp32
+// (host checks <= 64) the running max and its rescaling are dropped: l = sum_b 2^S2, m = 0.  This is the reference's own
+// non-stabilised exp / sum form (ncl.py:362-365) and halves the epilogue's instruction count.
+template <int KC, bool BOUNDED>  // KC = number of 64-wide K chunks (d_pad = 64 * KC)
 __global__ void __launch_bounds__(kLseThreads, 1)
 lse_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, long long n_b,
                   int n_tiles, int tiles_per_split, float* __restrict__ part_m, float* __restrict__ part_l,
@@ -136,7 +139,7 @@ lse_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     if (lane == 0) {
       for (int s = 0; s < kLseStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
       mbar_init(a_bar, 1);
-      for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
+      for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 8); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -191,23 +194,24 @@ lse_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       }
     }
   } else {
-    // ===== epilogue: thread = one row of the tile; online base-2 log-sum-exp =====
+    // ===== epilogue: thread = one row x one half of the tile's columns; online base-2 log-sum-exp =====
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;                // columns [half * 128, half * 128 + 128) of every 256-column tile
     const int row = quad * 32 + lane;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_run = BOUNDED ? 0.f : -INFINITY, l_run = 0.f;
     for (int it = 0; it < my_tiles; ++it) {
       const int acc = it & 1;
       const int t = t_begin + it;
       mbar_wait(acc_full + acc, (it >> 1) & 1);
       fence_after_sync();
-      const long long col0 = (long long)t * kTileN;
-      const bool ragged = col0 + kTileN > n_b;       // tile contains zero-padded rows of B: mask them out
-      const long long diag = (long long)m_tile * kTileM + row - col0;  // column of this row's diagonal element in the tile
-      const bool has_diag = skip_diag && diag >= 0 && diag < kTileN;   // DirectAU: pairs i != j only
+      const long long col0 = (long long)t * kTileN + half * (kTileN / 2);
+      const bool ragged = col0 + kTileN / 2 > n_b;   // contains zero-padded rows of B: mask them out
+      const long long diag = (long long)m_tile * kTileM + row - col0;  // column of this row's diagonal element
+      const bool has_diag = skip_diag && diag >= 0 && diag < kTileN / 2;   // DirectAU: pairs i != j only
 #pragma unroll 1
-      for (int c = 0; c < kTileN / 32; ++c) {
+      for (int c = 0; c < kTileN / 64; ++c) {
         float v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileN + c * 32), v);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileN + half * (kTileN / 2) + c * 32), v);
         if (ragged) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -218,28 +222,39 @@ lse_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           for (int j = 0; j < 32; ++j)
             if (j == (int)(diag & 31)) v[j] = -INFINITY;
         }
-        float cm = v[0];
-#pragma unroll
-        for (int j = 1; j < 32; ++j) cm = fmaxf(cm, v[j]);
-        if (cm > m_run) {  // lazy rescale: only when the running max moves
-          l_run *= exp2f(m_run - cm);  // m_run = -inf -> factor 0 (l_run is 0 anyway)
-          m_run = cm;
-        }
-        if (m_run > -INFINITY) {
+        if (BOUNDED) {
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            s0 += exp2f(v[j] - m_run); s1 += exp2f(v[j + 1] - m_run);
-            s2 += exp2f(v[j + 2] - m_run); s3 += exp2f(v[j + 3] - m_run);
+            s0 += ex2_approx(v[j]); s1 += ex2_approx(v[j + 1]); s2 += ex2_approx(v[j + 2]); s3 += ex2_approx(v[j + 3]);
           }
           l_run += (s0 + s1) + (s2 + s3);
+        } else {
+          float cm = v[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) cm = fmaxf(cm, v[j]);
+          if (cm > m_run) {  // lazy rescale: only when the running max moves
+            l_run *= exp2f(m_run - cm);  // m_run = -inf -> factor 0 (l_run is 0 anyway)
+            m_run = cm;
+          }
+          if (m_run > -INFINITY) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              s0 += ex2_approx(v[j] - m_run); s1 += ex2_approx(v[j + 1] - m_run);
+              s2 += ex2_approx(v[j + 2] - m_run); s3 += ex2_approx(v[j + 3] - m_run);
+            }
+            l_run += (s0 + s1) + (s2 + s3);
+          }
         }
       }
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + acc);
     }
-    const long long out = (long long)split * m_pad + (long long)m_tile * kTileM + row;
+    if (BOUNDED && l_run == 0.f) m_run = -INFINITY;  // nothing unmasked in this slice: neutral element for the merge
+    // the two column halves are merged like two more splits
+    const long long out = ((long long)split * 2 + half) * m_pad + (long long)m_tile * kTileM + row;
     part_m[out] = m_run;
     part_l[out] = l_run;
   }
@@ -297,8 +312,9 @@ static LsePlan plan_lse(long long n_a, long long n_b) {
   p.b_pad = round_up(std::max<long long>(n_b, 1), kTileN);
   p.m_tiles = (int)(p.a_pad / kTileM);
   p.n_tiles = (int)(p.b_pad / kTileN);
+  // column splits so that the grid fills the SMs in ONE wave (a 160-CTA grid on 148 SMs costs a second, nearly empty wave)
   const int sms = sm_count();
-  int splits = std::max(1, std::min(p.n_tiles, (sms + p.m_tiles - 1) / p.m_tiles));
+  int splits = std::max(1, std::min(p.n_tiles, sms / std::max(p.m_tiles, 1)));
   p.tiles_per_split = (p.n_tiles + splits - 1) / splits;
   p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   return p;
@@ -310,7 +326,7 @@ static size_t lse_smem_bytes(int kc) {
 
 // (m, l) partials -> lse[n_a]; ab/bb are the prepared bf16 operands ([a_pad, d_pad], [b_pad, d_pad])
 static int run_lse(const __nv_bfloat16* ab, long long n_a, const __nv_bfloat16* bb, long long n_b, int d_pad,
-                   float* part_m, float* part_l, float* lse_out, cudaStream_t st, int skip_diag = 0) {
+                   float* part_m, float* part_l, float* lse_out, cudaStream_t st, int skip_diag = 0, bool bounded = false) {
   const LsePlan p = plan_lse(n_a, n_b);
   CUtensorMap tm_a, tm_b;
   int rc = make_tmap(&tm_a, ab, p.a_pad, d_pad, kTileM);
@@ -320,11 +336,16 @@ static int run_lse(const __nv_bfloat16* ab, long long n_a, const __nv_bfloat16* 
   const int kc = d_pad / kChunkK;
   const size_t smem = lse_smem_bytes(kc);
   dim3 grid(p.m_tiles, p.n_splits);
-#define GCF_LSE_LAUNCH(KC)                                                                                          \
-  do {                                                                                                              \
-    GCF_CUDA(cudaFuncSetAttribute(lse_stream_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    lse_stream_kernel<KC><<<grid, kLseThreads, smem, st>>>(tm_a, tm_b, n_b, p.n_tiles, p.tiles_per_split, part_m,   \
-                                                           part_l, p.a_pad, skip_diag);                            \
+#define GCF_LSE_LAUNCH2(KC, B)                                                                                         \
+  do {                                                                                                                 \
+    GCF_CUDA(cudaFuncSetAttribute(lse_stream_kernel<KC, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    lse_stream_kernel<KC, B><<<grid, kLseThreads, smem, st>>>(tm_a, tm_b, n_b, p.n_tiles, p.tiles_per_split, part_m,   \
+                                                              part_l, p.a_pad, skip_diag);                            \
+  } while (0)
+#define GCF_LSE_LAUNCH(KC)                                      \
+  do {                                                          \
+    if (bounded) GCF_LSE_LAUNCH2(KC, true);                     \
+    else GCF_LSE_LAUNCH2(KC, false);                            \
   } while (0)
   switch (kc) {
     case 1: GCF_LSE_LAUNCH(1); break;
@@ -334,8 +355,9 @@ static int run_lse(const __nv_bfloat16* ab, long long n_a, const __nv_bfloat16* 
     default: set_error("infonce: d_pad=%d unsupported (d <= 256)", d_pad); return GCF_EUNSUPPORTED;
   }
 #undef GCF_LSE_LAUNCH
+#undef GCF_LSE_LAUNCH2
   GCF_LAUNCH_CHECK("lse_stream_kernel");
-  combine_lse_kernel<<<(unsigned)cdiv(n_a, 256), 256, 0, st>>>(part_m, part_l, p.n_splits, p.a_pad, n_a, lse_out);
+  combine_lse_kernel<<<(unsigned)cdiv(n_a, 256), 256, 0, st>>>(part_m, part_l, 2 * p.n_splits, p.a_pad, n_a, lse_out);
   GCF_LAUNCH_CHECK("combine_lse_kernel");
   return GCF_OK;
 }
@@ -347,7 +369,7 @@ static int run_lse(const __nv_bfloat16* ab, long long n_a, const __nv_bfloat16* 
 // warp 0: TMA, warp 1: MMA issuer, warps 2-5: S (TMEM) -> P (bf16, swizzled smem) conversion and the final G read-out.
 // ------------------------------------------------------------------------------------------------
 constexpr int kGradTileN = 128;   // B rows per tile = K extent of the second MMA
-constexpr int kGradThreads = 192;
+constexpr int kGradThreads = 320;  // warp 0: TMA, warp 1: MMA, warps 2-9: conversion (two per TMEM lane quadrant)
 constexpr int kChunkBytes = 128 * 128;  // one [128 x 64] bf16 swizzled chunk = 16 KB
 
 template <int KC> struct GradCfg {
@@ -397,8 +419,8 @@ grad_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     if (lane == 0) {
       for (int i = 0; i < NS; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
       mbar_init(a_bar, 1);
-      for (int i = 0; i < 2; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, 4); }
-      for (int i = 0; i < NP; ++i) { mbar_init(p_full + i, 4); mbar_init(p_empty + i, 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, 8); }
+      for (int i = 0; i < NP; ++i) { mbar_init(p_full + i, 8); mbar_init(p_empty + i, 1); }
       mbar_init(g_full, 1);
       fence_barrier_init();
     }
@@ -471,10 +493,11 @@ grad_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       umma_commit(g_full);
     }
   } else {
-    // ===== conversion warps: thread = one row of the tile =====
+    // ===== conversion warps: thread = one row of the tile x one 64-column half (= one swizzled P chunk) =====
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..127 (staging of the per-column vectors)
+    const int et = threadIdx.x - 64;  // 0..255; the first 128 stage the per-column vectors
     const long long row_g = (long long)m_tile * kTileM + row;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     float wr = 0.f, lr = 0.f;
@@ -485,10 +508,12 @@ grad_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       float* cw = cvec + (it % NCV) * 2 * kGradTileN;
       float* cl = cw + kGradTileN;
       if (HAS_COL) {
-        const long long j = col0 + et;
-        cw[et] = (j < n_b) ? w_c[j] : 0.f;
-        cl[et] = (j < n_b) ? lse_c[j] * kLog2e : 0.f;
-        named_bar_sync(1, 128);
+        if (et < kGradTileN) {
+          const long long j = col0 + et;
+          cw[et] = (j < n_b) ? w_c[j] : 0.f;
+          cl[et] = (j < n_b) ? lse_c[j] * kLog2e : 0.f;
+        }
+        named_bar_sync(1, 256);
       }
       mbar_wait(s_full + acc, (it >> 1) & 1);
       fence_after_sync();
@@ -497,7 +522,7 @@ grad_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       const bool has_diag = skip_diag && diag >= 0 && diag < kGradTileN;
       uint8_t* prow = smem_p + pb * 2 * kChunkBytes + row * 128;
 #pragma unroll 1
-      for (int c = 0; c < kGradTileN / 32; ++c) {
+      for (int c = 2 * half; c < 2 * half + 2; ++c) {
         float v[32];
         tmem_ld_32x32(tmem_base + lane_off + (uint32_t)(acc * kGradTileN + c * 32), v);
 #pragma unroll
@@ -537,7 +562,7 @@ grad_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           *reinterpret_cast<uint4*>(pchunk + unit * 16) = pk;
         }
       }
-      if (HAS_COL && NCV == 1) named_bar_sync(1, 128);  // single staging buffer: everyone is done reading it
+      if (HAS_COL && NCV == 1) named_bar_sync(1, 256);  // single staging buffer: everyone is done reading it
       fence_proxy_async_smem();   // generic-proxy P writes -> visible to the tensor core's async-proxy reads
       fence_before_sync();
       __syncwarp();
@@ -549,14 +574,14 @@ grad_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       mbar_wait(g_full, 0);
       fence_after_sync();
 #pragma unroll 1
-      for (int c = 0; c < DP / 32; ++c) {
+      for (int c = half; c < DP / 32; c += 2) {
         float v[32];
         tmem_ld_32x32(tmem_base + lane_off + kTmemG + (uint32_t)(c * 32), v);
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<float4*>(out + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
-    } else {
+    } else if (half == 0) {
       for (int c = 0; c < DP; c += 4) *reinterpret_cast<float4*>(out + c) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -648,7 +673,7 @@ static GradPlan plan_grad(long long n_a, long long n_b) {
   p.m_tiles = (int)(p.a_pad / kTileM);
   p.n_tiles = (int)cdiv(std::max<long long>(n_b, 1), kGradTileN);
   const int sms = sm_count();
-  int splits = std::max(1, std::min(p.n_tiles, (sms + p.m_tiles - 1) / p.m_tiles));
+  int splits = std::max(1, std::min(p.n_tiles, sms / std::max(p.m_tiles, 1)));
   p.tiles_per_split = (p.n_tiles + splits - 1) / splits;
   p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   return p;
@@ -707,7 +732,7 @@ static InfoWs carve_ws(void* ws, long long m, long long n, int d) {
   const GradPlan gq = plan_grad(m, n), gk = plan_grad(n, m);
   // operands are padded for every role (stationary: multiple of 128, streamed: multiple of 256 / 128)
   const long long q_rows = round_up(std::max<long long>(m, 1), kTileN), k_rows = round_up(std::max<long long>(n, 1), kTileN);
-  const size_t part = std::max((size_t)pq.n_splits * pq.a_pad, (size_t)pk.n_splits * pk.a_pad);
+  const size_t part = 2 * std::max((size_t)pq.n_splits * pq.a_pad, (size_t)pk.n_splits * pk.a_pad);  // x2: column halves
   const size_t gpart = std::max((size_t)gq.n_splits * gq.a_pad, (size_t)gk.n_splits * gk.a_pad) * d_pad;
   InfoWs w;
   size_t off = 0;
@@ -836,12 +861,13 @@ extern "C" int gcf_infonce_fwd(const float* Q, int64_t ldq, int64_t M, const flo
   if (rc != GCF_OK) return rc;
   rc = prep(Kmat, ldk, N, d, cos, 1.f, w.kb, w.k_inv, st);
   if (rc != GCF_OK) return rc;
+  const bool bounded = cos != 0 && kLog2e / tau <= 64.f;  // |S2| <= log2e / tau: 2^S2 and its sums stay inside fp32
   if (row_lse != nullptr) {
-    rc = run_lse(w.qb, M, w.kb, N, d_pad, w.part_m, w.part_l, row_lse, st);
+    rc = run_lse(w.qb, M, w.kb, N, d_pad, w.part_m, w.part_l, row_lse, st, 0, bounded);
     if (rc != GCF_OK) return rc;
   }
   if (col_lse != nullptr) {  // column log-sum-exp = row log-sum-exp of the transposed product
-    rc = run_lse(w.kb, N, w.qb, M, d_pad, w.part_m, w.part_l, col_lse, st);
+    rc = run_lse(w.kb, N, w.qb, M, d_pad, w.part_m, w.part_l, col_lse, st, 0, bounded);
     if (rc != GCF_OK) return rc;
   }
   if (pos != nullptr) {
@@ -955,7 +981,7 @@ extern "C" int gcf_directau_fwd(const float* x, int64_t ldx, const float* y, int
     if (rc != GCF_OK) return rc;
     rc = prep(src[which], lds[which], B, d, 1, 1.f, w.kb, invs[which], st);
     if (rc != GCF_OK) return rc;
-    rc = run_lse(w.qb, B, w.kb, B, d_pad, w.part_m, w.part_l, lses[which], st, 1);
+    rc = run_lse(w.qb, B, w.kb, B, d_pad, w.part_m, w.part_l, lses[which], st, 1, 2.f * t * kLog2e <= 64.f);
     if (rc != GCF_OK) return rc;
   }
   directau_finish_kernel<<<1, 256, 0, st>>>(x, ldx, w.q_inv, y, ldy, w.k_inv, B, d, t, dw.lse_x, dw.lse_y, out3);
