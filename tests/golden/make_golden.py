@@ -206,6 +206,77 @@ def main():
     g_gb = grads_of(l_gb, ue, pe, ne)
     np.savez(OUT / "gcl_losses.npz", z1=t2n(z1), z2=t2n(z2), info_nce=t2n(l_g), g_z1=g_g[0], g_z2=g_g[1],
              ue=t2n(ue), pe=t2n(pe), ne=t2n(ne), reg_weight=1e-3, bpr_reg=t2n(l_gb), g_u=g_gb[0], g_p=g_gb[1], g_n=g_gb[2])
+    # ------------------------------------------------------------------ mhcn (univariate/mhcn.py; `tensorflow` is imported but unused)
+    mh = load_ref("mhcn", "univariate/mhcn.py", stubs=("tensorflow",))
+    srng = np.random.default_rng(11)
+    s_users = sorted({r[0] for r in train})
+    social = []
+    for _ in range(260):
+        a, b = srng.choice(len(s_users), 2, replace=False)
+        social.append([s_users[a], s_users[b], 1.0])
+    for k in range(0, 120, 2):  # reciprocal edges: the bidirectional motif matrices must not be empty
+        social.append([social[k][1], social[k][0], 1.0])
+    conf = {"model": {"name": "MHCN"}, "MHCN": {"n_layer": 2, "ss_rate": 0.01}, "emb_size": d, "batch_size": 64, "lr": 0.001,
+            "reg_lambda": 1e-4, "max.epoch": 1}
+    torch.manual_seed(5)
+    m = mh.MHCN(conf, [tuple(r) for r in train], [tuple(r) for r in test], [list(x) for x in social])
+    m.build()
+    Hs, Hj, Hp = [x.tocsr() for x in m.build_hyper_adj_mats()]
+    Rn = mh.Graph.normalize_graph_mat(m.data.interaction_mat).tocsr()
+    mu = torch.tensor(srng.integers(0, m.data.user_num, 24)); mv = torch.tensor(srng.integers(0, m.data.item_num, 24))
+    mn = torch.tensor(srng.integers(0, m.data.item_num, 24))
+    perms = []
+    real_randperm = torch.randperm
+
+    def logged_randperm(n, **kw):
+        p = real_randperm(n, **kw)
+        perms.append(p.clone())
+        return p
+    torch.randperm = logged_randperm
+    try:
+        out = m.forward(mu, mv, mn)
+    finally:
+        torch.randperm = real_randperm
+    rec = mh.bpr_loss(out[0], out[1], out[2])
+    total = rec + out[3]
+    names = sorted(n for n, _ in m.named_parameters())
+    params = dict(m.named_parameters())
+    gs = grads_of(total, *[params[n] for n in names])
+    csr = lambda M: dict(indptr=M.indptr, indices=M.indices, data=M.data.astype(np.float32), shape=np.array(M.shape))
+    np.savez(OUT / "mhcn_model.npz", n_layers=2, ss_rate=0.01, user_num=m.data.user_num, item_num=m.data.item_num,
+             u_idx=t2n(mu), v_idx=t2n(mv), neg_idx=t2n(mn), perms=np.stack([t2n(p) for p in perms]),
+             **{f"Hs_{k}": v for k, v in csr(Hs).items()}, **{f"Hj_{k}": v for k, v in csr(Hj).items()},
+             **{f"Hp_{k}": v for k, v in csr(Hp).items()}, **{f"R_{k}": v for k, v in csr(Rn).items()},
+             **{f"param__{n}": t2n(params[n]) for n in names}, **{f"grad__{n}": g for n, g in zip(names, gs)},
+             batch_user=t2n(out[0]), batch_pos=t2n(out[1]), batch_neg=t2n(out[2]), ss_loss=t2n(out[3]),
+             final_user=t2n(out[4]), final_item=t2n(out[5]), rec_loss=t2n(rec))
+
+    # ------------------------------------------------------------------ diffnet (univariate/diffnet.py:1124-1132, forward only needs attributes)
+    dn = load_ref("diffnet", "univariate/diffnet.py", stubs=("tensorflow",))
+    import scipy.sparse as sp
+    nU2, nI2, K2 = m.data.user_num, m.data.item_num, 2
+    S_raw = sp.coo_matrix((np.ones(len(social), np.float32), ([m.data.user[x[0]] for x in social], [m.data.user[x[1]] for x in social])),
+                          shape=(nU2, nU2)).tocsr()
+    S_raw.sum_duplicates()
+    rs = np.asarray(S_raw.sum(1)).ravel(); rs[rs == 0] = 1
+    S_n = sp.diags(1.0 / rs).dot(S_raw).tocsr().astype(np.float32)          # 1/|followees| weights (diffnet.py:1070-1078)
+    A_m = m.data.interaction_mat.tocsr().astype(np.float32)
+    to_t = lambda M: torch.sparse_coo_tensor(np.vstack(M.tocoo().coords), M.tocoo().data, M.shape).coalesce()
+    ns2 = SimpleNamespace(n_layers=K2, S=to_t(S_n), A=to_t(A_m),
+                          user_embeddings=(torch.randn(nU2, d) * 0.05).requires_grad_(True),
+                          item_embeddings=(torch.randn(nI2, d) * 0.05).requires_grad_(True),
+                          weights=[torch.nn.init.xavier_uniform_(torch.empty(2 * d, d)).requires_grad_(True) for _ in range(K2)])
+    fu = dn.DiffNet.forward(ns2)
+    du = torch.tensor(srng.integers(0, nU2, 32)); di = torch.tensor(srng.integers(0, nI2, 32)); dj = torch.tensor(srng.integers(0, nI2, 32))
+    ue2, ve2, ne2 = fu[du], ns2.item_embeddings[di], ns2.item_embeddings[dj]
+    y = (ue2 * ve2).sum(1) - (ue2 * ne2).sum(1)
+    dloss = -torch.sum(torch.log(torch.sigmoid(y))) + 1e-4 * (torch.norm(ue2, 2) + torch.norm(ve2, 2) + torch.norm(ne2, 2))  # diffnet.py:1107-1115
+    dg = grads_of(dloss, ns2.user_embeddings, ns2.item_embeddings, *ns2.weights)
+    np.savez(OUT / "diffnet_model.npz", n_layers=K2, num_users=nU2, num_items=nI2, regU=1e-4,
+             **{f"S_{k}": v for k, v in csr(S_n).items()}, **{f"A_{k}": v for k, v in csr(A_m).items()},
+             user_w=t2n(ns2.user_embeddings), item_w=t2n(ns2.item_embeddings), weights=np.stack([t2n(w) for w in ns2.weights]),
+             u_idx=t2n(du), i_idx=t2n(di), j_idx=t2n(dj), final_user=t2n(fu), loss=t2n(dloss),
+             g_user_w=dg[0], g_item_w=dg[1], g_weights=np.stack(dg[2:]))
     print("golden fixtures written to", OUT)
 
 

@@ -184,3 +184,52 @@ def test_next_batch_pairwise_semantics(cuda):
     assert not np.array_equal(first, np.array([p[0] for p in seen[:128]]))  # reshuffled per epoch
     negs = np.concatenate([b[2].cpu().numpy() for b in data._gcf_sampler.batches(700, n_negs=1)])
     assert len(np.unique(negs)) > I // 2                                    # spread over the item set
+
+
+# ------------------------------------------------------------------------------------------ social variants (cfg 4)
+def _csr(z, prefix):
+    shape = tuple(int(x) for x in z[f"{prefix}_shape"])
+    return sp.csr_matrix((z[f"{prefix}_data"], z[f"{prefix}_indices"], z[f"{prefix}_indptr"]), shape=shape)
+
+
+def test_mhcn_model_fixture(cuda, golden):
+    from recommendation_b200 import social
+
+    z = golden("mhcn_model")
+    m = social.MHCNModel(int(z["user_num"]), int(z["item_num"]), z["param__user_embeddings"].shape[1], int(z["n_layers"]), float(z["ss_rate"]),
+                         _csr(z, "Hs"), _csr(z, "Hj"), _csr(z, "Hp"), _csr(z, "R"))
+    names = sorted(k[len("param__"):] for k in z.keys() if k.startswith("param__"))
+    assert sorted(m.state_dict().keys()) == names                      # the reference's 20 keys
+    m.load_state_dict({n: torch.from_numpy(z[f"param__{n}"]) for n in names})
+    perms = [torch.from_numpy(p).to(cuda) for p in z["perms"]]
+    out = m(z["u_idx"].tolist(), z["v_idx"].tolist(), z["neg_idx"].tolist(), perms=perms)
+    for got, key in zip(out, ("batch_user", "batch_pos", "batch_neg", "ss_loss", "final_user", "final_item")):
+        _close(got, z[key], rtol=1e-3, atol=1e-5)
+    total = losses.bpr_loss(out[0], out[1], out[2]) + out[3]
+    np.testing.assert_allclose(total.item(), float(z["rec_loss"]) + float(z["ss_loss"]), rtol=1e-4)
+    total.backward()
+    params = dict(m.named_parameters())
+    for n in names:
+        want = z[f"grad__{n}"]
+        got = np.zeros_like(want) if params[n].grad is None else params[n].grad.cpu().numpy()   # sgating_*.4 are unused
+        np.testing.assert_allclose(got, want, rtol=5e-3, atol=1e-5 * max(1.0, np.abs(want).max()))
+    out2 = m(z["u_idx"].tolist(), z["v_idx"].tolist(), z["neg_idx"].tolist())   # training path: device randperm
+    assert torch.isfinite(out2[3])
+
+
+def test_diffnet_model_fixture(cuda, golden):
+    from recommendation_b200 import social
+
+    z = golden("diffnet_model")
+    m = social.DiffNetModel(int(z["num_users"]), int(z["num_items"]), z["user_w"].shape[1], int(z["n_layers"]), _csr(z, "S"), _csr(z, "A"))
+    assert sorted(m.state_dict().keys()) == ["item_embeddings", "user_embeddings", "weights.0", "weights.1"]
+    m.load_state_dict({"user_embeddings": torch.from_numpy(z["user_w"]), "item_embeddings": torch.from_numpy(z["item_w"]),
+                       "weights.0": torch.from_numpy(z["weights"][0]), "weights.1": torch.from_numpy(z["weights"][1])})
+    fu = m()
+    _close(fu, z["final_user"], rtol=1e-3, atol=1e-6)
+    loss = m.bpr_sum_loss(fu, z["u_idx"].tolist(), z["i_idx"].tolist(), z["j_idx"].tolist(), float(z["regU"]))
+    _close(loss, z["loss"], rtol=1e-4)
+    loss.backward()
+    _close(m.user_embeddings.grad, z["g_user_w"], atol=1e-6); _close(m.item_embeddings.grad, z["g_item_w"], atol=1e-6)
+    for k in range(2):
+        _close(m.weights[k].grad, z["g_weights"][k], atol=1e-6)

@@ -229,3 +229,41 @@ def test_sampler_oracle_properties():
     assert (c % 2 == 1).all()
     unchanged = a % 2 == 1
     assert np.array_equal(c[unchanged], a[unchanged])  # accepted first candidates are untouched
+
+
+def _dense(z, prefix):
+    import scipy.sparse as sp
+    shape = tuple(int(x) for x in z[f"{prefix}_shape"])
+    return torch.from_numpy(sp.csr_matrix((z[f"{prefix}_data"], z[f"{prefix}_indices"], z[f"{prefix}_indptr"]), shape=shape).toarray()).double()
+
+
+def test_mhcn_forward_matches_reference(golden):
+    from oracle import social_ref
+
+    z = golden("mhcn_model")
+    names = [k[len("param__"):] for k in z.keys() if k.startswith("param__")]
+    p = {n: T(z[f"param__{n}"].astype(np.float64), True) for n in names}
+    perms = [torch.from_numpy(x) for x in z["perms"]]
+    out = social_ref.mhcn_forward(p, _dense(z, "Hs"), _dense(z, "Hj"), _dense(z, "Hp"), _dense(z, "R"), int(z["n_layers"]),
+                                  float(z["ss_rate"]), T(z["u_idx"]), T(z["v_idx"]), T(z["neg_idx"]), perms)
+    for got, key in zip(out, ("batch_user", "batch_pos", "batch_neg", "ss_loss", "final_user", "final_item")):
+        np.testing.assert_allclose(got.detach().numpy(), z[key], rtol=1e-4, atol=1e-5)
+    total = losses_ref.bpr_log_eps_sigmoid(out[0], out[1], out[2]) + out[3]
+    grads = torch.autograd.grad(total, [p[n] for n in names], allow_unused=True)
+    for n, g in zip(names, grads):
+        g = np.zeros_like(z[f"grad__{n}"]) if g is None else g.numpy()   # sgating_*.4 take no part in the forward
+        np.testing.assert_allclose(g, z[f"grad__{n}"], rtol=2e-3, atol=2e-6)
+
+
+def test_diffnet_forward_matches_reference(golden):
+    from oracle import social_ref
+
+    z = golden("diffnet_model")
+    uw, iw = T(z["user_w"].astype(np.float64), True), T(z["item_w"].astype(np.float64), True)
+    ws = [T(w.astype(np.float64), True) for w in z["weights"]]
+    fu = social_ref.diffnet_forward(uw, iw, ws, _dense(z, "S"), _dense(z, "A"))
+    np.testing.assert_allclose(fu.detach().numpy(), z["final_user"], rtol=1e-5, atol=1e-7)
+    u, v, n = fu[T(z["u_idx"])], iw[T(z["i_idx"])], iw[T(z["j_idx"])]
+    y = (u * v).sum(1) - (u * n).sum(1)
+    loss = -torch.log(torch.sigmoid(y)).sum() + float(z["regU"]) * (u.norm(2) + v.norm(2) + n.norm(2))
+    _check(loss, (uw, iw, *ws), z["loss"], (z["g_user_w"], z["g_item_w"], *z["g_weights"]), rtol=1e-4)
