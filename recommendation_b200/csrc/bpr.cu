@@ -319,8 +319,8 @@ __device__ __forceinline__ void load_row_stream(const float* __restrict__ base, 
 // gather traffic of the separate fwd + bwd kernels, which is what bounds them once the tables outgrow the L2.
 // Negative rows are uniformly random (no reuse): gathered and reduced with L2 evict_first so they do not push the
 // popular positive rows out of the cache.
-template <int LPR, int VPL, bool GUARD, int BATCH>
-__global__ void __launch_bounds__(kBprThreads)
+template <int LPR, int VPL, bool GUARD, int BATCH, int MINB = 1>
+__global__ void __launch_bounds__(kBprThreads, MINB)
 bpr_fused_kernel(const float* __restrict__ uemb, long long ldu, const float* __restrict__ iemb, long long ldi, int dvec,
                  const int64_t* __restrict__ u_idx, const int64_t* __restrict__ p_idx, const int64_t* __restrict__ n_idx,
                  long long n, int n_negs, int variant, float eps, float w_loss, float reg_u, float reg_p, float reg_n,
@@ -595,7 +595,9 @@ extern "C" int gcf_bpr_fwd_bwd(const float* user_emb, int64_t ld_user, const flo
     case 8:   bpr_fused_kernel<2, 1, false, 2><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
     case 16:  bpr_fused_kernel<4, 1, false, 2><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
     case 32:  bpr_fused_kernel<8, 1, false, 2><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
-    case 64:  bpr_fused_kernel<16, 1, false, 2><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
+    // d = 64: 4 triples (12 row gathers) in flight per sub-warp at <= 128 registers, 2 CTAs / SM -- measured best of
+    // {batch 1, 2, 4, 8} x {1..4 CTAs / SM} on cfg5 (29.4 -> 25.7 ms, profiles/r01_exp_variants_cfg5.log)
+    case 64:  bpr_fused_kernel<16, 1, false, 4, 2><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
     case 128: bpr_fused_kernel<32, 1, false, 2><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
     case 256: bpr_fused_kernel<32, 2, false, 1><<<grid, kBprThreads, 0, st>>>(GCF_BPR_FUSED_ARGS); break;
     default:
