@@ -281,6 +281,23 @@ int gcf_directau_bwd(const float* x, int64_t ldx, const float* y, int64_t ldy, i
                      const float* out3, const float* w3, float* gx, int64_t ldgx, float* gy, int64_t ldgy,
                      void* workspace, size_t workspace_bytes, gcf_stream_t stream);
 
+/* ---- batched evaluation ---------------------------------------------------
+ *
+ * scores [n_queries, n_items] fp32 (ld elements per row) is the dense score block user_emb[q] . item_emb^T -- a plain
+ * GEMM, produced by the caller (cuBLAS).  For every row: the training items of user users[q] (NULL -> q), given as a
+ * per-user sorted CSR, are overwritten IN PLACE with mask_value (-1e8 in ncl.py:257-259), then the n_top (<= 128) best
+ * items are selected exactly (score descending, ties by ascending item id) into out_idx / out_val [n_queries, n_top].
+ * Replaces the predict / mask / torch.topk loop of test() (ncl.py:253-266, lightgcn.py:48-74). */
+int gcf_masked_topn(float* scores, int64_t ld, int64_t n_queries, int64_t n_items, const int64_t* users,
+                    const int32_t* pos_row_ptr, const int32_t* pos_col_idx, float mask_value, int32_t n_top,
+                    int64_t* out_idx, float* out_val, gcf_stream_t stream);
+
+/* hits[q, c] = |top-cutoffs[c] of row q  ∩  test items of users[q]|, dcg[q, c] = sum_{hit at rank i < cutoffs[c]} 1/log2(i+2)
+ * (Metric.hits / Metric.NDCG, ncl.py:136-162); cutoffs ascending int32 device array.  test CSR: per-user sorted items. */
+int gcf_ranking_hits(const int64_t* topn, int64_t n_queries, int32_t n_top, const int64_t* users,
+                     const int32_t* test_row_ptr, const int32_t* test_col_idx, const int32_t* cutoffs, int32_t n_cutoffs,
+                     int32_t* hits, float* dcg, gcf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

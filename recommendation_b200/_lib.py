@@ -85,6 +85,10 @@ _SIGNATURES = {
     "gcf_infonce_bwd": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32, c_float,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "gcf_masked_topn": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_void_p,
+                                  c_void_p, c_void_p]),
+    "gcf_ranking_hits": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
+                                   c_void_p, c_void_p]),
     "gcf_directau_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "gcf_directau_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_float, c_void_p,
                                    c_void_p, c_size_t, c_void_p]),

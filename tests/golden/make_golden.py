@@ -277,6 +277,21 @@ def main():
              user_w=t2n(ns2.user_embeddings), item_w=t2n(ns2.item_embeddings), weights=np.stack([t2n(w) for w in ns2.weights]),
              u_idx=t2n(du), i_idx=t2n(di), j_idx=t2n(dj), final_user=t2n(fu), loss=t2n(dloss),
              g_user_w=dg[0], g_item_w=dg[1], g_weights=np.stack(dg[2:]))
+    # ------------------------------------------------------------------ ranking_evaluation (ncl.py:133-178) on random lists
+    erng = np.random.default_rng(21)
+    eU, eI, eN = 30, 80, 20
+    origin, res = {}, {}
+    lists = np.stack([erng.permutation(eI)[:eN] for _ in range(eU)])
+    test_items = []
+    for u in range(eU):
+        its = erng.choice(eI, size=int(erng.integers(1, 9)), replace=False)
+        origin[f"u{u}"] = {f"i{i}": 1 for i in its}
+        res[f"u{u}"] = [(f"i{i}", float(eN - r)) for r, i in enumerate(lists[u])]
+        test_items.append(np.array(sorted(its)))
+    strings = ncl.ranking_evaluation(origin, res, [5, 10, 20])
+    vals = np.array([float(x.split(":")[1]) for x in strings if ":" in x]).reshape(3, 4)
+    np.savez(OUT / "eval_metrics.npz", lists=lists, test_ptr=np.concatenate([[0], np.cumsum([len(t) for t in test_items])]),
+             test_items=np.concatenate(test_items), top_ns=np.array([5, 10, 20]), measures=vals)
     print("golden fixtures written to", OUT)
 
 

@@ -7,7 +7,7 @@ import pytest
 import scipy.sparse as sp
 import torch
 
-from recommendation_b200 import encoders, losses, sampling
+from recommendation_b200 import _lib as _lib_mod, encoders, losses, sampling
 from recommendation_b200.graph import CSRGraph
 
 pytestmark = pytest.mark.gpu
@@ -233,3 +233,51 @@ def test_diffnet_model_fixture(cuda, golden):
     _close(m.user_embeddings.grad, z["g_user_w"], atol=1e-6); _close(m.item_embeddings.grad, z["g_item_w"], atol=1e-6)
     for k in range(2):
         _close(m.weights[k].grad, z["g_weights"][k], atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ batched evaluation (8f row 2)
+def test_masked_topn_vs_oracle(cuda):
+    from oracle import eval_ref
+    from recommendation_b200 import evaluation
+
+    rng = np.random.default_rng(5)
+    U, I, d = 300, 5000, 32
+    ue = torch.from_numpy(rng.standard_normal((U, d)).astype(np.float32)).to(cuda)
+    ie = torch.from_numpy(rng.standard_normal((I, d)).astype(np.float32)).to(cuda)
+    tr_u = rng.integers(0, U, 9000); tr_i = rng.integers(0, I, 9000)
+    tr_u[:600] = 7; tr_i[:600] = rng.permutation(I)[:600]            # a user with many rated items
+    train_pos = evaluation.positives_csr(torch.from_numpy(tr_u).to(cuda), torch.from_numpy(tr_i).to(cuda), U, I)
+    query = torch.from_numpy(rng.permutation(U)[:200].astype(np.int64)).to(cuda)
+    for n_top, block in ((50, 1 << 30), (128, 64 * 4 * I), (1, 1 << 30)):
+        idx, val = evaluation.recommend_topn(ue, ie, query, n_top, train_pos=train_pos, block_bytes=block)
+        scores = (ue[query] @ ie.T).cpu().numpy()
+        per_user = [np.unique(tr_i[tr_u == int(u)]) for u in query.cpu().numpy()]
+        want_idx, want_val = eval_ref.masked_topn(scores, per_user, n_top)
+        assert np.array_equal(idx.cpu().numpy(), want_idx)              # exact selection and order
+        np.testing.assert_array_equal(val.cpu().numpy(), want_val)
+        for r, its in enumerate(per_user):
+            assert not set(idx[r].cpu().numpy().tolist()) & set(its.tolist())   # rated items are never recommended
+    # ties: constant scores -> the lowest item ids, in order
+    flat = torch.zeros(4, 1000, device=cuda)
+    lib = _lib_mod.load()
+    oi = torch.empty(4, 10, dtype=torch.int64, device=cuda); ov = torch.empty(4, 10, device=cuda)
+    _lib_mod.check(lib.gcf_masked_topn(_lib_mod.ptr(flat), 1000, 4, 1000, None, None, None, -1e8, 10, _lib_mod.ptr(oi), _lib_mod.ptr(ov),
+                                       _lib_mod.current_stream()), "topn")
+    assert torch.equal(oi.cpu(), torch.arange(10).repeat(4, 1))
+
+
+def test_ranking_measures_match_reference_fixture(cuda, golden):
+    from recommendation_b200 import evaluation
+
+    z = golden("eval_metrics")
+    lists = torch.from_numpy(z["lists"].astype(np.int64)).to(cuda)
+    U = lists.shape[0]
+    ptr = z["test_ptr"]
+    te_u = np.repeat(np.arange(U), np.diff(ptr))
+    test_pos = evaluation.positives_csr(torch.from_numpy(te_u).to(cuda), torch.from_numpy(z["test_items"].astype(np.int64)).to(cuda), U, 80)
+    got = evaluation.ranking_measures(lists, torch.arange(U, device=cuda), test_pos, [int(n) for n in z["top_ns"]])
+    for row, n in zip(z["measures"], z["top_ns"]):
+        m = got[int(n)]
+        np.testing.assert_allclose([m["Hit Ratio"], m["Precision"], m["Recall"], m["NDCG"]], row, rtol=0, atol=1.1e-5)
+    lines = evaluation.format_measures(got)
+    assert lines[0] == "Top 5\n" and lines[1].startswith("Hit Ratio:") and len(lines) == 15

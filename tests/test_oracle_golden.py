@@ -267,3 +267,14 @@ def test_diffnet_forward_matches_reference(golden):
     y = (u * v).sum(1) - (u * n).sum(1)
     loss = -torch.log(torch.sigmoid(y)).sum() + float(z["regU"]) * (u.norm(2) + v.norm(2) + n.norm(2))
     _check(loss, (uw, iw, *ws), z["loss"], (z["g_user_w"], z["g_item_w"], *z["g_weights"]), rtol=1e-4)
+
+
+def test_eval_measures_match_reference(golden):
+    from oracle import eval_ref
+
+    z = golden("eval_metrics")
+    ptr = z["test_ptr"]
+    tests = [z["test_items"][ptr[u]:ptr[u + 1]] for u in range(len(ptr) - 1)]
+    got = eval_ref.measures(z["lists"], tests, [int(n) for n in z["top_ns"]])
+    for row, n in zip(z["measures"], z["top_ns"]):
+        np.testing.assert_allclose(got[int(n)], row, rtol=0, atol=1e-5)
