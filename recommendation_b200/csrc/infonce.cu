@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 
 namespace gcf {
@@ -29,6 +30,7 @@ constexpr int kTileN = 256;      // rows of the streamed operand per MMA tile (=
 constexpr int kChunkK = 64;      // bf16 elements per 128-byte swizzled row
 constexpr int kLseStages = 4;    // TMA ring depth (one stage = one [kTileN x 64] chunk = 32 KB)
 constexpr int kLseThreads = 320; // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue (two per TMEM lane quadrant)
+constexpr int kPolyOf8 = 2;       // exponentials evaluated on the FMA pipe per 8 logits (measured best of 0 / 2 / 3 / 4: r01 profiles)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -108,7 +110,7 @@ struct LseSmem {
 // BOUNDED: the operands are L2-normalised, so |S2| <= log2e / tau is known up front; when that bound is small enough for fp32
 // (host checks <= 64) the running max and its rescaling are dropped: l = sum_b 2^S2, m = 0.  This is the reference's own
 // non-stabilised exp / sum form (ncl.py:362-365) and halves the epilogue's instruction count.
-template <int KC, bool BOUNDED>  // KC = number of 64-wide K chunks (d_pad = 64 * KC)
+template <int KC, bool BOUNDED, int POLY>  // KC = number of 64-wide K chunks (d_pad = 64 * KC); POLY: see ex2_mixed
 __global__ void __launch_bounds__(kLseThreads, 1)
 lse_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, long long n_b,
                   int n_tiles, int tiles_per_split, float* __restrict__ part_m, float* __restrict__ part_l,
@@ -226,7 +228,8 @@ lse_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            s0 += ex2_approx(v[j]); s1 += ex2_approx(v[j + 1]); s2 += ex2_approx(v[j + 2]); s3 += ex2_approx(v[j + 3]);
+            s0 += ex2_mixed<POLY>(v[j], j); s1 += ex2_mixed<POLY>(v[j + 1], j + 1);
+            s2 += ex2_mixed<POLY>(v[j + 2], j + 2); s3 += ex2_mixed<POLY>(v[j + 3], j + 3);
           }
           l_run += (s0 + s1) + (s2 + s3);
         } else {
@@ -241,8 +244,8 @@ lse_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              s0 += ex2_approx(v[j] - m_run); s1 += ex2_approx(v[j + 1] - m_run);
-              s2 += ex2_approx(v[j + 2] - m_run); s3 += ex2_approx(v[j + 3] - m_run);
+              s0 += ex2_mixed<POLY>(v[j] - m_run, j); s1 += ex2_mixed<POLY>(v[j + 1] - m_run, j + 1);
+              s2 += ex2_mixed<POLY>(v[j + 2] - m_run, j + 2); s3 += ex2_mixed<POLY>(v[j + 3] - m_run, j + 3);
             }
             l_run += (s0 + s1) + (s2 + s3);
           }
@@ -336,11 +339,11 @@ static int run_lse(const __nv_bfloat16* ab, long long n_a, const __nv_bfloat16* 
   const int kc = d_pad / kChunkK;
   const size_t smem = lse_smem_bytes(kc);
   dim3 grid(p.m_tiles, p.n_splits);
-#define GCF_LSE_LAUNCH2(KC, B)                                                                                         \
-  do {                                                                                                                 \
-    GCF_CUDA(cudaFuncSetAttribute(lse_stream_kernel<KC, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    lse_stream_kernel<KC, B><<<grid, kLseThreads, smem, st>>>(tm_a, tm_b, n_b, p.n_tiles, p.tiles_per_split, part_m,   \
-                                                              part_l, p.a_pad, skip_diag);                            \
+#define GCF_LSE_LAUNCH2(KC, B)                                                                                                \
+  do {                                                                                                                        \
+    GCF_CUDA(cudaFuncSetAttribute(lse_stream_kernel<KC, B, kPolyOf8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    lse_stream_kernel<KC, B, kPolyOf8><<<grid, kLseThreads, smem, st>>>(tm_a, tm_b, n_b, p.n_tiles, p.tiles_per_split, part_m,   \
+                                                                        part_l, p.a_pad, skip_diag);                           \
   } while (0)
 #define GCF_LSE_LAUNCH(KC)                                      \
   do {                                                          \
@@ -537,8 +540,8 @@ grad_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           for (int q = 0; q < 4; ++q) {
             const float sv = v[j4 + q];
             float pv = 0.f;
-            if (HAS_ROW) pv = wr * ex2_approx(sv - lr);
-            if (HAS_COL) pv = fmaf(wv[q], ex2_approx(sv - lv[q]), pv);
+            if (HAS_ROW) pv = wr * ex2_mixed<kPolyOf8>(sv - lr, j4 + q);
+            if (HAS_COL) pv = fmaf(wv[q], ex2_mixed<kPolyOf8>(sv - lv[q], j4 + q), pv);
             v[j4 + q] = pv;
           }
         }

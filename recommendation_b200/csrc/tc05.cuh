@@ -106,6 +106,26 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x on the FMA pipe (Cody-Waite split + degree-3 polynomial, max relative error 1.9e-4 -- two orders below the bf16
+// rounding of the logits it is applied to).  The MUFU pipe delivers 16 ex2 / clk / SM while the FMA pipe issues 128 lanes /
+// clk / SM, so evaluating a fraction of the exponentials here (7 FMA-pipe instructions each) raises the exp throughput of
+// the exp-bound InfoNCE epilogues.  x must be finite and >= -126 (callers clamp).
+__device__ __forceinline__ float ex2_poly3(float x) {
+  const float magic = 12582912.f;                    // 1.5 * 2^23: adding it leaves round(x) in the low mantissa bits
+  const float t = x + magic;
+  const float f = x - (t - magic);                   // f in [-0.5, 0.5]
+  float p = fmaf(0.05587569f, f, 0.24229546f);
+  p = fmaf(p, f, 0.6931273f);
+  p = fmaf(p, f, 0.9999482f);
+  // 2^round(x): add round(x) to the exponent field.  (bits(t) << 23) == round(x) << 23 because bits(magic) << 23 wraps to 0
+  return __int_as_float(__float_as_int(t) * (1 << 23) + __float_as_int(p));
+}
+// exponential of logit j of a 32-wide chunk: POLY of every 8 consecutive columns take the FMA-pipe path
+template <int POLY>
+__device__ __forceinline__ float ex2_mixed(float x, int j) {
+  return ((j & 7) < POLY) ? ex2_poly3(fmaxf(x, -126.f)) : ex2_approx(x);
+}
+
 // ---- descriptors ------------------------------------------------------------------------
 // Shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor layout, version 1 = Blackwell):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 |
