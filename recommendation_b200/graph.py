@@ -248,3 +248,31 @@ class CSRGraph:
     def __repr__(self) -> str:
         return (f"CSRGraph({self.n_rows}x{self.n_cols}, nnz={self.nnz}, symmetric={self.symmetric}, "
                 f"long_rows={self.plan.n_long}, chunks={self.plan.n_chunks})")
+
+
+# =========================================================================================
+# Reference-named helpers (selfcf.py:219-255 = ncl.py:30-44,203-209 = mhcn.py:47-84)
+# =========================================================================================
+class Graph:
+    """`Graph.normalize_graph_mat(adj_mat)` with the reference's semantics -- square: D^-1/2 A D^-1/2, otherwise D^-1 A,
+    inf -> 0 -- computed by the integer / normalisation kernels on the GPU.  Returns a scipy CSR matrix like the
+    reference (callers store it as `data.norm_adj`); `normalize_to_device` skips the download."""
+
+    @staticmethod
+    def normalize_to_device(adj_mat, device: Optional[torch.device] = None) -> CSRGraph:
+        shape = adj_mat.get_shape() if hasattr(adj_mat, "get_shape") else adj_mat.shape
+        norm = "sym" if shape[0] == shape[1] else "row"
+        return CSRGraph.from_scipy(adj_mat, norm=norm, device=device)
+
+    @staticmethod
+    def normalize_graph_mat(adj_mat):
+        return Graph.normalize_to_device(adj_mat).to_scipy()
+
+
+class TorchGraphInterface:
+    """`convert_sparse_mat_to_tensor(X)`: the reference builds an uncoalesced torch.sparse COO tensor; here the result
+    is the device CSR operator the SpMM kernels consume (use it with functional.spmm / propagate)."""
+
+    @staticmethod
+    def convert_sparse_mat_to_tensor(X, device: Optional[torch.device] = None) -> CSRGraph:
+        return CSRGraph.from_scipy(X, norm="none", device=device)

@@ -281,3 +281,25 @@ def test_ranking_measures_match_reference_fixture(cuda, golden):
         np.testing.assert_allclose([m["Hit Ratio"], m["Precision"], m["Recall"], m["NDCG"]], row, rtol=0, atol=1.1e-5)
     lines = evaluation.format_measures(got)
     assert lines[0] == "Top 5\n" and lines[1].startswith("Hit Ratio:") and len(lines) == 15
+
+
+def test_reference_named_graph_helpers(cuda, golden):
+    import scipy.sparse as sp
+    from recommendation_b200 import functional as F_
+    from recommendation_b200.graph import Graph, TorchGraphInterface
+
+    g = golden("selfcf_graph")
+    U, I = int(g["n_users"]), int(g["n_items"])
+    ui = sp.csr_matrix((g["ui_data"], g["ui_indices"], g["ui_indptr"]), shape=(U + I, U + I))       # data.ui_adj of the reference
+    norm = Graph.normalize_graph_mat(ui)                                                             # selfcf.py:240-255
+    assert np.array_equal(norm.indptr, g["norm_indptr"]) and np.array_equal(norm.indices, g["norm_indices"])
+    np.testing.assert_allclose(norm.data, g["norm_data"], rtol=3e-7)
+    rect = ui[:U, U:]                                                                                # non-square: D^-1 A
+    got = Graph.normalize_graph_mat(rect).toarray()
+    rs = np.asarray(rect.sum(1)).ravel()
+    with np.errstate(divide="ignore"):
+        dinv = np.where(rs > 0, 1.0 / rs, 0.0)
+    np.testing.assert_allclose(got, sp.diags(dinv).dot(rect).toarray(), rtol=1e-6)
+    op = TorchGraphInterface.convert_sparse_mat_to_tensor(norm)                                      # selfcf.py:219-225
+    x = torch.randn(U + I, 16, device=cuda)
+    np.testing.assert_allclose(F_.spmm(op, x).cpu().numpy(), norm.dot(x.cpu().numpy()), rtol=1e-4, atol=1e-5)

@@ -497,3 +497,59 @@ def test_fused_bpr_applies_upstream_gradient(cuda):
     with torch.no_grad():   # no gradient requested: plain forward kernel, same value
         loss2 = bpr_step_loss(ue_g.detach(), ie_g.detach(), dev_t(pu, cuda), dev_t(pi, cuda), dev_t(ni, cuda), 1e-3)
     np.testing.assert_allclose(loss2.item(), loss.item(), rtol=1e-6)
+
+
+# ====================================================================== feature-sharded building blocks on ONE GPU
+@pytest.mark.parametrize("n_shards", [2, 4, 8])
+def test_feature_slices_reproduce_the_full_step(cuda, n_shards):
+    """The pieces FeatureShardedLightGCNTrainer runs per rank (d/G-wide SpMM, raw partial scores, loss from the summed
+    scores, d/G-wide gradient pass), executed slice after slice on one GPU, against the unsharded kernels."""
+    inter = synth.power_law_bipartite(400, 600, 9000, seed=8)
+    U, I, d, K = 400, 600, 64, 2
+    dg = d // n_shards
+    lib = _lib.load(); st = _lib.current_stream()
+    g = CSRGraph.from_pairs(dev_t(inter.users, cuda), dev_t(inter.items, cuda), U, I, norm="sym", chunk=64)
+    x = torch.randn(U + I, d, device=cuda) * 0.3
+    full = F_.propagate(g, x, K, mode="sum")
+    rng = np.random.default_rng(3)
+    T = inter.n_edges
+    order = np.argsort(inter.users, kind="stable")
+    pu, pi = dev_t(inter.users[order], cuda), dev_t(inter.items[order], cuda)
+    ni = dev_t(rng.integers(0, I, T), cuda)
+    reg = 1e-3
+    ws_bytes = lib.gcf_bpr_workspace_bytes(T); ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cuda)
+    # unsharded reference: fused forward+backward on the full-width tables
+    want_loss = torch.empty((), device=cuda); want_g = torch.zeros_like(full)
+    _lib.check(lib.gcf_bpr_fwd_bwd(_lib.ptr(full[:U]), d, _lib.ptr(full[U:]), d, d, _lib.ptr(pu), _lib.ptr(pi), _lib.ptr(ni), T, 1,
+                                   _lib.BPR_SOFTPLUS, 0.0, _lib.REDUCE_MEAN, reg, reg, 0.0, 1.0, _lib.ptr(want_loss), None,
+                                   _lib.ptr(want_g[:U]), d, _lib.ptr(want_g[U:]), d, _lib.ptr(ws), ws_bytes, st), "fused")
+    scores = torch.zeros(T, device=cuda); reg_sum = torch.zeros((), device=cuda)
+    finals = []
+    for r in range(n_shards):
+        xs = x[:, r * dg:(r + 1) * dg].contiguous()
+        fs = F_.propagate(g, xs, K, mode="sum")                       # no exchange between slices
+        torch.testing.assert_close(fs, full[:, r * dg:(r + 1) * dg], rtol=1e-5, atol=1e-6)
+        finals.append(fs)
+        part = torch.empty(T, device=cuda); lr = torch.empty((), device=cuda)
+        _lib.check(lib.gcf_bpr_fwd(_lib.ptr(fs[:U]), dg, _lib.ptr(fs[U:]), dg, dg, _lib.ptr(pu), _lib.ptr(pi), _lib.ptr(ni), T, 1,
+                                   _lib.BPR_RAW_SCORE, 0.0, _lib.REDUCE_SUM, reg, reg, 0.0, _lib.ptr(lr), _lib.ptr(part),
+                                   _lib.ptr(ws), ws_bytes, st), "raw scores")
+        scores += part; reg_sum += lr                                   # = the all-reduce
+    coef = torch.empty(T, device=cuda); loss_pt = torch.empty((), device=cuda)
+    _lib.check(lib.gcf_bpr_coef_from_scores(_lib.ptr(scores), T, _lib.BPR_SOFTPLUS, 0.0, _lib.REDUCE_MEAN, _lib.ptr(loss_pt),
+                                            _lib.ptr(coef), _lib.ptr(ws), ws_bytes, st), "coef")
+    np.testing.assert_allclose((loss_pt + reg_sum).item(), want_loss.item(), rtol=1e-5)
+    for r, fs in enumerate(finals):
+        gs = torch.zeros_like(fs)
+        _lib.check(lib.gcf_bpr_bwd(_lib.ptr(fs[:U]), dg, _lib.ptr(fs[U:]), dg, dg, _lib.ptr(pu), _lib.ptr(pi), _lib.ptr(ni), T, 1,
+                                   _lib.ptr(coef), None, reg, reg, 0.0, _lib.ptr(gs[:U]), dg, _lib.ptr(gs[U:]), dg, st), "bwd")
+        torch.testing.assert_close(gs, want_g[:, r * dg:(r + 1) * dg], rtol=1e-3, atol=1e-8)
+
+
+def test_raw_score_mode_rejects_mean_reduction(cuda):
+    lib = _lib.load()
+    t = torch.zeros(4, 8, device=cuda); i = torch.zeros(2, dtype=torch.int64, device=cuda); o = torch.zeros(2, device=cuda)
+    ws = torch.empty(lib.gcf_bpr_workspace_bytes(2), dtype=torch.uint8, device=cuda)
+    rc = lib.gcf_bpr_fwd(_lib.ptr(t), 8, _lib.ptr(t), 8, 8, _lib.ptr(i), _lib.ptr(i), _lib.ptr(i), 2, 1, _lib.BPR_RAW_SCORE, 0.0,
+                         _lib.REDUCE_MEAN, 0.0, 0.0, 0.0, _lib.ptr(o), _lib.ptr(o), _lib.ptr(ws), ws.numel(), _lib.current_stream())
+    assert rc == -1 and b"raw scores need reduction = sum" in lib.gcf_last_error()
