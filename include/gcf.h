@@ -182,6 +182,15 @@ int gcf_sample_negatives(uint64_t seed, uint64_t offset, const int64_t* users, i
                          int64_t n_items, const int32_t* pos_row_ptr, const int32_t* pos_col_idx,
                          int32_t max_trials, int64_t* out, gcf_stream_t stream);
 
+/* Stochastic edge dropout of a sparse operator's values (buir.py:300-309 sparse_dropout):
+ *   out[j] = keep(e) ? vals[e] / (1 - rate) : 0,   e = index ? index[j] : j,
+ *   keep(e) <=> Philox4x32-10(counter = (e, offset), key = seed)[0] < (1 - rate) * 2^32
+ * Every stored entry is kept independently with probability 1 - rate (rate = 0 keeps all: thresh = 2^32 - 1 drops one
+ * value in 2^32).  With index = the transposition permutation of the CSR the same call yields the values of the dropped
+ * operator's TRANSPOSE (same mask per entry), which the backward of the propagation needs. */
+int gcf_csr_dropout_values(const float* vals, int64_t n, const int32_t* index, float rate, uint64_t seed, uint64_t offset,
+                           float* out, gcf_stream_t stream);
+
 /* ---- (3) losses ----------------------------------------------------------------------- */
 
 #define GCF_BPR_LOG_EPS_SIGMOID 0 /* -log(eps + sigmoid(x))      ncl.py:116-120, mhcn.py:35-39 */

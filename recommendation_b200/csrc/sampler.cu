@@ -61,9 +61,38 @@ sample_negatives_kernel(uint32_t seed_lo, uint32_t key_hi, uint32_t offset_lo, c
   }
 }
 
+// out[j] = keep(e) ? vals[e] / (1 - rate) : 0,  e = index ? index[j] : j,  keep(e) <=> Philox(e; seed, offset)[0] < (1 - rate) 2^32
+__global__ void __launch_bounds__(256)
+dropout_values_kernel(const float* __restrict__ vals, long long n, const int* __restrict__ index, uint32_t thresh, float scale,
+                      uint32_t seed_lo, uint32_t seed_hi, uint32_t off_lo, uint32_t off_hi, float* __restrict__ out) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    const long long e = index != nullptr ? (long long)index[j] : j;
+    uint32_t w[4];
+    philox4x32_10((uint32_t)e, (uint32_t)((unsigned long long)e >> 32), off_lo, off_hi, seed_lo, seed_hi, w);
+    out[j] = (w[0] < thresh) ? vals[e] * scale : 0.f;
+  }
+}
+
 }  // namespace gcf
 
 using namespace gcf;
+
+extern "C" int gcf_csr_dropout_values(const float* vals, int64_t n, const int32_t* index, float rate, uint64_t seed,
+                                      uint64_t offset, float* out, gcf_stream_t stream) {
+  GCF_REQUIRE(n >= 0, "gcf_csr_dropout_values: negative n");
+  GCF_REQUIRE(rate >= 0.f && rate < 1.f, "gcf_csr_dropout_values: rate must be in [0, 1)");
+  if (n == 0) return GCF_OK;
+  GCF_REQUIRE(vals != nullptr && out != nullptr, "gcf_csr_dropout_values: null pointers");
+  const double keep = 1.0 - (double)rate;
+  const uint32_t thresh = keep >= 1.0 ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(n, 256), (long long)sm_count() * 16));
+  dropout_values_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      vals, n, index, thresh, (float)(1.0 / keep), (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)offset,
+      (uint32_t)(offset >> 32), out);
+  GCF_LAUNCH_CHECK("dropout_values_kernel");
+  return GCF_OK;
+}
+
 
 extern "C" int gcf_sample_negatives(uint64_t seed, uint64_t offset, const int64_t* users, int64_t n, int32_t n_negs,
                                     int64_t n_items, const int32_t* pos_row_ptr, const int32_t* pos_col_idx,

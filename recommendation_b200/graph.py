@@ -216,6 +216,51 @@ class CSRGraph:
             self._transpose._transpose = self
         return self._transpose
 
+    def with_values(self, vals: torch.Tensor, *, symmetric: bool = False) -> "CSRGraph":
+        """Same sparsity pattern and long-row schedule, different values (shares row_ptr / col_idx / workspaces)."""
+        if vals.shape != self.vals.shape or vals.dtype != torch.float32 or not vals.is_cuda:
+            raise ValueError("with_values: need a float32 CUDA tensor with one value per stored entry")
+        g = object.__new__(CSRGraph)
+        g.__dict__.update(self.__dict__)
+        g.__dict__.pop("_tperm", None)
+        g.vals = vals.contiguous()
+        g.symmetric = symmetric
+        g._transpose = None
+        g.rowsum = g.dinv = None
+        g._struct = _lib.CsrStruct.from_buffer_copy(self._struct)
+        g._struct.vals = g.vals.data_ptr() if self.nnz else None
+        return g
+
+    def transpose_permutation(self) -> torch.Tensor:
+        """perm int32 [nnz]: entry j of the transposed CSR is entry perm[j] of this one (cached).  The stable transpose
+        kernel moves the value payload bit for bit, so the entry ids ride through it re-interpreted as float32."""
+        p = getattr(self, "_tperm", None)
+        if p is None:
+            ids = torch.arange(self.nnz, dtype=torch.int32, device=self.device).view(torch.float32)
+            p = self.with_values(ids).transpose().vals.view(torch.int32)   # with_values() drops the "symmetric" shortcut
+            self._tperm = p
+        return p
+
+    def dropout(self, rate: float, *, seed: int, offset: int = 0) -> "CSRGraph":
+        """Entry-wise dropout of the operator (sparse_dropout, buir.py:300-309): every stored entry kept independently with
+        probability 1 - rate and rescaled by 1 / (1 - rate).  The result carries its exact transpose (same mask), so
+        autograd through functional.spmm / propagate is consistent.  The pattern is kept; dropped entries are zeros."""
+        lib = _lib.load()
+        st = _lib.current_stream()
+        seed, offset = int(seed) & (2**64 - 1), int(offset) & (2**64 - 1)
+        out = torch.empty_like(self.vals)
+        _lib.check(lib.gcf_csr_dropout_values(_lib.ptr(self.vals), self.nnz, None, float(rate), seed, offset, _lib.ptr(out), st),
+                   "gcf_csr_dropout_values")
+        fwd = self.with_values(out)
+        # the transpose keeps ITS pattern too (self for a symmetric operator); only the values move, through the permutation
+        base_t, perm = self.transpose(), self.transpose_permutation()
+        out_t = torch.empty_like(self.vals)
+        _lib.check(lib.gcf_csr_dropout_values(_lib.ptr(self.vals), self.nnz, _lib.ptr(perm), float(rate), seed, offset,
+                                              _lib.ptr(out_t), st), "gcf_csr_dropout_values")
+        bwd = base_t.with_values(out_t)
+        fwd._transpose, bwd._transpose = bwd, fwd
+        return fwd
+
     # ---- plumbing for the kernels ---------------------------------------------------------
     @property
     def struct(self) -> "_lib.CsrStruct":

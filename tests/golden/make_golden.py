@@ -60,7 +60,7 @@ def tiny_dataset(seed=7, n_users=37, n_items=53, n_inter=420, n_dups=17):
 
 
 def t2n(t):
-    return t.detach().cpu().numpy()
+    return t.detach().cpu().numpy().copy()   # copy: the array must not alias a parameter that is updated in place later
 
 
 def grads_of(loss, *params):
@@ -277,6 +277,30 @@ def main():
              user_w=t2n(ns2.user_embeddings), item_w=t2n(ns2.item_embeddings), weights=np.stack([t2n(w) for w in ns2.weights]),
              u_idx=t2n(du), i_idx=t2n(di), j_idx=t2n(dj), final_user=t2n(fu), loss=t2n(dloss),
              g_user_w=dg[0], g_item_w=dg[1], g_weights=np.stack(dg[2:]))
+    # ------------------------------------------------------------------ buir (univariate/buir.py): BUIR_NB without dropout
+    bu_mod = load_ref("buir", "univariate/buir.py", stubs=("tensorflow", "faiss"))
+    bdata = bu_mod.Interaction({}, [list(r) for r in train], [list(r) for r in test])
+    bna = bdata.norm_adj.tocsr(); bna.sort_indices()
+    torch.manual_seed(9)
+    bm = bu_mod.BUIR_NB(bdata, d, 0.9, 2, 0.2, drop_flag=False)
+    with torch.no_grad():  # make online and target differ, as after a few updates
+        bm.target_encoder.embedding_dict["user_emb"].mul_(0.7); bm.target_encoder.embedding_dict["item_emb"].add_(0.01)
+    brng = np.random.default_rng(13)
+    b_users = brng.integers(0, bdata.user_num, 24).tolist(); b_items = brng.integers(0, bdata.item_num, 24).tolist()
+    tgt_u0 = t2n(bm.target_encoder.embedding_dict["user_emb"]); tgt_i0 = t2n(bm.target_encoder.embedding_dict["item_emb"])
+    bout = bm({"user": b_users, "item": b_items})
+    bloss = bm.get_loss(bout)
+    bparams = [bm.online_encoder.embedding_dict["user_emb"], bm.online_encoder.embedding_dict["item_emb"], bm.predictor.weight, bm.predictor.bias]
+    bg = grads_of(bloss, *bparams)
+    bm.update_target(b_users, b_items)
+    np.savez(OUT / "buir_nb.npz", n_users=bdata.user_num, n_items=bdata.item_num, momentum=0.9, n_layers=2,
+             norm_indptr=bna.indptr, norm_indices=bna.indices, norm_data=bna.data.astype(np.float32),
+             users=np.array(b_users), items=np.array(b_items), online_user=t2n(bparams[0]), online_item=t2n(bparams[1]),
+             target_user0=tgt_u0, target_item0=tgt_i0, pred_w=t2n(bparams[2]), pred_b=t2n(bparams[3]),
+             out_u_online=t2n(bout[0]), out_u_target=t2n(bout[1]), out_i_online=t2n(bout[2]), out_i_target=t2n(bout[3]),
+             loss=t2n(bloss), g_user=bg[0], g_item=bg[1], g_pred_w=bg[2], g_pred_b=bg[3],
+             target_user1=t2n(bm.target_encoder.embedding_dict["user_emb"]), target_item1=t2n(bm.target_encoder.embedding_dict["item_emb"]))
+
     # ------------------------------------------------------------------ ranking_evaluation (ncl.py:133-178) on random lists
     erng = np.random.default_rng(21)
     eU, eI, eN = 30, 80, 20

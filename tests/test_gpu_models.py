@@ -303,3 +303,77 @@ def test_reference_named_graph_helpers(cuda, golden):
     op = TorchGraphInterface.convert_sparse_mat_to_tensor(norm)                                      # selfcf.py:219-225
     x = torch.randn(U + I, 16, device=cuda)
     np.testing.assert_allclose(F_.spmm(op, x).cpu().numpy(), norm.dot(x.cpu().numpy()), rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ BUIR + edge dropout (8f row 3)
+def test_buir_nb_fixture(cuda, golden):
+    from recommendation_b200 import buir
+
+    z = golden("buir_nb")
+    U, I = int(z["n_users"]), int(z["n_items"])
+    data = SimpleNamespace(user_num=U, item_num=I, norm_adj=sp.csr_matrix((z["norm_data"], z["norm_indices"], z["norm_indptr"]), shape=(U + I, U + I)))
+    m = buir.BUIR_NB(data, z["online_user"].shape[1], float(z["momentum"]), int(z["n_layers"]), 0.2, drop_flag=False)
+    keys = sorted(m.state_dict().keys())
+    assert keys == sorted(["online_encoder.embedding_dict.user_emb", "online_encoder.embedding_dict.item_emb",
+                           "target_encoder.embedding_dict.user_emb", "target_encoder.embedding_dict.item_emb", "predictor.weight", "predictor.bias"])
+    assert not any(p.requires_grad for p in m.target_encoder.parameters())
+    m.load_state_dict({"online_encoder.embedding_dict.user_emb": torch.from_numpy(z["online_user"]),
+                       "online_encoder.embedding_dict.item_emb": torch.from_numpy(z["online_item"]),
+                       "target_encoder.embedding_dict.user_emb": torch.from_numpy(z["target_user0"]),
+                       "target_encoder.embedding_dict.item_emb": torch.from_numpy(z["target_item0"]),
+                       "predictor.weight": torch.from_numpy(z["pred_w"]), "predictor.bias": torch.from_numpy(z["pred_b"])})
+    users, items = z["users"].tolist(), z["items"].tolist()
+    out = m({"user": users, "item": items})
+    for got, key in zip(out, ("out_u_online", "out_u_target", "out_i_online", "out_i_target")):
+        _close(got, z[key], atol=1e-5)
+    loss = m.get_loss(out)
+    _close(loss, z["loss"], rtol=1e-4)
+    loss.backward()
+    on = m.online_encoder.embedding_dict
+    _close(on["user_emb"].grad, z["g_user"], atol=1e-6); _close(on["item_emb"].grad, z["g_item"], atol=1e-6)
+    _close(m.predictor.weight.grad, z["g_pred_w"], atol=1e-6); _close(m.predictor.bias.grad, z["g_pred_b"], atol=1e-6)
+    m.update_target(users, items)
+    tg = m.target_encoder.embedding_dict
+    _close(tg["user_emb"], z["target_user1"], atol=1e-6); _close(tg["item_emb"], z["target_item1"], atol=1e-6)
+
+
+def test_edge_dropout_operator(cuda):
+    """gcf_csr_dropout_values: mask bit-exact vs the Philox oracle, kept values rescaled, the attached transpose is the exact
+    transpose of the dropped operator, and autograd through the dropped propagation matches a dense fp64 reference."""
+    from oracle import philox_ref
+    from recommendation_b200 import functional as F_, synth
+
+    inter = synth.power_law_bipartite(300, 400, 6000, seed=12)
+    g = CSRGraph.from_pairs(torch.from_numpy(inter.users).to(cuda), torch.from_numpy(inter.items).to(cuda), 300, 400, norm="sym", chunk=64)
+    rate, seed, off = 0.3, 77, 5
+    gd = g.dropout(rate, seed=seed, offset=off)
+    words = philox_ref.philox4x32_10((np.arange(g.nnz, dtype=np.uint32), np.uint32(0), np.uint32(off), np.uint32(0)),
+                                     (np.uint32(seed), np.uint32(0)))[0]
+    keep = words < np.uint32(int((1 - rate) * 4294967296.0))
+    want = np.where(keep, g.vals.cpu().numpy() * np.float32(1.0 / (1.0 - rate)), np.float32(0))
+    np.testing.assert_array_equal(gd.vals.cpu().numpy(), want.astype(np.float32))
+    assert abs(keep.mean() - (1 - rate)) < 0.02
+    a = gd.to_scipy()
+    assert abs(a - a.T).max() > 0                                   # entries are dropped independently per direction
+    at = gd.transpose().to_scipy()
+    assert abs(at - a.T).max() == 0                                 # the attached transpose is exact
+    assert g.dropout(0.0, seed=1).vals.equal(g.vals)
+    d, K = 32, 2
+    x = (torch.randn(700, d, device=cuda) * 0.2).requires_grad_(True)
+    w = torch.randn(700, d, device=cuda)
+    (F_.propagate(gd, x, K, mode="mean") * w).sum().backward()
+    ad = torch.from_numpy(a.toarray()).double()
+    xd = x.detach().cpu().double().requires_grad_(True)
+    layers = [xd]
+    for _ in range(K):
+        layers.append(ad @ layers[-1])
+    (torch.stack(layers).mean(0) * w.cpu().double()).sum().backward()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), xd.grad.numpy(), rtol=1e-3, atol=1e-6)
+    # the encoder draws a fresh mask per forward when drop_flag is set
+    from recommendation_b200 import buir
+    data = SimpleNamespace(user_num=300, item_num=400, norm_adj=g.to_scipy())
+    enc = buir.LGCN_Encoder(data, 16, 2, 0.5, drop_flag=True)
+    o1 = enc({"user": [1, 2, 3], "item": [4, 5, 6]})[0]; o2 = enc({"user": [1, 2, 3], "item": [4, 5, 6]})[0]
+    assert not torch.equal(o1, o2)
+    e1 = enc.get_embedding()[0]; e2 = enc.get_embedding()[0]
+    assert torch.equal(e1, e2)                                      # evaluation uses the full operator

@@ -278,3 +278,32 @@ def test_eval_measures_match_reference(golden):
     got = eval_ref.measures(z["lists"], tests, [int(n) for n in z["top_ns"]])
     for row, n in zip(z["measures"], z["top_ns"]):
         np.testing.assert_allclose(got[int(n)], row, rtol=0, atol=1e-5)
+
+
+def test_buir_nb_matches_reference(golden):
+    """BUIR_NB (univariate/buir.py:236-277) without dropout: online / target propagation, predictor, loss, momentum update."""
+    z = golden("buir_nb")
+    U, I, K, mom = int(z["n_users"]), int(z["n_items"]), int(z["n_layers"]), float(z["momentum"])
+    rp, ci, v = z["norm_indptr"], z["norm_indices"], z["norm_data"]
+    A = torch.zeros(U + I, U + I, dtype=torch.float64)
+    A[torch.from_numpy(np.repeat(np.arange(U + I), np.diff(rp))), torch.from_numpy(ci.astype(np.int64))] = torch.from_numpy(v).double()
+
+    def enc(uw, iw):
+        x = torch.cat([uw, iw]); layers = [x]
+        for _ in range(K):
+            layers.append(A @ layers[-1])
+        f = torch.stack(layers, 1).mean(1)
+        return f[:U], f[U:]
+    ou, oi = T(z["online_user"].astype(np.float64), True), T(z["online_item"].astype(np.float64), True)
+    W, b = T(z["pred_w"].astype(np.float64), True), T(z["pred_b"].astype(np.float64), True)
+    users, items = T(z["users"]), T(z["items"])
+    uo, io = enc(ou, oi)
+    ut, it = enc(T(z["target_user0"].astype(np.float64)), T(z["target_item0"].astype(np.float64)))
+    out = (uo[users] @ W.T + b, ut[users], io[items] @ W.T + b, it[items])
+    for got, key in zip(out, ("out_u_online", "out_u_target", "out_i_online", "out_i_target")):
+        np.testing.assert_allclose(got.detach().numpy(), z[key], rtol=1e-4, atol=1e-5)
+    n = lambda t: torch.nn.functional.normalize(t, dim=-1)
+    loss = ((2 - 2 * (n(out[0]) * n(out[3])).sum(-1)) + (2 - 2 * (n(out[2]) * n(out[1])).sum(-1))).mean()
+    _check(loss, (ou, oi, W, b), z["loss"], (z["g_user"], z["g_item"], z["g_pred_w"], z["g_pred_b"]), rtol=1e-4)
+    t1 = z["target_user0"].copy(); t1[z["users"]] = z["target_user0"][z["users"]] * mom + z["online_user"][z["users"]] * (1 - mom)
+    np.testing.assert_allclose(t1, z["target_user1"], rtol=1e-6, atol=1e-7)
