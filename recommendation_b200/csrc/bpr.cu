@@ -549,10 +549,10 @@ extern "C" int gcf_bpr_bwd(const float* user_emb, int64_t ld_user, const float* 
   const long long grid = bpr_blocks(n_triples, lpr_for(d));
   GCF_REQUIRE(grid < 2147483647LL, "gcf_bpr_bwd: too many triples for one launch");
   const int dvec = d / 4;
-  static const int bwd_batch = [] { const char* e = getenv("GCF_BPR_BWD_BATCH"); return e ? atoi(e) : 2; }();
-  if (d == 64 && bwd_batch == 2)
+  // d = 64 / 128: two triples in flight per sub-warp (128 registers with four) -- measured best on cfg1 and cfg5
+  if (d == 64)
     bpr_bwd_kernel<16, 1, false, 2><<<grid, kBprThreads, 0, st>>>(user_emb, ld_user, item_emb, ld_item, dvec, u_idx, p_idx, n_idx, n_triples, n_negs, coef, grad_out, reg_u, reg_p, reg_n, g_user, ldg_user, g_item, ldg_item);
-  else if (d == 128 && bwd_batch == 2)
+  else if (d == 128)
     bpr_bwd_kernel<32, 1, false, 2><<<grid, kBprThreads, 0, st>>>(user_emb, ld_user, item_emb, ld_item, dvec, u_idx, p_idx, n_idx, n_triples, n_negs, coef, grad_out, reg_u, reg_p, reg_n, g_user, ldg_user, g_item, ldg_item);
   else
     GCF_BPR_DISPATCH(bpr_bwd_kernel, user_emb, ld_user, item_emb, ld_item, dvec, u_idx, p_idx, n_idx, n_triples, n_negs,
