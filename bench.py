@@ -254,7 +254,7 @@ def run_ours(args):
         # all-gathers run inside row groups on d/F-wide rows.  Default picked from the measured r01 sweep.
         F = args.feature_shards
         if F <= 0:
-            F = {2: 2, 4: 2, 8: 4}.get(world, 1)
+            F = {2: 2, 4: 4, 8: 4}.get(world, 1)
         while F > 1 and (world % F != 0 or d % F != 0 or (d // F) % 4 != 0 or d // F < 8):
             F //= 2
         if F == world:
