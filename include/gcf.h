@@ -155,6 +155,16 @@ int gcf_propagate_bwd(const gcf_csr_t* At, int32_t d, int32_t n_layers, const fl
                       const float* const* extra, float scale, float* ping, float* pong, float* g_x0,
                       void* workspace, size_t workspace_bytes, gcf_stream_t stream);
 
+/* gcf_propagate_bwd with the optimiser fused into the epilogue of its LAST SpMM: G(0), the gradient of the embedding
+ * table, is consumed row by row by an in-place Adam / AdamW update of param / exp_avg / exp_avg_sq ([n_rows, d], ld = d;
+ * torch.optim.Adam numerics, see gcf_adam_step) instead of being written out and read back.  g_x0 may be NULL (the
+ * gradient is then never materialised) or a buffer that additionally receives it. */
+int gcf_propagate_bwd_adam(const gcf_csr_t* At, int32_t d, int32_t n_layers, const float* g_final,
+                           const float* const* extra, float scale, float* ping, float* pong, float* g_x0,
+                           float* param, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, int32_t decoupled, int64_t step,
+                           void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+
 /* ---- (4) gather / scatter-add / sampler ----------------------------------------------- */
 
 /* out[t, :] = table[idx[t], :]   (x[idx], ncl.py:314-316, lightgcn.py:95-102, ...) */

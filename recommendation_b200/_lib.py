@@ -59,6 +59,9 @@ _SIGNATURES = {
                                     c_void_p, c_size_t, c_void_p]),
     "gcf_propagate_bwd": (c_int32, [POINTER(CsrStruct), c_int32, c_int32, c_void_p, POINTER(c_void_p), c_float,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gcf_propagate_bwd_adam": (c_int32, [POINTER(CsrStruct), c_int32, c_int32, c_void_p, POINTER(c_void_p), c_float,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
+                                         c_float, c_float, c_int32, c_int64, c_void_p, c_size_t, c_void_p]),
     "gcf_gather_rows": (c_int32, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "gcf_scatter_add_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
     "gcf_scatter_add_rows": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32,

@@ -1,6 +1,7 @@
 // Shared helpers for libgcf (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdint>
 #include <cstddef>
 #include "../../include/gcf.h"
@@ -126,6 +127,38 @@ __device__ __forceinline__ void f4_fma(float4& a, float s, const float4& x) {
 __device__ __forceinline__ void f4_add(float4& a, const float4& x) { a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w; }
 __device__ __forceinline__ float f4_dot(const float4& a, const float4& b) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+// ---- Adam (torch.optim.Adam single-tensor update order; see optim.cu) --------------------------
+struct AdamArgs {
+  float one_minus_b1, b2, one_minus_b2, eps, wd, decay_mul, step_size, bc2_sqrt;
+  int decoupled;
+};
+
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamArgs& a) {
+  if (a.decoupled) p *= a.decay_mul;
+  else if (a.wd != 0.f) g = fmaf(a.wd, p, g);
+  m = fmaf(g - m, a.one_minus_b1, m);
+  v = fmaf(a.one_minus_b2 * g, g, a.b2 * v);
+  const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+  p = fmaf(-a.step_size, m / denom, p);
+}
+
+// host: hyper-parameters + 1-based step count -> the constants of one update
+inline AdamArgs make_adam_args(float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled, long long step) {
+  AdamArgs a;
+  a.one_minus_b1 = 1.f - beta1;
+  a.b2 = beta2;
+  a.one_minus_b2 = 1.f - beta2;
+  a.eps = eps;
+  a.wd = weight_decay;
+  a.decoupled = decoupled ? 1 : 0;
+  a.decay_mul = 1.f - lr * weight_decay;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  a.step_size = (float)((double)lr / bc1);
+  a.bc2_sqrt = (float)sqrt(bc2);
+  return a;
 }
 
 }  // namespace gcf

@@ -9,20 +9,6 @@
 
 namespace gcf {
 
-struct AdamArgs {
-  float one_minus_b1, b2, one_minus_b2, eps, wd, decay_mul, step_size, bc2_sqrt;
-  int decoupled;
-};
-
-__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamArgs& a) {
-  if (a.decoupled) p *= a.decay_mul;
-  else if (a.wd != 0.f) g = fmaf(a.wd, p, g);
-  m = fmaf(g - m, a.one_minus_b1, m);
-  v = fmaf(a.one_minus_b2 * g, g, a.b2 * v);
-  const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
-  p = fmaf(-a.step_size, m / denom, p);
-}
-
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
             long long n, AdamArgs a) {
@@ -70,18 +56,7 @@ extern "C" int gcf_adam_step(float* param, const float* grad, float* exp_avg, fl
   GCF_REQUIRE(param && grad && exp_avg && exp_avg_sq, "gcf_adam_step: null pointers");
   auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   GCF_REQUIRE(a16(param) && a16(grad) && a16(exp_avg) && a16(exp_avg_sq), "gcf_adam_step: pointers must be 16B aligned");
-  AdamArgs a;
-  a.one_minus_b1 = 1.f - beta1;
-  a.b2 = beta2;
-  a.one_minus_b2 = 1.f - beta2;
-  a.eps = eps;
-  a.wd = weight_decay;
-  a.decoupled = decoupled ? 1 : 0;
-  a.decay_mul = 1.f - lr * weight_decay;
-  const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
-  a.step_size = (float)((double)lr / bc1);
-  a.bc2_sqrt = (float)std::sqrt(bc2);
+  const AdamArgs a = make_adam_args(lr, beta1, beta2, eps, weight_decay, decoupled, step);
   const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(n / 4 + 1, 256), (long long)sm_count() * 16));
   adam_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, a);
   GCF_LAUNCH_CHECK("adam_kernel");

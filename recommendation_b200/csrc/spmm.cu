@@ -27,6 +27,10 @@ struct Epi {
   int n_add;
   const float* add[GCF_MAX_ADDENDS];
   float beta[GCF_MAX_ADDENDS];
+  // optional fused optimiser: the epilogue value IS the gradient of row `row` of a dense [n_rows, d] table (ld = ldo);
+  // Adam is applied in place and the gradient is not stored unless O is given (gcf_propagate_bwd_adam)
+  float* ad_p; float* ad_m; float* ad_v;
+  AdamArgs adam;
 };
 
 struct LongPlan {
@@ -113,7 +117,7 @@ __device__ __forceinline__ void finish_row(const Epi& ep, long long row, int sl,
       if (!GUARD || idx < dvec) y[idx] = acc[k];
     }
   }
-  if (ep.O != nullptr) {
+  if (ep.O != nullptr || ep.ad_p != nullptr) {
     float inv = 1.f;
     if (ep.epilogue == GCF_EPILOGUE_L2NORM) {
       float ss = 0.f;
@@ -124,7 +128,7 @@ __device__ __forceinline__ void finish_row(const Epi& ep, long long row, int sl,
       inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(|x|, eps)
     }
     const float a = ep.alpha * inv;
-    float4* o = reinterpret_cast<float4*>(ep.O + row * ep.ldo);
+    float4* o = ep.O != nullptr ? reinterpret_cast<float4*>(ep.O + row * ep.ldo) : nullptr;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int idx = sl + k * LPR;
@@ -136,7 +140,18 @@ __device__ __forceinline__ void finish_row(const Epi& ep, long long row, int sl,
         }
         f4_fma(r, a, acc[k]);
         r.x *= ep.post; r.y *= ep.post; r.z *= ep.post; r.w *= ep.post;
-        o[idx] = r;
+        if (o != nullptr) o[idx] = r;
+        if (ep.ad_p != nullptr) {
+          float4* p4 = reinterpret_cast<float4*>(ep.ad_p + row * ep.ldo) + idx;
+          float4* m4 = reinterpret_cast<float4*>(ep.ad_m + row * ep.ldo) + idx;
+          float4* v4 = reinterpret_cast<float4*>(ep.ad_v + row * ep.ldo) + idx;
+          float4 p = *p4, mm = *m4, vv = *v4;
+          adam_update(p.x, r.x, mm.x, vv.x, ep.adam);
+          adam_update(p.y, r.y, mm.y, vv.y, ep.adam);
+          adam_update(p.z, r.z, mm.z, vv.z, ep.adam);
+          adam_update(p.w, r.w, mm.w, vv.w, ep.adam);
+          *p4 = p; *m4 = mm; *v4 = vv;
+        }
       }
     }
   }
@@ -267,13 +282,17 @@ extern "C" size_t gcf_spmm_workspace_bytes(const gcf_csr_t* A, int32_t d) {
   return gcf_spmm_counter_offset(A, d) + align_up((size_t)A->n_long * sizeof(int32_t));
 }
 
-extern "C" int gcf_spmm_csr_f32(const gcf_csr_t* A, int32_t d, const float* X, int64_t ldx, float* Y, int64_t ldy,
-                                float* OUT, int64_t ld_out, int32_t epilogue, float alpha, float post,
-                                int32_t n_addends, const float* const* addends, const float* betas, void* workspace,
-                                size_t workspace_bytes, int32_t variant, gcf_stream_t stream) {
+namespace gcf {
+struct AdamFuse { float* param; float* m; float* v; AdamArgs args; };
+}
+
+static int spmm_impl(const gcf_csr_t* A, int32_t d, const float* X, int64_t ldx, float* Y, int64_t ldy, float* OUT,
+                     int64_t ld_out, int32_t epilogue, float alpha, float post, int32_t n_addends,
+                     const float* const* addends, const float* betas, void* workspace, size_t workspace_bytes,
+                     int32_t variant, gcf_stream_t stream, const AdamFuse* adam) {
   GCF_REQUIRE(A != nullptr && X != nullptr, "gcf_spmm_csr_f32: null operator or X");
   GCF_REQUIRE(A->n_rows >= 0 && A->n_cols >= 0, "gcf_spmm_csr_f32: negative shape");
-  GCF_REQUIRE(Y != nullptr || OUT != nullptr, "gcf_spmm_csr_f32: no output requested");
+  GCF_REQUIRE(Y != nullptr || OUT != nullptr || adam != nullptr, "gcf_spmm_csr_f32: no output requested");
   if (d <= 0 || (d & 3) != 0 || d > 1024) {
     set_error("gcf_spmm_csr_f32: d=%d unsupported (need d %% 4 == 0 and d <= 1024)", d);
     return GCF_EUNSUPPORTED;
@@ -282,8 +301,10 @@ extern "C" int gcf_spmm_csr_f32(const gcf_csr_t* A, int32_t d, const float* X, i
   GCF_REQUIRE(Y == nullptr || (ldy >= d && (ldy & 3) == 0 && aligned16(Y)), "gcf_spmm_csr_f32: bad Y alignment/ld");
   GCF_REQUIRE(OUT == nullptr || (ld_out >= d && (ld_out & 3) == 0 && aligned16(OUT)), "gcf_spmm_csr_f32: bad OUT alignment/ld");
   GCF_REQUIRE(n_addends >= 0 && n_addends <= GCF_MAX_ADDENDS, "gcf_spmm_csr_f32: n_addends out of range");
-  GCF_REQUIRE(n_addends == 0 || (addends != nullptr && betas != nullptr && OUT != nullptr),
+  GCF_REQUIRE(n_addends == 0 || (addends != nullptr && betas != nullptr && (OUT != nullptr || adam != nullptr)),
               "gcf_spmm_csr_f32: addends need OUT, pointer and beta arrays");
+  GCF_REQUIRE(adam == nullptr || (ld_out >= d && (ld_out & 3) == 0 && aligned16(adam->param) && aligned16(adam->m) && aligned16(adam->v)),
+              "gcf_spmm_csr_f32: fused Adam needs 16B aligned tables and their leading dimension in ld_out");
   GCF_REQUIRE(epilogue == GCF_EPILOGUE_NONE || epilogue == GCF_EPILOGUE_L2NORM, "gcf_spmm_csr_f32: bad epilogue");
   if (A->n_rows == 0) return GCF_OK;
   GCF_REQUIRE(A->row_ptr != nullptr, "gcf_spmm_csr_f32: null row_ptr");
@@ -291,6 +312,9 @@ extern "C" int gcf_spmm_csr_f32(const gcf_csr_t* A, int32_t d, const float* X, i
   Epi ep;
   ep.Y = Y; ep.ldy = ldy; ep.O = OUT; ep.ldo = ld_out;
   ep.epilogue = epilogue; ep.alpha = alpha; ep.post = post; ep.n_add = n_addends;
+  ep.ad_p = ep.ad_m = ep.ad_v = nullptr;
+  ep.adam = AdamArgs{};
+  if (adam != nullptr) { ep.ad_p = adam->param; ep.ad_m = adam->m; ep.ad_v = adam->v; ep.adam = adam->args; }
   for (int q = 0; q < GCF_MAX_ADDENDS; ++q) { ep.add[q] = nullptr; ep.beta[q] = 0.f; }
   for (int q = 0; q < n_addends; ++q) {
     GCF_REQUIRE(addends[q] != nullptr && aligned16(addends[q]), "gcf_spmm_csr_f32: addend %d null or misaligned", q);
@@ -340,6 +364,14 @@ extern "C" int gcf_spmm_csr_f32(const gcf_csr_t* A, int32_t d, const float* X, i
   return launch<32, 8, 2, true, 1>(A, X, ldx, dvec, ep, lp, st);
 }
 
+extern "C" int gcf_spmm_csr_f32(const gcf_csr_t* A, int32_t d, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                                float* OUT, int64_t ld_out, int32_t epilogue, float alpha, float post,
+                                int32_t n_addends, const float* const* addends, const float* betas, void* workspace,
+                                size_t workspace_bytes, int32_t variant, gcf_stream_t stream) {
+  return spmm_impl(A, d, X, ldx, Y, ldy, OUT, ld_out, epilogue, alpha, post, n_addends, addends, betas, workspace,
+                   workspace_bytes, variant, stream, nullptr);
+}
+
 extern "C" int gcf_propagate_fwd(const gcf_csr_t* A, int32_t d, int32_t n_layers, const float* X0,
                                  float* const* layers, float* final_out, float scale, void* workspace,
                                  size_t workspace_bytes, gcf_stream_t stream) {
@@ -373,10 +405,10 @@ extern "C" int gcf_propagate_fwd(const gcf_csr_t* A, int32_t d, int32_t n_layers
   return GCF_OK;
 }
 
-extern "C" int gcf_propagate_bwd(const gcf_csr_t* At, int32_t d, int32_t n_layers, const float* g_final,
-                                 const float* const* extra, float scale, float* ping, float* pong, float* g_x0,
-                                 void* workspace, size_t workspace_bytes, gcf_stream_t stream) {
-  GCF_REQUIRE(At != nullptr && g_x0 != nullptr, "gcf_propagate_bwd: null operator or output");
+static int propagate_bwd_impl(const gcf_csr_t* At, int32_t d, int32_t n_layers, const float* g_final,
+                              const float* const* extra, float scale, float* ping, float* pong, float* g_x0,
+                              void* workspace, size_t workspace_bytes, gcf_stream_t stream, const AdamFuse* adam) {
+  GCF_REQUIRE(At != nullptr && (g_x0 != nullptr || adam != nullptr), "gcf_propagate_bwd: null operator or output");
   GCF_REQUIRE(n_layers >= 1 && n_layers <= GCF_MAX_ADDENDS, "gcf_propagate_bwd: n_layers must be in [1, %d]", GCF_MAX_ADDENDS);
   GCF_REQUIRE(At->n_rows == At->n_cols, "gcf_propagate_bwd: operator must be square");
   GCF_REQUIRE(n_layers == 1 || (ping != nullptr && pong != nullptr), "gcf_propagate_bwd: ping/pong scratch required");
@@ -414,12 +446,29 @@ extern "C" int gcf_propagate_bwd(const gcf_csr_t* At, int32_t d, int32_t n_layer
     int na = 0;
     if (g_final != nullptr) { adds[na] = g_final; betas[na] = scale; ++na; }
     if (ex(k) != nullptr) { adds[na] = ex(k); betas[na] = 1.f; ++na; }
-    int rc = gcf_spmm_csr_f32(At, d, cur, d, nullptr, 0, out, d, GCF_EPILOGUE_NONE, cur_alpha, 1.f, na, adds, betas,
-                              workspace, workspace_bytes, 0, stream);
+    int rc = spmm_impl(At, d, cur, d, nullptr, 0, out, d, GCF_EPILOGUE_NONE, cur_alpha, 1.f, na, adds, betas, workspace,
+                       workspace_bytes, 0, stream, k == 0 ? adam : nullptr);
     if (rc != GCF_OK) return rc;
     cur = out;
     cur_alpha = 1.f;
     which ^= 1;
   }
   return GCF_OK;
+}
+
+extern "C" int gcf_propagate_bwd(const gcf_csr_t* At, int32_t d, int32_t n_layers, const float* g_final,
+                                 const float* const* extra, float scale, float* ping, float* pong, float* g_x0,
+                                 void* workspace, size_t workspace_bytes, gcf_stream_t stream) {
+  return propagate_bwd_impl(At, d, n_layers, g_final, extra, scale, ping, pong, g_x0, workspace, workspace_bytes, stream, nullptr);
+}
+
+extern "C" int gcf_propagate_bwd_adam(const gcf_csr_t* At, int32_t d, int32_t n_layers, const float* g_final,
+                                      const float* const* extra, float scale, float* ping, float* pong, float* g_x0,
+                                      float* param, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2,
+                                      float eps, float weight_decay, int32_t decoupled, int64_t step, void* workspace,
+                                      size_t workspace_bytes, gcf_stream_t stream) {
+  GCF_REQUIRE(param && exp_avg && exp_avg_sq, "gcf_propagate_bwd_adam: null optimiser state");
+  GCF_REQUIRE(step >= 1, "gcf_propagate_bwd_adam: step must be >= 1");
+  AdamFuse af{param, exp_avg, exp_avg_sq, make_adam_args(lr, beta1, beta2, eps, weight_decay, decoupled, step)};
+  return propagate_bwd_impl(At, d, n_layers, g_final, extra, scale, ping, pong, g_x0, workspace, workspace_bytes, stream, &af);
 }

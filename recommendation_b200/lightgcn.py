@@ -140,9 +140,10 @@ class FusedLightGCNTrainer:
     def __init__(self, graph: CSRGraph, n_users: int, n_items: int, table: torch.Tensor, pos_u: torch.Tensor,
                  pos_i: torch.Tensor, *, n_layers: int = 3, lr: float = 0.01, reg_weight: float = 1e-4,
                  weight_decay: float = 0.0, n_neg: int = 1, seed: int = 0, sort_triples: bool = True,
-                 fused_bpr: bool = True):
+                 fused_bpr: bool = True, fused_adam: bool = True):
         self.lib = _lib.load()
         self.fused_bpr = fused_bpr
+        self.fused_adam = fused_adam
         self.order = None
         self.graph, self.n_users, self.n_items = graph, n_users, n_items
         self.table = table
@@ -165,7 +166,7 @@ class FusedLightGCNTrainer:
         self.g_final = torch.empty_like(table)
         self.ping = torch.empty_like(table) if n_layers > 1 else None
         self.pong = torch.empty_like(table) if n_layers > 1 else None
-        self.g_x0 = torch.empty_like(table)
+        self.g_x0 = None if fused_adam else torch.empty_like(table)  # fused Adam consumes G(0) inside the last SpMM
         self.exp_avg = torch.zeros_like(table)
         self.exp_avg_sq = torch.zeros_like(table)
         self.neg = torch.empty(self.n_triples * n_neg, dtype=torch.int64, device=dev)
@@ -176,7 +177,7 @@ class FusedLightGCNTrainer:
         self.ws, self.ws_bytes = graph.workspace(self.d)
         self.step_count = 0
         # libgcf kernels only: K fwd + K bwd SpMM, sampler, bpr (fused fwd+bwd | fwd, bwd) + reduce, adam
-        self.launches_per_step = 2 * n_layers + (4 if fused_bpr else 5)
+        self.launches_per_step = 2 * n_layers + (4 if fused_bpr else 5) - (1 if fused_adam else 0)
 
     def step(self, neg_i: Optional[torch.Tensor] = None, marks: Optional[list] = None) -> torch.Tensor:
         """One optimisation step.  `marks` (optional list) receives (start_event, end_event, n_spmm_launches)
@@ -220,14 +221,21 @@ class FusedLightGCNTrainer:
         gt = g.transpose()
         if marks is not None:
             e2.record()
-        _lib.check(lib.gcf_propagate_bwd(gt.struct_ref(), d, self.k, _lib.ptr(self.g_final), None, 1.0, _lib.ptr(self.ping),
-                                         _lib.ptr(self.pong), _lib.ptr(self.g_x0), _lib.ptr(self.ws), self.ws_bytes, st),
-                   "gcf_propagate_bwd")
+        if self.fused_adam:
+            _lib.check(lib.gcf_propagate_bwd_adam(gt.struct_ref(), d, self.k, _lib.ptr(self.g_final), None, 1.0, _lib.ptr(self.ping),
+                                                  _lib.ptr(self.pong), None, _lib.ptr(self.table), _lib.ptr(self.exp_avg),
+                                                  _lib.ptr(self.exp_avg_sq), self.lr, 0.9, 0.999, 1e-8, self.wd, 0, self.step_count,
+                                                  _lib.ptr(self.ws), self.ws_bytes, st), "gcf_propagate_bwd_adam")
+        else:
+            _lib.check(lib.gcf_propagate_bwd(gt.struct_ref(), d, self.k, _lib.ptr(self.g_final), None, 1.0, _lib.ptr(self.ping),
+                                             _lib.ptr(self.pong), _lib.ptr(self.g_x0), _lib.ptr(self.ws), self.ws_bytes, st),
+                       "gcf_propagate_bwd")
         if marks is not None:
             e3.record()
             marks.append((e0, e1, self.k))
             marks.append((e2, e3, self.k))
-        _lib.check(lib.gcf_adam_step(_lib.ptr(self.table), _lib.ptr(self.g_x0), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
-                                     self.table.numel(), self.lr, 0.9, 0.999, 1e-8, self.wd, 0, self.step_count, st),
-                   "gcf_adam_step")
+        if not self.fused_adam:
+            _lib.check(lib.gcf_adam_step(_lib.ptr(self.table), _lib.ptr(self.g_x0), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                                         self.table.numel(), self.lr, 0.9, 0.999, 1e-8, self.wd, 0, self.step_count, st),
+                       "gcf_adam_step")
         return self.loss

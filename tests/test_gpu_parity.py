@@ -553,3 +553,26 @@ def test_raw_score_mode_rejects_mean_reduction(cuda):
     rc = lib.gcf_bpr_fwd(_lib.ptr(t), 8, _lib.ptr(t), 8, 8, _lib.ptr(i), _lib.ptr(i), _lib.ptr(i), 2, 1, _lib.BPR_RAW_SCORE, 0.0,
                          _lib.REDUCE_MEAN, 0.0, 0.0, 0.0, _lib.ptr(o), _lib.ptr(o), _lib.ptr(ws), ws.numel(), _lib.current_stream())
     assert rc == -1 and b"raw scores need reduction = sum" in lib.gcf_last_error()
+
+
+def test_fused_adam_epilogue_equals_separate_adam(cuda):
+    """gcf_propagate_bwd_adam (Adam applied inside the last backward SpMM) against gcf_propagate_bwd + gcf_adam_step."""
+    inter, pu, pi = _tiny_problem(seed=5, U=400, I=600, E=9000)
+    U, I, d, K = inter.n_users, inter.n_items, 64, 3
+    g = CSRGraph.from_pairs(pu.to(cuda), pi.to(cuda), U, I, norm="sym", chunk=64)      # chunk=64: long rows take the chunked path
+    assert g.plan.n_long > 0
+    t0 = torch.randn(U + I, d, device=cuda) * 0.05
+    a = FusedLightGCNTrainer(g, U, I, t0.clone(), pu, pi, n_layers=K, lr=0.01, reg_weight=1e-4, weight_decay=1e-3, fused_adam=True)
+    b = FusedLightGCNTrainer(g, U, I, t0.clone(), pu, pi, n_layers=K, lr=0.01, reg_weight=1e-4, weight_decay=1e-3, fused_adam=False)
+    rng = np.random.default_rng(9)
+    for s in range(3):
+        neg = torch.from_numpy(rng.integers(0, I, pu.numel())).to(cuda)
+        la, lb = a.step(neg_i=neg), b.step(neg_i=neg)
+        np.testing.assert_allclose(la.item(), lb.item(), rtol=1e-4)
+        if s == 0:
+            # same gradient values feed the same update function; only the atomics of the BPR scatter reorder fp32 sums
+            for x, y in ((a.exp_avg, b.exp_avg), (a.exp_avg_sq, b.exp_avg_sq)):
+                assert ((x - y).norm() / y.norm()).item() < 1e-5
+    err = (a.table - b.table).abs()
+    frac = (err <= 2e-5 + 1e-3 * b.table.abs()).float().mean().item()
+    assert frac > 0.999 and err.max().item() <= 0.07, f"fraction within tolerance {frac}, max deviation {err.max().item()}"
