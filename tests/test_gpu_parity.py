@@ -576,3 +576,33 @@ def test_fused_adam_epilogue_equals_separate_adam(cuda):
     err = (a.table - b.table).abs()
     frac = (err <= 2e-5 + 1e-3 * b.table.abs()).float().mean().item()
     assert frac > 0.999 and err.max().item() <= 0.07, f"fraction within tolerance {frac}, max deviation {err.max().item()}"
+
+
+# ====================================================================== error behaviour of the C-ABI
+def test_c_abi_reports_errors_instead_of_crashing(cuda):
+    lib = _lib.load(); st = _lib.current_stream()
+    inter = synth.power_law_bipartite(50, 60, 400, seed=1)
+    g = CSRGraph.from_pairs(dev_t(inter.users, cuda), dev_t(inter.items, cuda), 50, 60, norm="sym", chunk=8)
+    x = torch.randn(110, 6, device=cuda); y = torch.empty_like(x)
+    rc = lib.gcf_spmm_csr_f32(g.struct_ref(), 6, _lib.ptr(x), 6, _lib.ptr(y), 6, None, 0, 0, 1.0, 1.0, 0, None, None, None, 0, 0, st)
+    assert rc == -4 and b"d=6 unsupported" in lib.gcf_last_error()                       # GCF_EUNSUPPORTED
+    x = torch.randn(110, 64, device=cuda); y = torch.empty_like(x)
+    assert g.plan.n_long > 0
+    rc = lib.gcf_spmm_csr_f32(g.struct_ref(), 64, _lib.ptr(x), 64, _lib.ptr(y), 64, None, 0, 0, 1.0, 1.0, 0, None, None, None, 0, 0, st)
+    assert rc == -3 and b"workspace too small" in lib.gcf_last_error()                   # GCF_EWORKSPACE
+    rc = lib.gcf_spmm_csr_f32(g.struct_ref(), 64, _lib.ptr(x), 64, None, 0, None, 0, 0, 1.0, 1.0, 0, None, None, None, 0, 0, st)
+    assert rc == -1 and b"no output requested" in lib.gcf_last_error()                   # GCF_EINVAL
+    with pytest.raises(_lib.GcfError, match="temperature must be positive"):
+        F_.infonce_stats_raw(torch.randn(4, 16, device=cuda), torch.randn(4, 16, device=cuda), 0.0)
+    with pytest.raises(_lib.GcfError, match="unsupported"):
+        F_.infonce_stats_raw(torch.randn(4, 512, device=cuda), torch.randn(4, 512, device=cuda), 0.2)
+    with pytest.raises(ValueError):
+        F_.spmm(g, torch.randn(7, 64, device=cuda))                                       # row count mismatch
+    with pytest.raises(RuntimeError, match="CUDA"):
+        F_.gather_rows(torch.randn(4, 8), torch.tensor([0]))                             # CPU tensors are rejected
+    # out-of-range COO entries are dropped by the builder rather than corrupting memory
+    r = torch.tensor([0, 1, 200, -1], device=cuda); c = torch.tensor([1, 0, 0, 0], device=cuda)
+    bad = CSRGraph.from_coo(r, c, None, 3, 3, norm="none")
+    assert bad.nnz == 2
+    torch.cuda.synchronize()   # nothing above left a sticky CUDA error behind
+    assert torch.isfinite(F_.spmm(bad, torch.ones(3, 16, device=cuda))).all()
