@@ -32,3 +32,26 @@ def measures(lists, test_items_per_user, top_ns):
         out[n] = (round(sum(hits) / total, 5), round(sum(hits) / (len(lists) * n), 5),
                   round(float(np.mean([h / len(t) for h, t in zip(hits, test_items_per_user)])), 5), round(sum(dcgs) / len(lists), 5))
     return out
+
+
+def lightgcn_evaluate(scores, train_pos, test_users, test_items, k_list):
+    """lightgcn.py:48-74 restated: scores [U, I]; train_pos {user: set}; test pairs as arrays.  Returns {k: {HR, P, R, NDCG}}."""
+    out = {k: {"HR": 0.0, "P": 0.0, "R": 0.0, "NDCG": 0.0} for k in k_list}
+    users = np.unique(test_users)
+    for u in users:
+        s = np.array(scores[u], dtype=np.float64)
+        known = list(train_pos.get(int(u), ()))
+        if known:
+            s[known] = -np.inf
+        top = np.lexsort((np.arange(s.shape[0]), -s))[:max(k_list)]
+        tset = set(int(x) for x in test_items[test_users == u])
+        for k in k_list:
+            hits = sum(1 for it in top[:k] if int(it) in tset)
+            out[k]["HR"] += hits > 0
+            out[k]["P"] += hits / k
+            out[k]["R"] += hits / len(tset) if tset else 0
+            out[k]["NDCG"] += sum(1 / np.log2(i + 2) for i in range(k) if int(top[i]) in tset)
+    for k in k_list:
+        for m in out[k]:
+            out[k][m] /= len(users)
+    return out

@@ -53,16 +53,15 @@ def recommend_topn(user_emb: torch.Tensor, item_emb: torch.Tensor, query_users: 
     return out_idx, out_val
 
 
-def ranking_measures(topn_idx: torch.Tensor, query_users: torch.Tensor, test_pos: Tuple[torch.Tensor, torch.Tensor],
-                     top_ns: Sequence[int]) -> Dict[int, Dict[str, float]]:
-    """{N: {'Hit Ratio', 'Precision', 'Recall', 'NDCG'}} with the definitions (and 5-decimal rounding) of Metric
-    (ncl.py:133-162).  Every query user must have at least one test item (the reference iterates over test_set)."""
+def hits_and_dcg(topn_idx: torch.Tensor, query_users: torch.Tensor, test_pos: Tuple[torch.Tensor, torch.Tensor],
+                 cuts: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(hits int32 [Q, len(cuts)], dcg fp32 [Q, len(cuts)]) at ascending cut-offs (gcf_ranking_hits)."""
     lib = _lib.load()
     dev = topn_idx.device
     q, n_top = topn_idx.shape
-    cuts = sorted(int(n) for n in top_ns)
-    if cuts[-1] > n_top:
-        raise ValueError("a cut-off exceeds the length of the recommendation lists")
+    cuts = [int(c) for c in cuts]
+    if cuts != sorted(cuts) or cuts[-1] > n_top:
+        raise ValueError("cut-offs must be ascending and not exceed the length of the recommendation lists")
     cut_t = torch.tensor(cuts, dtype=torch.int32, device=dev)
     hits = torch.empty(q, len(cuts), dtype=torch.int32, device=dev)
     dcg = torch.empty(q, len(cuts), dtype=torch.float32, device=dev)
@@ -71,6 +70,19 @@ def ranking_measures(topn_idx: torch.Tensor, query_users: torch.Tensor, test_pos
     _lib.check(lib.gcf_ranking_hits(_lib.ptr(topn_idx.contiguous()), q, n_top, _lib.ptr(users), _lib.ptr(rp), _lib.ptr(ci),
                                     _lib.ptr(cut_t), len(cuts), _lib.ptr(hits), _lib.ptr(dcg), _lib.current_stream()),
                "gcf_ranking_hits")
+    return hits, dcg
+
+
+def ranking_measures(topn_idx: torch.Tensor, query_users: torch.Tensor, test_pos: Tuple[torch.Tensor, torch.Tensor],
+                     top_ns: Sequence[int]) -> Dict[int, Dict[str, float]]:
+    """{N: {'Hit Ratio', 'Precision', 'Recall', 'NDCG'}} with the definitions (and 5-decimal rounding) of Metric
+    (ncl.py:133-162).  Every query user must have at least one test item (the reference iterates over test_set)."""
+    dev = topn_idx.device
+    q, n_top = topn_idx.shape
+    cuts = sorted(int(n) for n in top_ns)
+    hits, dcg = hits_and_dcg(topn_idx, query_users, test_pos, cuts)
+    rp, ci = test_pos
+    users = query_users.to(dev, torch.int64).contiguous()
     n_test = (rp[users + 1] - rp[users]).to(torch.float64)       # len(origin[u])
     idcg_table = torch.tensor([0.0] + list(np.cumsum([1.0 / math.log2(i + 2) for i in range(cuts[-1])])), dtype=torch.float64, device=dev)
     out: Dict[int, Dict[str, float]] = {}

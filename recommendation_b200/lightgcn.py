@@ -18,6 +18,7 @@ from __future__ import annotations
 
 from typing import Dict, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -239,3 +240,71 @@ class FusedLightGCNTrainer:
                                          self.table.numel(), self.lr, 0.9, 0.999, 1e-8, self.wd, 0, self.step_count, st),
                        "gcf_adam_step")
         return self.loss
+
+
+# =========================================================================================
+# The rest of lightgcn.py's script surface: load_data, evaluate, train_model (lightgcn.py:29-124)
+# =========================================================================================
+def load_data(train_path: str, test_path: str, device=None):
+    """`user item rating` text files -> (edge_index [2, 2E] int64 on the GPU, train_df, test_df, num_users, num_items),
+    the return signature of lightgcn.py:29-40."""
+    import pandas as pd
+
+    train_df = pd.read_csv(train_path, sep=" ", names=["user", "item", "rating"])
+    test_df = pd.read_csv(test_path, sep=" ", names=["user", "item", "rating"])
+    num_users = int(max(train_df["user"].max(), test_df["user"].max()) + 1)
+    num_items = int(max(train_df["item"].max(), test_df["item"].max()) + 1)
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    users = torch.from_numpy(train_df["user"].values.astype("int64")).to(dev)
+    items = torch.from_numpy(train_df["item"].values.astype("int64")).to(dev)
+    return build_edge_index(users, items, num_users), train_df, test_df, num_users, num_items
+
+
+def evaluate(user_emb: torch.Tensor, item_emb: torch.Tensor, test_df, train_pos=None, k_list=(10,), *, train_df=None):
+    """lightgcn.py:48-74 for all test users at once: HR = share of users with at least one hit, P = hits / k, R = hits /
+    |test items|, NDCG = the un-normalised DCG the reference accumulates, each averaged over the test users.
+    `train_pos` ({user: set(items)}, as get_user_positive_items returns) or `train_df` names the items to exclude."""
+    from . import evaluation
+
+    dev = user_emb.device
+    n_users, n_items = user_emb.shape[0], item_emb.shape[0]
+    if train_df is not None:
+        tr_u, tr_i = train_df["user"].values, train_df["item"].values
+    elif train_pos:
+        tr_u = [u for u, its in train_pos.items() for _ in its]
+        tr_i = [i for its in train_pos.values() for i in its]
+    else:
+        tr_u, tr_i = [], []
+    as_t = lambda a: torch.tensor(np.asarray(a, dtype=np.int64)).to(dev)   # (copy: pandas hands out read-only views)
+    train_csr = evaluation.positives_csr(as_t(tr_u), as_t(tr_i), n_users, n_items) if len(tr_u) else None
+    te_u, te_i = as_t(test_df["user"].values), as_t(test_df["item"].values)
+    test_csr = evaluation.positives_csr(te_u, te_i, n_users, n_items)
+    query = torch.unique(te_u)
+    ks = sorted(int(k) for k in k_list)
+    idx, _ = evaluation.recommend_topn(user_emb, item_emb, query, ks[-1], train_pos=train_csr)
+    hits, dcg = evaluation.hits_and_dcg(idx, query, test_csr, ks)
+    n_test = (test_csr[0][query + 1] - test_csr[0][query]).to(torch.float64)
+    out = {}
+    for c, k in enumerate(ks):
+        h = hits[:, c].to(torch.float64)
+        out[k] = {"HR": float((h > 0).double().mean()), "P": float((h / k).mean()), "R": float((h / n_test).mean()),
+                  "NDCG": float(dcg[:, c].double().mean())}
+    return out
+
+
+def train_model(config: dict, train_path: str = "./data/train.txt", test_path: str = "./data/test.txt", epochs: int = 30,
+                seed: int = 0):
+    """lightgcn.py:77-124: 30 full-batch epochs, then evaluation at k = 10."""
+    edge_index, train_df, test_df, num_users, num_items = load_data(train_path, test_path)
+    dev = edge_index.device
+    model = LightGCN(num_users, num_items, embedding_dim=config["embedding_dim"], num_layers=config["num_layers"]).to(dev)
+    optimizer = getattr(torch.optim, config["optimizer"])(model.parameters(), lr=config["lr"], weight_decay=config["weight_decay"])
+    pos_u = torch.from_numpy(train_df["user"].values.astype("int64")).to(dev)
+    pos_i = torch.from_numpy(train_df["item"].values.astype("int64")).to(dev)
+    model.train()
+    for epoch in range(epochs):
+        train_step(model, optimizer, edge_index, pos_u, pos_i, num_items, config, seed=seed, step=epoch)
+    model.eval()
+    with torch.no_grad():
+        user_emb, item_emb = model(edge_index)
+        return evaluate(user_emb, item_emb, test_df, train_df=train_df, k_list=[10])

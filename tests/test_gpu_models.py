@@ -377,3 +377,38 @@ def test_edge_dropout_operator(cuda):
     assert not torch.equal(o1, o2)
     e1 = enc.get_embedding()[0]; e2 = enc.get_embedding()[0]
     assert torch.equal(e1, e2)                                      # evaluation uses the full operator
+
+
+def test_lightgcn_script_surface(cuda, tmp_path):
+    """load_data / evaluate / train_model of lightgcn.py:29-124 on a small text dataset."""
+    import pandas as pd
+    from oracle import eval_ref
+    from recommendation_b200 import lightgcn as lg
+
+    rng = np.random.default_rng(17)
+    U, I = 60, 90
+    pairs = np.unique(np.stack([rng.integers(0, U, 1500), rng.integers(0, I, 1500)], 1), axis=0)
+    rng.shuffle(pairs)
+    train, test = pairs[:1000], pairs[1000:1200]
+    for name, arr in (("train.txt", train), ("test.txt", test)):
+        with open(tmp_path / name, "w") as f:
+            f.writelines(f"{u} {i} 1\n" for u, i in arr)
+    ei, train_df, test_df, nu, ni = lg.load_data(str(tmp_path / "train.txt"), str(tmp_path / "test.txt"))
+    assert ei.is_cuda and ei.shape == (2, 2 * len(train)) and nu == pairs[:1200, 0].max() + 1 and ni == pairs[:1200, 1].max() + 1
+    want_ei = np.stack([np.concatenate([train[:, 0], train[:, 1] + nu]), np.concatenate([train[:, 1] + nu, train[:, 0]])])
+    assert np.array_equal(ei.cpu().numpy(), want_ei)                                 # lightgcn.py:36-39, bit-exact
+    ue = torch.randn(nu, 32, device=cuda); ie = torch.randn(ni, 32, device=cuda)
+    train_pos = {}
+    for u, i in train:
+        train_pos.setdefault(int(u), set()).add(int(i))
+    got = lg.evaluate(ue, ie, test_df, train_pos, k_list=[5, 10])
+    want = eval_ref.lightgcn_evaluate((ue @ ie.T).cpu().numpy(), train_pos, test[:, 0], test[:, 1], [5, 10])
+    for k in (5, 10):
+        for m in ("HR", "P", "R", "NDCG"):
+            np.testing.assert_allclose(got[k][m], want[k][m], rtol=1e-5, atol=1e-7)
+    got2 = lg.evaluate(ue, ie, test_df, train_df=train_df, k_list=[10])
+    assert got2[10] == got[10]
+    cfg = {"embedding_dim": 32, "num_layers": 2, "optimizer": "Adam", "lr": 0.01, "weight_decay": 0.0, "n_neg": 1, "reg_weight": 1e-4,
+           "loss_type": "bpr"}
+    metrics = lg.train_model(cfg, str(tmp_path / "train.txt"), str(tmp_path / "test.txt"), epochs=5)
+    assert set(metrics[10]) == {"HR", "P", "R", "NDCG"} and 0.0 <= metrics[10]["HR"] <= 1.0
