@@ -336,6 +336,7 @@ def run_ours(args):
     spmm_avg_us = sum(spmm_us) / max(len(spmm_us), 1)
     alg_bytes = spmm_algorithmic_bytes(spmm_rows, n, nnz, spmm_d)  # per launch on ONE rank
     achieved = alg_bytes / (spmm_avg_us * 1e-6) / 1e9 if spmm_avg_us > 0 else 0.0
+    traffic = ncu_traffic(args.workload) if world == 1 else None  # DRAM bytes actually moved per launch (ncu capture)
 
     # ---- e2e through the reference-facing API with host buffers (rank-local at N>1 is not defined: N=1 only) ----
     e2e = None
@@ -405,7 +406,9 @@ def run_ours(args):
             "e2e": e2e,
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "hbm", "kernel": "spmm_csr_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(args.workload) if world == 1 else None,
+                         "frac": achieved / peak, "traffic": traffic,
+                         "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None,
+                         "dram_rate_frac_of_peak": (traffic / (spmm_avg_us * 1e-6) / 1e9 / peak) if traffic and spmm_avg_us > 0 else None,
                          "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": spmm_avg_us,
