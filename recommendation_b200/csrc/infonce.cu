@@ -8,7 +8,8 @@
 //   DirectAU           directau.py:245-251                   pdist -> exp -> mean -> log
 // -- none of which ever materialises here: a CTA owns a 128-row tile of one operand, streams 256-row tiles of
 // the other through a TMA ring, one thread issues tcgen05.mma (bf16 x bf16 -> fp32 in TMEM, double-buffered),
-// and four epilogue warps read the accumulator back with tcgen05.ld and fold it into an online log-sum-exp.
+// and eight epilogue warps (two per TMEM lane quadrant, one column half each) read the accumulator back with tcgen05.ld
+// and fold it into an online log-sum-exp.
 //
 // Numerics: operands are L2-normalised (when cos != 0) in fp32, scaled by log2(e)/tau on the "query" side and
 // rounded to bf16 once; accumulation, running max / sum and every reduction are fp32.  Logit error is bounded
@@ -369,7 +370,7 @@ static int run_lse(const __nv_bfloat16* ab, long long n_a, const __nv_bfloat16* 
 // streaming gradient kernel:  for the CTA's 128 rows a of A and its slice of B's 128-row tiles
 //   P_ab = w_r[a] 2^(S2_ab - l_r[a]) + w_c[b] 2^(S2_ab - l_c[b]),   S2 = A B^T (log2 units, recomputed on the tensor cores)
 //   G_a  = sum_b P_ab B_b                                          (second MMA, accumulator stays in TMEM)
-// warp 0: TMA, warp 1: MMA issuer, warps 2-5: S (TMEM) -> P (bf16, swizzled smem) conversion and the final G read-out.
+// warp 0: TMA, warp 1: MMA issuer, warps 2-9: S (TMEM) -> P (bf16, swizzled smem) conversion and the final G read-out.
 // ------------------------------------------------------------------------------------------------
 constexpr int kGradTileN = 128;   // B rows per tile = K extent of the second MMA
 constexpr int kGradThreads = 320;  // warp 0: TMA, warp 1: MMA, warps 2-9: conversion (two per TMEM lane quadrant)
