@@ -111,15 +111,27 @@ struct LseSmem {
 // BOUNDED: the operands are L2-normalised, so |S2| <= log2e / tau is known up front; when that bound is small enough for fp32
 // (host checks <= 64) the running max and its rescaling are dropped: l = sum_b 2^S2, m = 0.  This is the reference's own
 // non-stabilised exp / sum form (ncl.py:362-365) and halves the epilogue's instruction count.
-template <int KC, bool BOUNDED, int POLY>  // KC = number of 64-wide K chunks (d_pad = 64 * KC); POLY: see ex2_mixed
+// PROBS (wide embeddings, d > 256): instead of reducing the logits, the epilogue writes
+//   P = w_r 2^(S2 - l_r) + w_c 2^(S2 - l_c)  as bf16 into a row-major [a_pad, ldp] buffer; the two gradient GEMMs P B and
+//   P^T A then run as plain library GEMMs (the accumulator of the fused backward kernel does not fit the TMEM at d > 256).
+struct ProbsArgs {
+  const float* w_r; const float* lse_r; const float* w_c; const float* lse_c;
+  __nv_bfloat16* P; long long ldp; long long n_a;
+};
+
+// KC > 0: the stationary operand (KC chunks of [128 x 64]) stays in shared memory.  KC == 0: d_pad > 256, its chunks are
+// streamed through the ring together with the other operand's (kc_rt chunks per tile, read from L2 once per tile).
+template <int KC, bool BOUNDED, int POLY, bool PROBS>
 __global__ void __launch_bounds__(kLseThreads, 1)
 lse_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, long long n_b,
                   int n_tiles, int tiles_per_split, float* __restrict__ part_m, float* __restrict__ part_l,
-                  long long m_pad, int skip_diag) {
+                  long long m_pad, int skip_diag, int kc_rt, ProbsArgs pa) {
+  constexpr bool kStreamA = KC == 0;
+  const int n_kc = kStreamA ? kc_rt : KC;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;                                               // KC chunks of [128 x 64] bf16
-  uint8_t* smem_b = smem + KC * LseSmem::kABytesPerChunk;               // kLseStages chunks of [256 x 64] bf16
+  uint8_t* smem_a = smem;                                               // KC resident chunks | kLseStages streamed chunks of [128 x 64]
+  uint8_t* smem_b = smem + (kStreamA ? kLseStages : KC) * LseSmem::kABytesPerChunk;   // kLseStages chunks of [256 x 64] bf16
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kLseStages * LseSmem::kBBytesPerStage);
   uint64_t* full_bar = bars;                    // [kLseStages]
   uint64_t* empty_bar = bars + kLseStages;      // [kLseStages]
@@ -156,13 +168,16 @@ lse_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0 && my_tiles > 0) {
-      mbar_expect_tx(a_bar, KC * LseSmem::kABytesPerChunk);
-      for (int kc = 0; kc < KC; ++kc) tma_load_2d(&tm_a, a_bar, smem_a + kc * LseSmem::kABytesPerChunk, kc * kChunkK, m_tile * kTileM);
+      if (!kStreamA) {
+        mbar_expect_tx(a_bar, KC * LseSmem::kABytesPerChunk);
+        for (int kc = 0; kc < KC; ++kc) tma_load_2d(&tm_a, a_bar, smem_a + kc * LseSmem::kABytesPerChunk, kc * kChunkK, m_tile * kTileM);
+      }
       int stage = 0; uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
-        for (int kc = 0; kc < KC; ++kc) {
+        for (int kc = 0; kc < n_kc; ++kc) {
           mbar_wait(empty_bar + stage, phase ^ 1);
-          mbar_expect_tx(full_bar + stage, LseSmem::kBBytesPerStage);
+          mbar_expect_tx(full_bar + stage, LseSmem::kBBytesPerStage + (kStreamA ? LseSmem::kABytesPerChunk : 0));
+          if (kStreamA) tma_load_2d(&tm_a, full_bar + stage, smem_a + stage * LseSmem::kABytesPerChunk, kc * kChunkK, m_tile * kTileM);
           tma_load_2d(&tm_b, full_bar + stage, smem_b + stage * LseSmem::kBBytesPerStage, kc * kChunkK, t * kTileN);
           if (++stage == kLseStages) { stage = 0; phase ^= 1; }
         }
@@ -172,17 +187,19 @@ lse_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     // ===== MMA issuer (one thread) =====
     if (lane == 0 && my_tiles > 0) {
       constexpr uint32_t idesc = idesc_bf16_f32(kTileM, kTileN, 0, 0);
-      mbar_wait(a_bar, 0);
-      fence_after_sync();
+      if (!kStreamA) {
+        mbar_wait(a_bar, 0);
+        fence_after_sync();
+      }
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const int acc = it & 1;
         mbar_wait(acc_empty + acc, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
         fence_after_sync();
-        for (int kc = 0; kc < KC; ++kc) {
+        for (int kc = 0; kc < n_kc; ++kc) {
           mbar_wait(full_bar + stage, phase);
           fence_after_sync();
-          const uint32_t a_addr = smem_u32(smem_a + kc * LseSmem::kABytesPerChunk);
+          const uint32_t a_addr = smem_u32(smem_a + (kStreamA ? stage : kc) * LseSmem::kABytesPerChunk);
           const uint32_t b_addr = smem_u32(smem_b + stage * LseSmem::kBBytesPerStage);
 #pragma unroll
           for (int kk = 0; kk < kChunkK / 16; ++kk) {  // UMMA_K = 16 bf16 = 32 bytes inside the swizzled row
