@@ -271,6 +271,9 @@ int gcf_scale_by_device_scalar(float* x, int64_t n, const float* g, gcf_stream_t
  *   batch_softmax    ssl4rec.py:25-30                 : mean_i -log(exp(pos-row_lse)+1e-6)
  *   info_nce_loss    gcl.py:28-35                     : (mean(row_lse-pos)+mean(col_lse-pos))/2
  */
+/* d <= 1024 (the reference's tuner grids reach embedding.size = 1024).  d <= 256 runs the fully fused TMEM kernels; wider
+ * embeddings stream both operands through the TMA ring in the forward, and the backward materialises P block-wise in bf16
+ * (<= 1 GiB of workspace at a time) and runs the two gradient products as cuBLAS bf16 GEMMs with fp32 accumulation. */
 size_t gcf_infonce_workspace_bytes(int64_t M, int64_t N, int32_t d);
 int gcf_infonce_fwd(const float* Q, int64_t ldq, int64_t M, const float* Kmat, int64_t ldk, int64_t N, int32_t d,
                     int32_t cos, float tau, const int64_t* pos_idx,

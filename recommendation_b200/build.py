@@ -76,7 +76,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     newest = max(o.stat().st_mtime for o in objs)
     if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < newest:
         cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs),
-               "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+               "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-lcublas"]
         if verbose:
             print(" ".join(cmd), flush=True)
         res = subprocess.run(cmd, capture_output=True, text=True)

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "tc05.cuh"
 #include <cuda_bf16.h>
+#include <cublas_v2.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -31,6 +32,7 @@ constexpr int kTileN = 256;      // rows of the streamed operand per MMA tile (=
 constexpr int kChunkK = 64;      // bf16 elements per 128-byte swizzled row
 constexpr int kLseStages = 4;    // TMA ring depth (one stage = one [kTileN x 64] chunk = 32 KB)
 constexpr int kLseThreads = 320; // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue (two per TMEM lane quadrant)
+constexpr int kMaxChunks = 16;   // d <= 1024 (the tuner grids of ncl.py / ssl4rec.py / gcl.py go up to 1024)
 constexpr int kPolyOf8 = 2;       // exponentials evaluated on the FMA pipe per 8 logits (measured best of 0 / 2 / 3 / 4: r01 profiles)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -219,12 +221,55 @@ lse_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int half = (warp - 2) >> 2;                // columns [half * 128, half * 128 + 128) of every 256-column tile
     const int row = quad * 32 + lane;
     float m_run = BOUNDED ? 0.f : -INFINITY, l_run = 0.f;
+    const long long row_g = (long long)m_tile * kTileM + row;
+    float wr = 0.f, lr = 0.f;
+    if (PROBS && pa.w_r != nullptr && row_g < pa.n_a) { wr = pa.w_r[row_g]; lr = pa.lse_r[row_g] * kLog2e; }
     for (int it = 0; it < my_tiles; ++it) {
       const int acc = it & 1;
       const int t = t_begin + it;
       mbar_wait(acc_full + acc, (it >> 1) & 1);
       fence_after_sync();
       const long long col0 = (long long)t * kTileN + half * (kTileN / 2);
+      if (PROBS) {
+        const long long diag = row_g - col0;
+        const bool has_diag = skip_diag && diag >= 0 && diag < kTileN / 2;
+#pragma unroll 1
+        for (int c = 0; c < kTileN / 64; ++c) {
+          float v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileN + half * (kTileN / 2) + c * 32), v);
+          const long long cc = col0 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float sv = v[j];
+            float pv = 0.f;
+            if (pa.w_r != nullptr) pv = wr * ex2_mixed<POLY>(sv - lr, j);
+            if (pa.w_c != nullptr && cc + j < n_b) pv = fmaf(__ldg(pa.w_c + cc + j), ex2_mixed<POLY>(sv - __ldg(pa.lse_c + cc + j) * kLog2e, j), pv);
+            v[j] = pv;
+          }
+          if (has_diag && (int)(diag >> 5) == c) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j == (int)(diag & 31)) v[j] = 0.f;
+          }
+          // rows beyond n_a and columns beyond n_b meet zero-padded operand rows in the GEMMs: their values are irrelevant
+          uint4* dst = reinterpret_cast<uint4*>(pa.P + row_g * pa.ldp + cc);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 pk;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * u + 0], v[8 * u + 1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * u + 2], v[8 * u + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * u + 4], v[8 * u + 5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * u + 6], v[8 * u + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            dst[u] = pk;
+          }
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + acc);
+        continue;
+      }
       const bool ragged = col0 + kTileN / 2 > n_b;   // contains zero-padded rows of B: mask them out
       const long long diag = (long long)m_tile * kTileM + row - col0;  // column of this row's diagonal element
       const bool has_diag = skip_diag && diag >= 0 && diag < kTileN / 2;   // DirectAU: pairs i != j only
@@ -273,11 +318,13 @@ lse_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + acc);
     }
-    if (BOUNDED && l_run == 0.f) m_run = -INFINITY;  // nothing unmasked in this slice: neutral element for the merge
-    // the two column halves are merged like two more splits
-    const long long out = ((long long)split * 2 + half) * m_pad + (long long)m_tile * kTileM + row;
-    part_m[out] = m_run;
-    part_l[out] = l_run;
+    if (!PROBS) {
+      if (BOUNDED && l_run == 0.f) m_run = -INFINITY;  // nothing unmasked in this slice: neutral element for the merge
+      // the two column halves are merged like two more splits
+      const long long out = ((long long)split * 2 + half) * m_pad + (long long)m_tile * kTileM + row;
+      part_m[out] = m_run;
+      part_l[out] = l_run;
+    }
   }
   fence_before_sync();
   __syncthreads();
@@ -341,8 +388,9 @@ static LsePlan plan_lse(long long n_a, long long n_b) {
   return p;
 }
 
-static size_t lse_smem_bytes(int kc) {
-  return 1024 + (size_t)kc * LseSmem::kABytesPerChunk + (size_t)kLseStages * LseSmem::kBBytesPerStage + 256;
+static size_t lse_smem_bytes(int kc) {  // kc > 4: the stationary operand's chunks ride in the ring (one per stage)
+  const int a_chunks = kc > 4 ? kLseStages : kc;
+  return 1024 + (size_t)a_chunks * LseSmem::kABytesPerChunk + (size_t)kLseStages * LseSmem::kBBytesPerStage + 256;
 }
 
 // (m, l) partials -> lse[n_a]; ab/bb are the prepared bf16 operands ([a_pad, d_pad], [b_pad, d_pad])
@@ -357,11 +405,12 @@ static int run_lse(const __nv_bfloat16* ab, long long n_a, const __nv_bfloat16* 
   const int kc = d_pad / kChunkK;
   const size_t smem = lse_smem_bytes(kc);
   dim3 grid(p.m_tiles, p.n_splits);
-#define GCF_LSE_LAUNCH2(KC, B)                                                                                                \
-  do {                                                                                                                        \
-    GCF_CUDA(cudaFuncSetAttribute(lse_stream_kernel<KC, B, kPolyOf8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    lse_stream_kernel<KC, B, kPolyOf8><<<grid, kLseThreads, smem, st>>>(tm_a, tm_b, n_b, p.n_tiles, p.tiles_per_split, part_m,   \
-                                                                        part_l, p.a_pad, skip_diag);                           \
+  const ProbsArgs no_probs{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
+#define GCF_LSE_LAUNCH2(KC, B)                                                                                                       \
+  do {                                                                                                                               \
+    GCF_CUDA(cudaFuncSetAttribute(lse_stream_kernel<KC, B, kPolyOf8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    lse_stream_kernel<KC, B, kPolyOf8, false><<<grid, kLseThreads, smem, st>>>(tm_a, tm_b, n_b, p.n_tiles, p.tiles_per_split, part_m,   \
+                                                                               part_l, p.a_pad, skip_diag, kc, no_probs);            \
   } while (0)
 #define GCF_LSE_LAUNCH(KC)                                      \
   do {                                                          \
@@ -373,7 +422,9 @@ static int run_lse(const __nv_bfloat16* ab, long long n_a, const __nv_bfloat16* 
     case 2: GCF_LSE_LAUNCH(2); break;
     case 3: GCF_LSE_LAUNCH(3); break;
     case 4: GCF_LSE_LAUNCH(4); break;
-    default: set_error("infonce: d_pad=%d unsupported (d <= 256)", d_pad); return GCF_EUNSUPPORTED;
+    default:
+      if (kc > kMaxChunks) { set_error("infonce: d_pad=%d unsupported (d <= %d)", d_pad, kMaxChunks * kChunkK); return GCF_EUNSUPPORTED; }
+      GCF_LSE_LAUNCH(0);  // wide embeddings: both operands streamed
   }
 #undef GCF_LSE_LAUNCH
 #undef GCF_LSE_LAUNCH2
@@ -616,8 +667,9 @@ grad_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 
 // g_hat[i] = scale * sum_s part[s][i] (+ pos term) (+ extra[i]);  then the chain rule of x^ = x / max(|x|, eps).
 // One warp per row.
+template <int NQ>  // 32 * NQ >= d columns per row, NQ values per lane
 __global__ void __launch_bounds__(256)
-grad_finish_kernel(const float* __restrict__ part, int n_splits, long long a_pad, int d_pad, float scale,
+grad_finish_kernel_t(const float* __restrict__ part, int n_splits, long long a_pad, int d_pad, float scale,
                    const float* __restrict__ x, long long ldx, const float* __restrict__ x_inv, long long n, int d,
                    int cos, const float* __restrict__ w_pos, const int64_t* __restrict__ pos_idx, float pos_scale,
                    const float* __restrict__ other, long long ld_other, const float* __restrict__ other_inv,
@@ -625,13 +677,13 @@ grad_finish_kernel(const float* __restrict__ part, int n_splits, long long a_pad
   const int lane = threadIdx.x & 31;
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= n) return;
-  float acc[8];
+  float acc[NQ];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+  for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
   for (int s = 0; s < n_splits; ++s) {
     const float* p = part + ((long long)s * a_pad + i) * d_pad;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int c = lane + 32 * q;
       if (c < d) acc[q] += p[c];
     }
@@ -646,7 +698,7 @@ grad_finish_kernel(const float* __restrict__ part, int n_splits, long long a_pad
   const float inv = cos ? x_inv[i] : 1.f;
   float dot = 0.f;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
+  for (int q = 0; q < NQ; ++q) {
     const int c = lane + 32 * q;
     if (c < d) {
       float v = acc[q] * scale;
@@ -662,7 +714,7 @@ grad_finish_kernel(const float* __restrict__ part, int n_splits, long long a_pad
     if (inv >= 1e12f) dot = 0.f;  // |x| below the F.normalize eps: x^ = x / eps, plain scaling
   }
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
+  for (int q = 0; q < NQ; ++q) {
     const int c = lane + 32 * q;
     if (c < d) {
       float v = acc[q];
@@ -670,6 +722,19 @@ grad_finish_kernel(const float* __restrict__ part, int n_splits, long long a_pad
       g[i * ldg + c] = v;
     }
   }
+}
+
+static void grad_finish_kernel_launch(unsigned blocks, cudaStream_t st, const float* part, int n_splits, long long a_pad, int d_pad,
+                                      float scale, const float* x, long long ldx, const float* x_inv, long long n, int d, int cos,
+                                      const float* w_pos, const int64_t* pos_idx, float pos_scale, const float* other,
+                                      long long ld_other, const float* other_inv, long long n_other, const float* extra, float* g,
+                                      long long ldg) {
+#define GCF_FINISH(NQ) grad_finish_kernel_t<NQ><<<blocks, 256, 0, st>>>(part, n_splits, a_pad, d_pad, scale, x, ldx, x_inv, n, d, cos, \
+                                                                        w_pos, pos_idx, pos_scale, other, ld_other, other_inv, n_other, extra, g, ldg)
+  if (d <= 256) GCF_FINISH(8);
+  else if (d <= 512) GCF_FINISH(16);
+  else GCF_FINISH(32);
+#undef GCF_FINISH
 }
 
 // extra[pos_i] += w_pos[i] * pos_scale * q^_i   (gradient of the positive logits w.r.t. the key rows)
@@ -741,9 +806,85 @@ static int run_grad(const __nv_bfloat16* ab, long long n_a, const __nv_bfloat16*
   return GCF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// wide embeddings (256 < d <= 1024): the d_pad-column gradient accumulator of grad_stream_kernel does not fit the TMEM
+// next to the logits, so the backward materialises P block-wise (bf16, PROBS mode of the streaming kernel) and runs the two
+// gradient products P B and P^T A as plain library GEMMs (cuBLAS, bf16 x bf16 -> fp32).  One P serves both gradients.
+// ------------------------------------------------------------------------------------------------
+constexpr size_t kProbsBlockBytes = size_t(1) << 30;
+
+static cublasHandle_t cublas_handle() {  // one handle per host thread and device, created on first use
+  static thread_local cublasHandle_t handles[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (handles[dev] == nullptr && cublasCreate(&handles[dev]) != CUBLAS_STATUS_SUCCESS) handles[dev] = nullptr;
+  return handles[dev];
+}
+
+static long long probs_block_rows(long long a_rows, long long b_rows) {
+  long long blk = (long long)(kProbsBlockBytes / ((size_t)b_rows * 2)) / kTileM * kTileM;
+  return std::max<long long>(kTileM, std::min(a_rows, blk));
+}
+
+// Ga[n_a.., d_pad] = P B (nullable), Gb[b_rows, d_pad] = P^T A (nullable); ab / bb: prepared operands with a_rows / b_rows
+// (multiples of 256) zero-padded rows; P: scratch of probs_block_rows(a_rows, b_rows) x b_rows bf16.
+static int run_grad_wide(const __nv_bfloat16* ab, long long n_a, long long a_rows, const __nv_bfloat16* bb, long long n_b,
+                         long long b_rows, int d_pad, const float* w_r, const float* lse_r, const float* w_c,
+                         const float* lse_c, int skip_diag, float* Ga, float* Gb, __nv_bfloat16* P, cudaStream_t st) {
+  cublasHandle_t h = cublas_handle();
+  if (h == nullptr) { set_error("infonce backward: cublasCreate failed"); return GCF_ECUDA; }
+  if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) { set_error("infonce backward: cublasSetStream failed"); return GCF_ECUDA; }
+  const int kc = d_pad / kChunkK;
+  const size_t smem = lse_smem_bytes(kc);
+  const long long blk = probs_block_rows(a_rows, b_rows);
+  const int n_tiles = (int)(b_rows / kTileN);
+  const float one = 1.f, zero = 0.f;
+  CUtensorMap tm_b;
+  int rc = make_tmap(&tm_b, bb, b_rows, d_pad, kTileN);
+  if (rc != GCF_OK) return rc;
+  const long long a_used = round_up(std::max<long long>(n_a, 1), kTileM);
+  for (long long r0 = 0, bi = 0; r0 < a_used; r0 += blk, ++bi) {
+    const long long rows = std::min(blk, a_used - r0);
+    CUtensorMap tm_a;
+    rc = make_tmap(&tm_a, ab + r0 * d_pad, rows, d_pad, kTileM);
+    if (rc != GCF_OK) return rc;
+    const int m_tiles = (int)(rows / kTileM);
+    int splits = std::max(1, std::min(n_tiles, sm_count() / std::max(m_tiles, 1)));
+    const int tiles_per_split = (n_tiles + splits - 1) / splits;
+    splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+    dim3 grid(m_tiles, splits);
+    ProbsArgs pa{w_r != nullptr ? w_r + r0 : nullptr, lse_r != nullptr ? lse_r + r0 : nullptr, w_c, lse_c, P, b_rows,
+                 std::max<long long>(0, n_a - r0)};
+    // the diagonal of a row block starts r0 columns in: shift it through the column origin seen by the kernel
+    const int sd = skip_diag;
+#define GCF_PROBS_LAUNCH(KC)                                                                                                        \
+    do {                                                                                                                            \
+      GCF_CUDA(cudaFuncSetAttribute(lse_stream_kernel<KC, false, kPolyOf8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      lse_stream_kernel<KC, false, kPolyOf8, true><<<grid, kLseThreads, smem, st>>>(tm_a, tm_b, n_b, n_tiles, tiles_per_split, nullptr, \
+                                                                                   nullptr, rows, sd, kc, pa);                     \
+    } while (0)
+    GCF_REQUIRE(!(skip_diag && r0 != 0), "infonce backward: diagonal masking needs the operand in one row block");
+    GCF_PROBS_LAUNCH(0);  // only reached for d_pad > 256: both operands streamed
+#undef GCF_PROBS_LAUNCH
+    GCF_LAUNCH_CHECK("lse_stream_kernel (probs)");
+    if (Ga != nullptr) {  // row-major Ga[r0 : r0 + rows] = P [rows x b_rows] * B [b_rows x d_pad]
+      if (cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, d_pad, (int)rows, (int)b_rows, &one, bb, CUDA_R_16BF, d_pad, P, CUDA_R_16BF,
+                       (int)b_rows, &zero, Ga + r0 * d_pad, CUDA_R_32F, d_pad, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT) !=
+          CUBLAS_STATUS_SUCCESS) { set_error("infonce backward: cublasGemmEx (P B) failed"); return GCF_ECUDA; }
+    }
+    if (Gb != nullptr) {  // row-major Gb += P^T [b_rows x rows] * A[r0 : r0 + rows] [rows x d_pad]
+      if (cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, d_pad, (int)b_rows, (int)rows, &one, ab + r0 * d_pad, CUDA_R_16BF, d_pad, P,
+                       CUDA_R_16BF, (int)b_rows, bi == 0 ? &zero : &one, Gb, CUDA_R_32F, d_pad, CUBLAS_COMPUTE_32F,
+                       CUBLAS_GEMM_DEFAULT) != CUBLAS_STATUS_SUCCESS) { set_error("infonce backward: cublasGemmEx (P^T A) failed"); return GCF_ECUDA; }
+    }
+  }
+  return GCF_OK;
+}
+
 struct InfoWs {
-  __nv_bfloat16 *qb, *kb;
-  float *q_inv, *k_inv, *part_m, *part_l, *gpart, *extra;
+  __nv_bfloat16 *qb, *kb, *probs;
+  float *q_inv, *k_inv, *part_m, *part_l, *gpart, *gpart_b, *extra;
+  long long q_rows, k_rows;
   size_t bytes;
 };
 
@@ -754,7 +895,12 @@ static InfoWs carve_ws(void* ws, long long m, long long n, int d) {
   // operands are padded for every role (stationary: multiple of 128, streamed: multiple of 256 / 128)
   const long long q_rows = round_up(std::max<long long>(m, 1), kTileN), k_rows = round_up(std::max<long long>(n, 1), kTileN);
   const size_t part = 2 * std::max((size_t)pq.n_splits * pq.a_pad, (size_t)pk.n_splits * pk.a_pad);  // x2: column halves
-  const size_t gpart = std::max((size_t)gq.n_splits * gq.a_pad, (size_t)gk.n_splits * gk.a_pad) * d_pad;
+  const bool wide = d_pad > 4 * kChunkK;
+  // d_pad <= 256: per-split partial gradients of the TMEM kernel; wider: the two full fp32 products + one P block
+  const size_t gpart = wide ? (size_t)q_rows * d_pad
+                            : std::max((size_t)gq.n_splits * gq.a_pad, (size_t)gk.n_splits * gk.a_pad) * d_pad;
+  const size_t gpart_b = wide ? (size_t)k_rows * d_pad : 0;
+  const size_t probs = wide ? (size_t)probs_block_rows(q_rows, k_rows) * k_rows : 0;
   InfoWs w;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
@@ -762,11 +908,14 @@ static InfoWs carve_ws(void* ws, long long m, long long n, int d) {
   const size_t o_qi = take((size_t)q_rows * 4), o_ki = take((size_t)k_rows * 4);
   const size_t o_pm = take(part * 4), o_pl = take(part * 4);
   const size_t o_gp = take(gpart * 4), o_ex = take((size_t)std::max<long long>(std::max(m, n), 1) * d * 4);
+  const size_t o_gb = take(gpart_b * 4), o_pr = take(probs * 2);
   char* b = static_cast<char*>(ws);
   w.qb = reinterpret_cast<__nv_bfloat16*>(b + o_qb); w.kb = reinterpret_cast<__nv_bfloat16*>(b + o_kb);
   w.q_inv = reinterpret_cast<float*>(b + o_qi); w.k_inv = reinterpret_cast<float*>(b + o_ki);
   w.part_m = reinterpret_cast<float*>(b + o_pm); w.part_l = reinterpret_cast<float*>(b + o_pl);
   w.gpart = reinterpret_cast<float*>(b + o_gp); w.extra = reinterpret_cast<float*>(b + o_ex);
+  w.gpart_b = reinterpret_cast<float*>(b + o_gb); w.probs = reinterpret_cast<__nv_bfloat16*>(b + o_pr);
+  w.q_rows = q_rows; w.k_rows = k_rows;
   w.bytes = off;
   return w;
 }
@@ -848,14 +997,14 @@ directau_align_grad_kernel(const float* __restrict__ x, long long ldx, const flo
 using namespace gcf;
 
 extern "C" size_t gcf_infonce_workspace_bytes(int64_t M, int64_t N, int32_t d) {
-  if (M < 0 || N < 0 || d <= 0 || d > 256) return 0;
+  if (M < 0 || N < 0 || d <= 0 || d > kMaxChunks * kChunkK) return 0;
   return carve_ws(nullptr, M, N, d).bytes + 1024;
 }
 
 static int infonce_check(const char* who, const float* Q, int64_t ldq, int64_t M, const float* Kmat, int64_t ldk, int64_t N,
                          int32_t d, float tau, void* workspace, size_t workspace_bytes) {
   GCF_REQUIRE(M >= 0 && N >= 0, "%s: negative sizes", who);
-  if (d <= 0 || d > 256) { set_error("%s: d=%d unsupported (1..256)", who, d); return GCF_EUNSUPPORTED; }
+  if (d <= 0 || d > kMaxChunks * kChunkK) { set_error("%s: d=%d unsupported (1..%d)", who, d, kMaxChunks * kChunkK); return GCF_EUNSUPPORTED; }
   GCF_REQUIRE(tau > 0.f, "%s: temperature must be positive", who);
   if (M == 0) return GCF_OK;
   GCF_REQUIRE(N > 0, "%s: empty key set", who);
@@ -919,6 +1068,33 @@ extern "C" int gcf_infonce_bwd(const float* Q, int64_t ldq, int64_t M, const flo
   if (rc != GCF_OK) return rc;
   const bool dense = w_row != nullptr || w_col != nullptr;
   const unsigned fin_q = (unsigned)cdiv(M * 32, 256), fin_k = (unsigned)cdiv(N * 32, 256);
+  if (d_pad > 4 * kChunkK) {
+    // wide embeddings: one block-wise P, both gradient products as library GEMMs, then the same finishing kernel
+    if (dense) {
+      rc = run_grad_wide(w.qb, M, w.q_rows, w.kb, N, w.k_rows, d_pad, w_row, row_lse, w_col, col_lse, 0,
+                         gQ != nullptr ? w.gpart : nullptr, gK != nullptr ? w.gpart_b : nullptr, w.probs, st);
+      if (rc != GCF_OK) return rc;
+    }
+    const int ns = dense ? 1 : 0;
+    if (gQ != nullptr) {
+      grad_finish_kernel_launch(fin_q, st, w.gpart, ns, w.q_rows, d_pad, 1.f / tau, Q, ldq, w.q_inv, M, d, cos, w_pos, pos_idx,
+                                                1.f / tau, Kmat, ldk, w.k_inv, N, nullptr, gQ, ldgq);
+      GCF_LAUNCH_CHECK("grad_finish_kernel");
+    }
+    if (gK != nullptr) {
+      const float* extra = nullptr;
+      if (w_pos != nullptr) {
+        GCF_CUDA(cudaMemsetAsync(w.extra, 0, (size_t)N * d * sizeof(float), st));
+        pos_scatter_kernel<<<fin_q, 256, 0, st>>>(Q, ldq, w.q_inv, M, d, cos, w_pos, pos_idx, 1.f / tau, N, w.extra);
+        GCF_LAUNCH_CHECK("pos_scatter_kernel");
+        extra = w.extra;
+      }
+      grad_finish_kernel_launch(fin_k, st, w.gpart_b, ns, w.k_rows, d_pad, kLn2, Kmat, ldk, w.k_inv, N, d, cos, nullptr, nullptr,
+                                                0.f, nullptr, 0, nullptr, 0, extra, gK, ldgk);
+      GCF_LAUNCH_CHECK("grad_finish_kernel");
+    }
+    return GCF_OK;
+  }
   if (gQ != nullptr) {
     // g q^_i = (1/tau) sum_j P_ij k^_j  (+ w_pos[i]/tau k^_pos(i))
     GradPlan gp{0, 0, 0, 0, 0};
@@ -926,7 +1102,7 @@ extern "C" int gcf_infonce_bwd(const float* Q, int64_t ldq, int64_t M, const flo
       rc = run_grad(w.qb, M, w.kb, N, d_pad, w_row, row_lse, w_col, col_lse, 0, w.gpart, &gp, st);
       if (rc != GCF_OK) return rc;
     }
-    grad_finish_kernel<<<fin_q, 256, 0, st>>>(w.gpart, gp.n_splits, gp.a_pad, d_pad, 1.f / tau, Q, ldq, w.q_inv, M, d, cos,
+    grad_finish_kernel_launch(fin_q, st, w.gpart, gp.n_splits, gp.a_pad, d_pad, 1.f / tau, Q, ldq, w.q_inv, M, d, cos,
                                               w_pos, pos_idx, 1.f / tau, Kmat, ldk, w.k_inv, N, nullptr, gQ, ldgq);
     GCF_LAUNCH_CHECK("grad_finish_kernel");
   }
@@ -944,7 +1120,7 @@ extern "C" int gcf_infonce_bwd(const float* Q, int64_t ldq, int64_t M, const flo
       GCF_LAUNCH_CHECK("pos_scatter_kernel");
       extra = w.extra;
     }
-    grad_finish_kernel<<<fin_k, 256, 0, st>>>(w.gpart, gp.n_splits, gp.a_pad, d_pad, kLn2, Kmat, ldk, w.k_inv, N, d, cos,
+    grad_finish_kernel_launch(fin_k, st, w.gpart, gp.n_splits, gp.a_pad, d_pad, kLn2, Kmat, ldk, w.k_inv, N, d, cos,
                                               nullptr, nullptr, 0.f, nullptr, 0, nullptr, 0, extra, gK, ldgk);
     GCF_LAUNCH_CHECK("grad_finish_kernel");
   }
@@ -953,7 +1129,7 @@ extern "C" int gcf_infonce_bwd(const float* Q, int64_t ldq, int64_t M, const flo
 
 // ---- DirectAU (directau.py:240-251) on the same two kernels: S = 2t x^ x^T with the diagonal masked -------------
 extern "C" size_t gcf_directau_workspace_bytes(int64_t B, int32_t d) {
-  if (B < 0 || d <= 0 || d > 256) return 0;
+  if (B < 0 || d <= 0 || d > kMaxChunks * kChunkK) return 0;
   return carve_ws(nullptr, B, B, d).bytes + 1024 + 4 * align_up((size_t)std::max<int64_t>(B, 1) * 4, 1024);
 }
 
@@ -969,7 +1145,7 @@ static DauWs carve_dau(void* ws_aligned, int64_t B, int32_t d) {
 
 static int directau_check(const char* who, const float* x, int64_t ldx, const float* y, int64_t ldy, int64_t B, int32_t d,
                           float t, void* workspace, size_t workspace_bytes) {
-  if (d <= 0 || d > 256) { set_error("%s: d=%d unsupported (1..256)", who, d); return GCF_EUNSUPPORTED; }
+  if (d <= 0 || d > kMaxChunks * kChunkK) { set_error("%s: d=%d unsupported (1..%d)", who, d, kMaxChunks * kChunkK); return GCF_EUNSUPPORTED; }
   GCF_REQUIRE(B >= 2, "%s: needs at least two rows (pdist of fewer is empty)", who);
   GCF_REQUIRE(B < (1LL << 31), "%s: B must fit int32", who);
   GCF_REQUIRE(x && y && ldx >= d && ldy >= d, "%s: null operands / bad leading dims", who);
@@ -1044,12 +1220,17 @@ extern "C" int gcf_directau_bwd(const float* x, int64_t ldx, const float* y, int
     directau_weights_kernel<<<(unsigned)cdiv(B, 256), 256, 0, st>>>(out3, w3, which, B, t, dw.w, dw.l);
     GCF_LAUNCH_CHECK("directau_weights_kernel");
     GradPlan gp{0, 0, 0, 0, 0};
-    rc = run_grad(w.qb, B, w.kb, B, d_pad, dw.w, dw.l, nullptr, nullptr, 1, w.gpart, &gp, st);
+    if (d_pad > 4 * kChunkK) {
+      rc = run_grad_wide(w.qb, B, w.q_rows, w.kb, B, w.k_rows, d_pad, dw.w, dw.l, nullptr, nullptr, 1, w.gpart, nullptr, w.probs, st);
+      gp.n_splits = 1; gp.a_pad = w.q_rows;
+    } else {
+      rc = run_grad(w.qb, B, w.kb, B, d_pad, dw.w, dw.l, nullptr, nullptr, 1, w.gpart, &gp, st);
+    }
     if (rc != GCF_OK) return rc;
     directau_align_grad_kernel<<<(unsigned)cdiv(B * d, 256), 256, 0, st>>>(x, ldx, inv_x, y, ldy, inv_y, B, d, w3,
                                                                           which == 0 ? 1.f : -1.f, w.extra);
     GCF_LAUNCH_CHECK("directau_align_grad_kernel");
-    grad_finish_kernel<<<fin, 256, 0, st>>>(w.gpart, gp.n_splits, gp.a_pad, d_pad, 1.f, src[which], lds[which], invs[which],
+    grad_finish_kernel_launch(fin, st, w.gpart, gp.n_splits, gp.a_pad, d_pad, 1.f, src[which], lds[which], invs[which],
                                             B, d, 1, nullptr, nullptr, 0.f, nullptr, 0, nullptr, 0, w.extra, outs[which],
                                             ldo[which]);
     GCF_LAUNCH_CHECK("grad_finish_kernel");

@@ -19,12 +19,13 @@ def _unit(x):
 
 
 @pytest.mark.parametrize("m,n,d", [(128, 256, 64), (100, 300, 64), (513, 1000, 128), (4096, 4096, 64), (257, 70000, 64),
-                                   (64, 129, 32), (300, 515, 256), (1, 1, 16)])
+                                   (64, 129, 32), (300, 515, 256), (1, 1, 16), (300, 700, 320), (257, 1000, 512), (130, 600, 1024)])
 @pytest.mark.parametrize("cos", [True, False])
 def test_lse_and_pos_vs_fp64(cuda, m, n, d, cos):
     g = torch.Generator().manual_seed(m * 7 + n)
-    q = torch.randn(m, d, generator=g) * (1.0 if cos else 0.3)
-    k = torch.randn(n, d, generator=g) * (1.0 if cos else 0.3)
+    scale = 1.0 if cos else 0.3 * (64.0 / max(d, 64)) ** 0.5   # keep un-normalised logits O(1) whatever the width
+    q = torch.randn(m, d, generator=g) * scale
+    k = torch.randn(n, d, generator=g) * scale
     tau = 0.2 if cos else 0.5
     pos_idx = torch.randint(0, n, (m,), generator=g)
     row, col, pos = F_.infonce_stats_raw(q.to(cuda), k.to(cuda), tau, cos=cos, pos_idx=pos_idx.to(cuda), want_col=True)
@@ -112,7 +113,8 @@ def test_directau_matches_fixture(cuda, golden):
 
 
 @pytest.mark.parametrize("m,n,d", [(128, 128, 64), (100, 300, 64), (513, 1000, 128), (2048, 2048, 64), (300, 20000, 64),
-                                   (64, 129, 32), (300, 515, 256), (257, 1000, 192), (3, 5, 16)])
+                                   (64, 129, 32), (300, 515, 256), (257, 1000, 192), (3, 5, 16),
+                                   (300, 700, 320), (513, 1000, 512), (260, 300, 1024)])   # d > 256: P materialised + library GEMMs
 @pytest.mark.parametrize("mode", ["row", "sym"])
 def test_infonce_backward_vs_fp64(cuda, m, n, d, mode):
     """Gradients of sum_i c_i (row_lse_i - pos_i) [+ column term] w.r.t. both operands against fp64 autograd."""
@@ -140,7 +142,7 @@ def test_infonce_backward_vs_fp64(cuda, m, n, d, mode):
     _grad_close(qc.grad, qd.grad); _grad_close(kc.grad, kd.grad)
 
 
-@pytest.mark.parametrize("b,d", [(48, 16), (2048, 128), (1000, 64), (130, 256)])
+@pytest.mark.parametrize("b,d", [(48, 16), (2048, 128), (1000, 64), (130, 256), (700, 512)])
 def test_directau_vs_fp64(cuda, b, d):
     g = torch.Generator().manual_seed(b + d)
     x = torch.randn(b, d, generator=g); y = x * 0.5 + torch.randn(b, d, generator=g)

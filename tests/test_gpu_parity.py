@@ -595,7 +595,7 @@ def test_c_abi_reports_errors_instead_of_crashing(cuda):
     with pytest.raises(_lib.GcfError, match="temperature must be positive"):
         F_.infonce_stats_raw(torch.randn(4, 16, device=cuda), torch.randn(4, 16, device=cuda), 0.0)
     with pytest.raises(_lib.GcfError, match="unsupported"):
-        F_.infonce_stats_raw(torch.randn(4, 512, device=cuda), torch.randn(4, 512, device=cuda), 0.2)
+        F_.infonce_stats_raw(torch.randn(4, 2048, device=cuda), torch.randn(4, 2048, device=cuda), 0.2)
     with pytest.raises(ValueError):
         F_.spmm(g, torch.randn(7, 64, device=cuda))                                       # row count mismatch
     with pytest.raises(RuntimeError, match="CUDA"):
