@@ -201,6 +201,11 @@ int gcf_sample_negatives(uint64_t seed, uint64_t offset, const int64_t* users, i
 int gcf_csr_dropout_values(const float* vals, int64_t n, const int32_t* index, float rate, uint64_t seed, uint64_t offset,
                            float* out, gcf_stream_t stream);
 
+/* out[j] = Philox4x32-10(counter = (j, offset), key = seed)[0] in [0, 2^32): one uniform key per entry.  The `keep`
+ * smallest keys select a uniformly random subset of exact size (GraphAugmentor.edge_dropout, sept.py:53-62:
+ * np.random.choice(idx, int(n * (1 - drop_rate)), replace=False)). */
+int gcf_philox_keys(int64_t n, uint64_t seed, uint64_t offset, int64_t* out, gcf_stream_t stream);
+
 /* ---- (3) losses ----------------------------------------------------------------------- */
 
 #define GCF_BPR_LOG_EPS_SIGMOID 0 /* -log(eps + sigmoid(x))      ncl.py:116-120, mhcn.py:35-39 */

@@ -68,6 +68,7 @@ _SIGNATURES = {
                                        c_void_p, c_size_t, c_void_p]),
     "gcf_sample_negatives": (c_int32, [c_uint64, c_uint64, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p,
                                        c_int32, c_void_p, c_void_p]),
+    "gcf_philox_keys": (c_int32, [c_int64, c_uint64, c_uint64, c_void_p, c_void_p]),
     "gcf_csr_dropout_values": (c_int32, [c_void_p, c_int64, c_void_p, c_float, c_uint64, c_uint64, c_void_p, c_void_p]),
     "gcf_bpr_workspace_bytes": (c_size_t, [c_int64]),
     "gcf_bpr_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32,

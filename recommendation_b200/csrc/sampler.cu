@@ -73,9 +73,30 @@ dropout_values_kernel(const float* __restrict__ vals, long long n, const int* __
   }
 }
 
+// out[j] = Philox4x32-10(counter = (j, offset), key = seed)[0]: one uniform 32-bit key per entry (random subsets of exact size)
+__global__ void __launch_bounds__(256)
+philox_keys_kernel(long long n, uint32_t seed_lo, uint32_t seed_hi, uint32_t off_lo, uint32_t off_hi, int64_t* __restrict__ out) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    uint32_t w[4];
+    philox4x32_10((uint32_t)j, (uint32_t)((unsigned long long)j >> 32), off_lo, off_hi, seed_lo, seed_hi, w);
+    out[j] = (int64_t)w[0];
+  }
+}
+
 }  // namespace gcf
 
 using namespace gcf;
+
+extern "C" int gcf_philox_keys(int64_t n, uint64_t seed, uint64_t offset, int64_t* out, gcf_stream_t stream) {
+  GCF_REQUIRE(n >= 0, "gcf_philox_keys: negative n");
+  if (n == 0) return GCF_OK;
+  GCF_REQUIRE(out != nullptr, "gcf_philox_keys: null output");
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(n, 256), (long long)sm_count() * 16));
+  philox_keys_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(n, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                                                          (uint32_t)offset, (uint32_t)(offset >> 32), out);
+  GCF_LAUNCH_CHECK("philox_keys_kernel");
+  return GCF_OK;
+}
 
 extern "C" int gcf_csr_dropout_values(const float* vals, int64_t n, const int32_t* index, float rate, uint64_t seed,
                                       uint64_t offset, float* out, gcf_stream_t stream) {

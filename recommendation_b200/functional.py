@@ -529,3 +529,52 @@ def l2_reg_loss(reg: float, *args: torch.Tensor) -> torch.Tensor:
     for emb in args:
         emb_loss = emb_loss + torch.norm(emb, p=2) / emb.shape[0]
     return emb_loss * reg
+
+
+# =========================================================================================
+# SpMM with the row-L2-normalise epilogue (sept.py:220-226, mhcn.py:440-457)
+# =========================================================================================
+class _SpMMNormalize(torch.autograd.Function):
+    """(t, y) = (A @ x, F.normalize(A @ x, dim=1)): ONE launch writes both (fused epilogue); the backward folds the chain rule
+    of the normalisation into the gradient of t and runs a single transposed SpMM."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, graph: CSRGraph):
+        x = _f32c(x, "x")
+        if x.shape[0] != graph.n_cols:
+            raise ValueError(f"spmm_normalize: X has {x.shape[0]} rows, operator has {graph.n_cols} columns")
+        t = torch.empty(graph.n_rows, x.shape[1], dtype=torch.float32, device=x.device)
+        y = torch.empty_like(t)
+        spmm_raw(graph, x, y=t, out=y, epilogue=_lib.EPILOGUE_L2NORM)
+        ctx.graph = graph
+        ctx.save_for_backward(t, y)
+        ctx.set_materialize_grads(False)
+        return t, y
+
+    @staticmethod
+    def backward(ctx, g_t, g_y):
+        t, y = ctx.saved_tensors
+        if g_t is None and g_y is None:
+            return None, None
+        total = None if g_t is None else _f32c(g_t, "grad")
+        if g_y is not None:
+            g_y = _f32c(g_y, "grad")
+            norm = t.norm(dim=1, keepdim=True)
+            through = (g_y - y * (y * g_y).sum(dim=1, keepdim=True)) / norm.clamp_min(1e-12)   # F.normalize eps
+            through = torch.where(norm < 1e-12, g_y / 1e-12, through)                          # |t| below eps: y = t / eps
+            total = through if total is None else total + through
+        graph_t = ctx.graph.transpose()
+        gx = torch.empty(graph_t.n_rows, total.shape[1], dtype=torch.float32, device=total.device)
+        spmm_raw(graph_t, total.contiguous(), y=gx)
+        return gx, None
+
+
+def spmm_and_normalize(graph: CSRGraph, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(A @ x, F.normalize(A @ x, dim=1)) -- mhcn.py:440-457 keeps the raw product for the next layer and the normalised one
+    for the layer sum."""
+    return _SpMMNormalize.apply(x, graph)
+
+
+def spmm_normalize(graph: CSRGraph, x: torch.Tensor) -> torch.Tensor:
+    """F.normalize(A @ x, dim=1) (sept.py:222-224)."""
+    return _SpMMNormalize.apply(x, graph)[1]

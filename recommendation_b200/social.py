@@ -75,11 +75,12 @@ class MHCNModel(nn.Module):
         for _ in range(self.n_layers):
             mixed, _ = self.channel_attention(c1, c2, c3)
             mixed = mixed + simple / 2
-            c1 = F_.spmm(self.H_s, c1); all_c1.append(TF.normalize(c1, p=2, dim=1))
-            c2 = F_.spmm(self.H_j, c2); all_c2.append(TF.normalize(c2, p=2, dim=1))
-            c3 = F_.spmm(self.H_p, c3); all_c3.append(TF.normalize(c3, p=2, dim=1))
-            new_item = F_.spmm(self.R_t, mixed); all_i.append(TF.normalize(new_item, p=2, dim=1))
-            simple = F_.spmm(self.R, item); all_simple.append(TF.normalize(simple, p=2, dim=1))
+            # every torch.sparse.mm + F.normalize pair of mhcn.py:440-457 is one launch (raw product + normalised rows)
+            c1, n1 = F_.spmm_and_normalize(self.H_s, c1); all_c1.append(n1)
+            c2, n2 = F_.spmm_and_normalize(self.H_j, c2); all_c2.append(n2)
+            c3, n3 = F_.spmm_and_normalize(self.H_p, c3); all_c3.append(n3)
+            new_item, ni = F_.spmm_and_normalize(self.R_t, mixed); all_i.append(ni)
+            simple, ns = F_.spmm_and_normalize(self.R, item); all_simple.append(ns)
             item = new_item
         c1, c2, c3 = (torch.stack(a).sum(dim=0) for a in (all_c1, all_c2, all_c3))
         simple = torch.stack(all_simple).sum(dim=0)

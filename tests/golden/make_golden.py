@@ -301,6 +301,23 @@ def main():
              loss=t2n(bloss), g_user=bg[0], g_item=bg[1], g_pred_w=bg[2], g_pred_b=bg[3],
              target_user1=t2n(bm.target_encoder.embedding_dict["user_emb"]), target_item1=t2n(bm.target_encoder.embedding_dict["item_emb"]))
 
+    # ------------------------------------------------------------------ sept (univariate/sept.py:53-62,220-226)
+    sp_mod = load_ref("sept", "univariate/sept.py", stubs=("tensorflow", "faiss"))
+    sdat = sp_mod.Interaction({}, [tuple(r) for r in train], [tuple(r) for r in test])
+    np.random.seed(31)
+    dropped = sp_mod.GraphAugmentor.edge_dropout(sdat.norm_adj, 0.25).tocsr()
+    dropped.sort_indices()
+    full = sdat.norm_adj.tocsr(); full.sort_indices()
+    s_emb = (torch.randn(sdat.user_num + sdat.item_num, d) * 0.3).requires_grad_(True)
+    coo = dropped.tocoo()
+    adj_t = torch.sparse_coo_tensor(np.vstack([coo.row, coo.col]), coo.data.astype(np.float32), coo.shape).coalesce()
+    s_out = sp_mod.SEPT.encoder(SimpleNamespace(n_layers=3), s_emb, adj_t)
+    s_proj = torch.randn_like(s_out)
+    np.savez(OUT / "sept_encoder.npz", n_layers=3, n_users=sdat.user_num, n_items=sdat.item_num,
+             full_indptr=full.indptr, full_indices=full.indices, full_data=full.data.astype(np.float32), full_nnz_nonzero=int(sdat.norm_adj.nnz),
+             drop_indptr=dropped.indptr, drop_indices=dropped.indices, drop_data=dropped.data.astype(np.float32),
+             emb=t2n(s_emb), out=t2n(s_out), proj=t2n(s_proj), grad=grads_of((s_out * s_proj).sum(), s_emb)[0])
+
     # ------------------------------------------------------------------ ranking_evaluation (ncl.py:133-178) on random lists
     erng = np.random.default_rng(21)
     eU, eI, eN = 30, 80, 20

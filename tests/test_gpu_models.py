@@ -412,3 +412,36 @@ def test_lightgcn_script_surface(cuda, tmp_path):
            "loss_type": "bpr"}
     metrics = lg.train_model(cfg, str(tmp_path / "train.txt"), str(tmp_path / "test.txt"), epochs=5)
     assert set(metrics[10]) == {"HR", "P", "R", "NDCG"} and 0.0 <= metrics[10]["HR"] <= 1.0
+
+
+def test_sept_encoder_and_augmentor(cuda, golden):
+    from recommendation_b200 import sept
+
+    z = golden("sept_encoder")
+    U, I, K = int(z["n_users"]), int(z["n_items"]), int(z["n_layers"])
+    n = U + I
+    full = sp.csr_matrix((z["full_data"], z["full_indices"], z["full_indptr"]), shape=(n, n))
+    dropped = sp.csr_matrix((z["drop_data"], z["drop_indices"], z["drop_indptr"]), shape=(n, n))   # produced by the reference's augmentor
+    data = SimpleNamespace(user_num=U, item_num=I, norm_adj=full)
+    m = sept.SEPTEncoder(data, z["emb"].shape[1], K, 0.25)
+    assert sorted(m.state_dict().keys()) == ["item_embeddings.weight", "user_embeddings.weight"]
+    emb = torch.from_numpy(z["emb"]).to(cuda).requires_grad_(True)
+    out = m.encoder(emb, CSRGraph.from_scipy(dropped, device=cuda))                  # sept.py:220-226 on the reference's graph
+    _close(out, z["out"], atol=1e-6)
+    (out * torch.from_numpy(z["proj"]).to(cuda)).sum().backward()
+    _close(emb.grad, z["grad"], atol=1e-6)
+    # augmentor: the reference enumerates stored entries INCLUDING duplicate interactions (sept.py:53-62)
+    rng = np.random.default_rng(0)
+    r = rng.integers(0, 50, 3000); c = rng.integers(0, 60, 3000)
+    raw = sp.coo_matrix((np.ones(3000, np.float32), (r, c)), shape=(50, 60))          # many duplicates
+    a1 = sept.GraphAugmentor.edge_dropout(raw, 0.3)
+    a2 = sept.GraphAugmentor.edge_dropout(raw, 0.3)
+    for a in (a1, a2):
+        kept = a.to_scipy()
+        assert abs(kept.sum() - int(3000 * 0.7)) < 1e-3                                  # exactly int(n (1 - rate)) entries kept
+        assert (raw.tocsr() - kept).min() >= 0                                          # a sub-multiset of the stored entries
+        assert np.allclose(kept.data, np.round(kept.data))                             # 0/1 entries, duplicates summed
+    assert abs(a1.to_scipy() - a2.to_scipy()).sum() > 0                               # a fresh draw per call
+    m.train(); u1, v1 = m()
+    m.eval(); u2, v2 = m(); u3, v3 = m()
+    assert u1.shape == (U, z["emb"].shape[1]) and torch.equal(u2, u3) and not torch.equal(u1, u2)
