@@ -445,3 +445,61 @@ def test_sept_encoder_and_augmentor(cuda, golden):
     m.train(); u1, v1 = m()
     m.eval(); u2, v2 = m(); u3, v3 = m()
     assert u1.shape == (U, z["emb"].shape[1]) and torch.equal(u2, u3) and not torch.equal(u1, u2)
+
+
+def test_gpu_kmeans_against_sklearn_lloyd(cuda):
+    """Same initial centroids -> the same Lloyd fixed point as scikit-learn (full-batch, 25 iterations), plus the invariants
+    of the result and NCL's k cap (ncl.py:347-356)."""
+    from sklearn.cluster import KMeans
+    from recommendation_b200 import kmeans as km
+
+    rng = np.random.default_rng(3)
+    centers = rng.standard_normal((12, 16)) * 4
+    x = (centers[rng.integers(0, 12, 4000)] + rng.standard_normal((4000, 16)) * 0.7).astype(np.float32)
+    init = x[rng.permutation(4000)[:12]].copy()
+    c, idx, obj = km.kmeans(torch.from_numpy(x).to(cuda), 12, niter=25, init=torch.from_numpy(init))
+    ref = KMeans(n_clusters=12, init=init, n_init=1, max_iter=25, tol=0.0, algorithm="lloyd").fit(x)
+    np.testing.assert_allclose(obj, ref.inertia_, rtol=1e-3)
+    assert (idx.cpu().numpy() == ref.labels_).mean() > 0.995
+    # invariants: every point sits with its nearest centroid; every centroid is the mean of its points
+    d2 = ((x[:, None, :] - c.cpu().numpy()[None]) ** 2).sum(-1)
+    assert (d2.argmin(1) == idx.cpu().numpy()).mean() > 0.999
+    c2, idx2, _ = km.kmeans(torch.from_numpy(x).to(cuda), 12, niter=60, init=torch.from_numpy(init))   # converged
+    for j in range(12):
+        np.testing.assert_allclose(c2[j].cpu().numpy(), x[idx2.cpu().numpy() == j].mean(0), rtol=1e-3, atol=1e-3)
+    cc, ii, k_used = km.run_kmeans(torch.from_numpy(x[:400]).to(cuda), 1000)
+    assert k_used == max(2, 400 // 39) and cc.shape == (k_used, 16) and ii.shape == (400,) and ii.dtype == torch.int64
+    # an empty cluster (duplicate initial centroids) is re-seeded instead of producing NaNs
+    bad = np.repeat(init[:1], 12, 0)
+    c3, idx3, _ = km.kmeans(torch.from_numpy(x).to(cuda), 12, niter=25, init=torch.from_numpy(bad))
+    assert torch.isfinite(c3).all() and len(torch.unique(idx3)) > 1
+
+
+def test_ncl_training_iteration_runs_and_learns(cuda):
+    """ncl.py:308-329 end to end on a small graph: E-step (GPU k-means), batch sampler, BPR + ssl_layer + ProtoNCE, Adam."""
+    from recommendation_b200 import ncl as ncl_mod
+    from recommendation_b200.losses import NCLLosses
+
+    rng = np.random.default_rng(2)
+    U, I, E = 400, 500, 12000
+    u = rng.integers(0, U, E); i = (rng.zipf(1.5, E) - 1) % I
+    raw = sp.coo_matrix((np.ones(2 * E, np.float32), (np.concatenate([u, i + U]), np.concatenate([i + U, u]))), shape=(U + I, U + I))
+    data = SimpleNamespace(user_num=U, item_num=I, norm_adj=raw, training_data=[[f"u{a}", f"i{b}", 1.0] for a, b in zip(u, i)],
+                           user={f"u{a}": a for a in range(U)}, item={f"i{b}": b for b in range(I)})
+    torch.manual_seed(0)
+    model = encoders.LGCNEncoder(data, 64, 3)
+    with torch.no_grad():   # the raw (un-normalised) adjacency of ncl.py grows activations by ~deg per layer
+        for p in model.parameters():
+            p.mul_(0.01)
+    ncl = NCLLosses(U, I, 0.1, 1e-6, 1.5, 8e-8, 512)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    k = ncl_mod.e_step(model, ncl, 20)
+    assert k == max(2, min(20, U // 39)) and ncl.user_2cluster.shape == (U,) and ncl.item_centroids.shape[1] == 64
+    first = last = None
+    for epoch in range(3):
+        for n, batch in enumerate(sampling.next_batch_pairwise(data, 512)):
+            total, parts = ncl_mod.ncl_step(model, ncl, opt, batch, 1e-4, 512, 1, k=k, refresh_clusters=(n % 8 == 0))
+            assert torch.isfinite(total) and all(torch.isfinite(v) for v in parts.values())
+            first = parts["rec"].item() if first is None else first
+            last = parts["rec"].item()
+    assert last < first            # the ranking loss goes down
