@@ -44,6 +44,59 @@ struct LongPlan {
 
 constexpr int kWarpsPerBlock = 8;
 
+// One batch of up to LPR (col, val) pairs -- lane t of the sub-warp holds pair t -- is broadcast lane by lane and
+// consumed UNR independent 128-bit row gathers at a time.
+template <int LPR, int VPL, int UNR, bool GUARD>
+__device__ __forceinline__ void consume_batch(int c, float v, int cnt, const float* __restrict__ X, long long ldx, int sl,
+                                              unsigned mask, int dvec, float4 (&acc)[VPL]) {
+  if (cnt == LPR) {
+#pragma unroll
+    for (int t0 = 0; t0 < LPR; t0 += UNR) {
+      float4 x[UNR][VPL];
+      float w[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int ct = __shfl_sync(mask, c, t0 + u, LPR);
+        w[u] = __shfl_sync(mask, v, t0 + u, LPR);
+        const float4* xr = reinterpret_cast<const float4*>(X + (long long)ct * ldx);
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          const int idx = sl + k * LPR;
+          x[u][k] = (!GUARD || idx < dvec) ? __ldg(xr + idx) : f4_zero();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) f4_fma(acc[k], w[u], x[u][k]);
+    }
+  } else {
+    // ragged tail: replay the last valid column with weight 0 to keep UNR loads in flight
+    for (int t0 = 0; t0 < cnt; t0 += UNR) {
+      float4 x[UNR][VPL];
+      float w[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int t = t0 + u;
+        const int tt = min(t, cnt - 1);
+        const int ct = __shfl_sync(mask, c, tt, LPR);
+        const float wt = __shfl_sync(mask, v, tt, LPR);
+        w[u] = (t < cnt) ? wt : 0.f;
+        const float4* xr = reinterpret_cast<const float4*>(X + (long long)ct * ldx);
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          const int idx = sl + k * LPR;
+          x[u][k] = (!GUARD || idx < dvec) ? __ldg(xr + idx) : f4_zero();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) f4_fma(acc[k], w[u], x[u][k]);
+    }
+  }
+}
+
 template <int LPR, int VPL, int UNR, bool GUARD>
 __device__ __forceinline__ void accumulate(const int* __restrict__ col_idx, const float* __restrict__ vals,
                                            int begin, int end, int stride, const float* __restrict__ X,
@@ -56,53 +109,48 @@ __device__ __forceinline__ void accumulate(const int* __restrict__ col_idx, cons
       c = ld_stream_i32(col_idx + j);
       v = ld_stream_f32(vals + j);
     }
-    const int cnt = min(LPR, end - base);
-    if (cnt == LPR) {
+    consume_batch<LPR, VPL, UNR, GUARD>(c, v, min(LPR, end - base), X, ldx, sl, mask, dvec, acc);
+  }
+}
+
+// Narrow rows (d <= 32 floats: feature-sharded slices): a sub-warp has only LPR = d/4 lanes, so one coalesced
+// (col, val) request per iteration would leave just LPR row gathers in flight.  Each lane loads PPL pairs
+// (stride LPR) instead and the sub-warp keeps LPR * PPL predicated 128-bit gathers in flight; the FMA order is
+// the entry order of accumulate<>, so the result is bit-identical to it.
+template <int LPR, int PPL>
+__device__ __forceinline__ void accumulate_multi(const int* __restrict__ col_idx, const float* __restrict__ vals,
+                                                 int begin, int end, int stride, const float* __restrict__ X,
+                                                 long long ldx, int sl, unsigned mask, float4& acc) {
+  // `stride` has accumulate<>'s meaning (distance between a sub-warp's consecutive groups of LPR entries), so the
+  // entries a sub-warp sums, and their order, do not depend on PPL
+  for (int base = begin; base < end; base += PPL * stride) {
+    int c[PPL];
+    float v[PPL];
 #pragma unroll
-      for (int t0 = 0; t0 < LPR; t0 += UNR) {
-        float4 x[UNR][VPL];
-        float w[UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int ct = __shfl_sync(mask, c, t0 + u, LPR);
-          w[u] = __shfl_sync(mask, v, t0 + u, LPR);
-          const float4* xr = reinterpret_cast<const float4*>(X + (long long)ct * ldx);
-#pragma unroll
-          for (int k = 0; k < VPL; ++k) {
-            const int idx = sl + k * LPR;
-            x[u][k] = (!GUARD || idx < dvec) ? __ldg(xr + idx) : f4_zero();
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u)
-#pragma unroll
-          for (int k = 0; k < VPL; ++k) f4_fma(acc[k], w[u], x[u][k]);
-      }
-    } else {
-      // ragged tail: replay the last valid column with weight 0 to keep UNR loads in flight
-      for (int t0 = 0; t0 < cnt; t0 += UNR) {
-        float4 x[UNR][VPL];
-        float w[UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int t = t0 + u;
-          const int tt = min(t, cnt - 1);
-          const int ct = __shfl_sync(mask, c, tt, LPR);
-          const float wt = __shfl_sync(mask, v, tt, LPR);
-          w[u] = (t < cnt) ? wt : 0.f;
-          const float4* xr = reinterpret_cast<const float4*>(X + (long long)ct * ldx);
-#pragma unroll
-          for (int k = 0; k < VPL; ++k) {
-            const int idx = sl + k * LPR;
-            x[u][k] = (!GUARD || idx < dvec) ? __ldg(xr + idx) : f4_zero();
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u)
-#pragma unroll
-          for (int k = 0; k < VPL; ++k) f4_fma(acc[k], w[u], x[u][k]);
+    for (int p = 0; p < PPL; ++p) {
+      const int j = base + p * stride + sl;
+      c[p] = -1;
+      v[p] = 0.f;
+      if (j < end) {
+        c[p] = ld_stream_i32(col_idx + j);
+        v[p] = ld_stream_f32(vals + j);
       }
     }
+    float4 x[PPL][LPR];
+    float w[PPL][LPR];
+#pragma unroll
+    for (int p = 0; p < PPL; ++p)
+#pragma unroll
+      for (int t = 0; t < LPR; ++t) {
+        const int ct = __shfl_sync(mask, c[p], t, LPR);
+        w[p][t] = __shfl_sync(mask, v[p], t, LPR);
+        x[p][t] = f4_zero();
+        if (ct >= 0) x[p][t] = __ldg(reinterpret_cast<const float4*>(X + (long long)ct * ldx) + sl);
+      }
+#pragma unroll
+    for (int p = 0; p < PPL; ++p)
+#pragma unroll
+      for (int t = 0; t < LPR; ++t) f4_fma(acc, w[p][t], x[p][t]);
   }
 }
 
@@ -157,7 +205,73 @@ __device__ __forceinline__ void finish_row(const Epi& ep, long long row, int sl,
   }
 }
 
-template <int LPR, int VPL, int UNR, bool GUARD, int MINB>
+// Long rows (power-law hubs): one warp per chunk of `lp.chunk` entries; the last-arriving chunk of a row reduces the
+// partial sums in chunk order (deterministic) and runs the epilogue.
+template <int LPR, int VPL, int UNR, bool GUARD, int PPL>
+__device__ __forceinline__ void long_chunk_path(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                                                const float* __restrict__ vals, const float* __restrict__ X,
+                                                long long ldx, int dvec, const Epi& ep, const LongPlan& lp, int warp,
+                                                int lane, int sub, int sl, unsigned mask, float4 (&acc)[VPL]) {
+  constexpr int RPW = 32 / LPR;
+  // ---- long-row chunk: one warp per chunk ----
+  const int chunk_id = blockIdx.x * kWarpsPerBlock + warp;
+  if (chunk_id >= lp.n_chunks) return;
+  const int L = lp.chunk_long[chunk_id];
+  const int row = lp.long_rows[L];
+  const int c0 = lp.long_chunk_ptr[L];
+  const int nck = lp.long_chunk_ptr[L + 1] - c0;
+  const int rs = row_ptr[row], re = row_ptr[row + 1];
+  const int s = rs + (chunk_id - c0) * lp.chunk;
+  const int e = min(s + lp.chunk, re);
+  if constexpr (PPL > 1)
+    accumulate_multi<LPR, PPL>(col_idx, vals, s + sub * LPR, e, LPR * RPW, X, ldx, sl, mask, acc[0]);
+  else
+    accumulate<LPR, VPL, UNR, GUARD>(col_idx, vals, s + sub * LPR, e, LPR * RPW, X, ldx, sl, mask, dvec, acc);
+  __syncwarp();
+#pragma unroll
+  for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, off);
+      acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, off);
+      acc[k].z += __shfl_xor_sync(0xffffffffu, acc[k].z, off);
+      acc[k].w += __shfl_xor_sync(0xffffffffu, acc[k].w, off);
+    }
+  const long long dpad = (long long)dvec * 4;
+  if (sub == 0) {
+    float4* part = reinterpret_cast<float4*>(lp.partial + (long long)chunk_id * dpad);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int idx = sl + k * LPR;
+      if (!GUARD || idx < dvec) part[idx] = acc[k];
+    }
+  }
+  __threadfence();
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) last = (atomicAdd(lp.counters + L, 1) == nck - 1);
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence();
+  if (sub == 0) {
+    float4 tot[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) tot[k] = f4_zero();
+    for (int q = 0; q < nck; ++q) {
+      const float4* p = reinterpret_cast<const float4*>(lp.partial + (long long)(c0 + q) * dpad);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int idx = sl + k * LPR;
+        if (!GUARD || idx < dvec) f4_add(tot[k], __ldcg(p + idx));
+      }
+    }
+    finish_row<LPR, VPL, GUARD>(ep, row, sl, mask, dvec, tot);
+  }
+  if (lane == 0) lp.counters[L] = 0;  // self-resetting ticket for the next launch
+  return;
+}
+
+template <int LPR, int VPL, int UNR, bool GUARD, int MINB, int PPL = 1>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 spmm_csr_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx, const float* __restrict__ vals,
                 long long n_rows, const float* __restrict__ X, long long ldx, int dvec, Epi ep, LongPlan lp,
@@ -174,58 +288,7 @@ spmm_csr_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx
   for (int k = 0; k < VPL; ++k) acc[k] = f4_zero();
 
   if ((int)blockIdx.x < long_blocks) {
-    // ---- long-row chunk: one warp per chunk ----
-    const int chunk_id = blockIdx.x * kWarpsPerBlock + warp;
-    if (chunk_id >= lp.n_chunks) return;
-    const int L = lp.chunk_long[chunk_id];
-    const int row = lp.long_rows[L];
-    const int c0 = lp.long_chunk_ptr[L];
-    const int nck = lp.long_chunk_ptr[L + 1] - c0;
-    const int rs = row_ptr[row], re = row_ptr[row + 1];
-    const int s = rs + (chunk_id - c0) * lp.chunk;
-    const int e = min(s + lp.chunk, re);
-    accumulate<LPR, VPL, UNR, GUARD>(col_idx, vals, s + sub * LPR, e, LPR * RPW, X, ldx, sl, mask, dvec, acc);
-    __syncwarp();
-#pragma unroll
-    for (int off = LPR; off < 32; off <<= 1)
-#pragma unroll
-      for (int k = 0; k < VPL; ++k) {
-        acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, off);
-        acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, off);
-        acc[k].z += __shfl_xor_sync(0xffffffffu, acc[k].z, off);
-        acc[k].w += __shfl_xor_sync(0xffffffffu, acc[k].w, off);
-      }
-    const long long dpad = (long long)dvec * 4;
-    if (sub == 0) {
-      float4* part = reinterpret_cast<float4*>(lp.partial + (long long)chunk_id * dpad);
-#pragma unroll
-      for (int k = 0; k < VPL; ++k) {
-        const int idx = sl + k * LPR;
-        if (!GUARD || idx < dvec) part[idx] = acc[k];
-      }
-    }
-    __threadfence();
-    __syncwarp();
-    int last = 0;
-    if (lane == 0) last = (atomicAdd(lp.counters + L, 1) == nck - 1);
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (!last) return;
-    __threadfence();
-    if (sub == 0) {
-      float4 tot[VPL];
-#pragma unroll
-      for (int k = 0; k < VPL; ++k) tot[k] = f4_zero();
-      for (int q = 0; q < nck; ++q) {
-        const float4* p = reinterpret_cast<const float4*>(lp.partial + (long long)(c0 + q) * dpad);
-#pragma unroll
-        for (int k = 0; k < VPL; ++k) {
-          const int idx = sl + k * LPR;
-          if (!GUARD || idx < dvec) f4_add(tot[k], __ldcg(p + idx));
-        }
-      }
-      finish_row<LPR, VPL, GUARD>(ep, row, sl, mask, dvec, tot);
-    }
-    if (lane == 0) lp.counters[L] = 0;  // self-resetting ticket for the next launch
+    long_chunk_path<LPR, VPL, UNR, GUARD, PPL>(row_ptr, col_idx, vals, X, ldx, dvec, ep, lp, warp, lane, sub, sl, mask, acc);
     return;
   }
 
@@ -234,11 +297,14 @@ spmm_csr_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx
   if (row >= n_rows) return;
   const int s = row_ptr[row], e = row_ptr[row + 1];
   if (lp.n_long > 0 && e - s > lp.chunk) return;  // owned by the long path
-  accumulate<LPR, VPL, UNR, GUARD>(col_idx, vals, s, e, LPR, X, ldx, sl, mask, dvec, acc);
+  if constexpr (PPL > 1)
+    accumulate_multi<LPR, PPL>(col_idx, vals, s, e, LPR, X, ldx, sl, mask, acc[0]);
+  else
+    accumulate<LPR, VPL, UNR, GUARD>(col_idx, vals, s, e, LPR, X, ldx, sl, mask, dvec, acc);
   finish_row<LPR, VPL, GUARD>(ep, row, sl, mask, dvec, acc);
 }
 
-template <int LPR, int VPL, int UNR, bool GUARD, int MINB>
+template <int LPR, int VPL, int UNR, bool GUARD, int MINB, int PPL = 1>
 static int launch(const gcf_csr_t* A, const float* X, long long ldx, int dvec, const Epi& ep, const LongPlan& lp,
                   cudaStream_t st) {
   constexpr int RPW = 32 / LPR;
@@ -247,7 +313,8 @@ static int launch(const gcf_csr_t* A, const float* X, long long ldx, int dvec, c
   const long long grid = long_blocks + short_blocks;
   if (grid <= 0) return GCF_OK;
   GCF_REQUIRE(grid < 2147483647LL, "gcf_spmm_csr_f32: grid too large");
-  spmm_csr_kernel<LPR, VPL, UNR, GUARD, MINB><<<(unsigned)grid, kWarpsPerBlock * 32, 0, st>>>(
+  static_assert(PPL == 1 || (VPL == 1 && !GUARD), "multi-pair batches are for exact narrow rows");
+  spmm_csr_kernel<LPR, VPL, UNR, GUARD, MINB, PPL><<<(unsigned)grid, kWarpsPerBlock * 32, 0, st>>>(
       A->row_ptr, A->col_idx, A->vals, A->n_rows, X, ldx, dvec, ep, lp, long_blocks);
   GCF_LAUNCH_CHECK("spmm_csr_kernel");
   return GCF_OK;
@@ -342,9 +409,22 @@ static int spmm_impl(const gcf_csr_t* A, int32_t d, const float* X, int64_t ldx,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int dvec = d / 4;
   switch (d) {
-    case 8:  return launch<2, 1, 2, false, 4>(A, X, ldx, dvec, ep, lp, st);  // feature-sharded slices (d / 8 GPUs)
-    case 16: return launch<4, 1, 4, false, 4>(A, X, ldx, dvec, ep, lp, st);
-    case 32: return launch<8, 1, 8, false, 3>(A, X, ldx, dvec, ep, lp, st);
+    // feature-sharded slices (d / G columns per rank).  Measured on the cfg5 graph (profiles/r01_exp_narrow_cfg5.log):
+    // d=8 4.23 -> 2.55 ms, d=16 4.65 -> 3.70 ms with 8 gathers in flight per sub-warp; d=32 6.85 -> 5.59 ms at 4 CTAs/SM
+    case 8:
+      if (variant == 1) return launch<2, 1, 2, false, 4>(A, X, ldx, dvec, ep, lp, st);      // 2 gathers in flight
+      if (variant == 2) return launch<2, 1, 2, false, 2, 8>(A, X, ldx, dvec, ep, lp, st);   // 16
+      if (variant == 3) return launch<2, 1, 2, false, 6, 2>(A, X, ldx, dvec, ep, lp, st);   // 4, 48 warps / SM
+      return launch<2, 1, 2, false, 4, 4>(A, X, ldx, dvec, ep, lp, st);                     // 8
+    case 16:
+      if (variant == 1) return launch<4, 1, 4, false, 4>(A, X, ldx, dvec, ep, lp, st);      // 4 gathers in flight
+      if (variant == 2) return launch<4, 1, 4, false, 2, 4>(A, X, ldx, dvec, ep, lp, st);   // 16
+      if (variant == 3) return launch<4, 1, 4, false, 6>(A, X, ldx, dvec, ep, lp, st);      // 4, 48 warps / SM
+      return launch<4, 1, 4, false, 4, 2>(A, X, ldx, dvec, ep, lp, st);                     // 8
+    case 32:
+      if (variant == 1) return launch<8, 1, 8, false, 2, 2>(A, X, ldx, dvec, ep, lp, st);   // 16 gathers in flight
+      if (variant == 2) return launch<8, 1, 8, false, 3>(A, X, ldx, dvec, ep, lp, st);
+      return launch<8, 1, 8, false, 4>(A, X, ldx, dvec, ep, lp, st);
     case 64:  // variants are tuning knobs (UNR loads in flight x resident blocks), same arithmetic
       if (variant == 1) return launch<16, 1, 4, false, 4>(A, X, ldx, dvec, ep, lp, st);
       if (variant == 2) return launch<16, 1, 16, false, 2>(A, X, ldx, dvec, ep, lp, st);
