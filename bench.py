@@ -254,14 +254,20 @@ def run_ours(args):
         # all-gathers run inside row groups on d/F-wide rows.  Default picked from the measured r01 sweep.
         F = args.feature_shards
         if F <= 0:
-            F = {2: 2, 4: 4, 8: 4}.get(world, 1)
+            F = {2: 2, 4: 4, 8: 8}.get(world, 1)
         while F > 1 and (world % F != 0 or d % F != 0 or (d // F) % 4 != 0 or d // F < 8):
             F //= 2
         if F == world:
-            trainer = FeatureShardedLightGCNTrainer(users, items, U, I, d=d, n_layers=K, lr=0.01, reg_weight=1e-4, seed=1234)
+            trainer = FeatureShardedLightGCNTrainer(users, items, U, I, d=d, n_layers=K, lr=0.01, reg_weight=1e-4, seed=1234,
+                                                    loss_layout=args.loss_layout)
             nnz, spmm_rows, spmm_d = trainer.local_nnz, n, trainer.dg
             parallelism = (f"feature-sharded over {world} GPUs: every rank owns d/G = {trainer.dg} columns of all [N, d] tables, "
-                           f"propagation / Adam without any collective, ONE NCCL all-reduce of E fp32 partial scores per step")
+                           f"propagation / Adam without any collective; ")
+            if args.loss_layout == "rows":
+                parallelism += ("loss on full-width rows of one user block per rank: item slices all-gathered, user slices "
+                                "all-to-all'ed, fused BPR on E/G triples, gradients returned by one reduce-scatter + one all-to-all")
+            else:
+                parallelism += "ONE NCCL all-reduce of E fp32 partial scores per step"
         else:
             trainer = ShardedLightGCNTrainer(users, items, U, I, d=d, n_layers=K, lr=0.01, reg_weight=1e-4, seed=1234,
                                              feature_shards=F)
@@ -428,6 +434,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", default=os.environ.get("GCF_BENCH_WORKLOAD", "cfg5"))
+    ap.add_argument("--loss-layout", choices=("rows", "scores"), default=os.environ.get("GCF_BENCH_LOSS_LAYOUT", "rows"),
+                    help="feature-sharded layout only: where the BPR loss is evaluated (see dist.FeatureShardedLightGCNTrainer)")
     ap.add_argument("--feature-shards", type=int, default=int(os.environ.get("GCF_BENCH_FEATURE_SHARDS", "0")),
                     help="N > 1 only: F feature shards x N/F row shards (1 = row-sharded, N = feature-sharded, 0 = measured default)")
     ap.add_argument("--no-e2e", action="store_true")

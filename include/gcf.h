@@ -181,6 +181,15 @@ int gcf_scatter_add_rows(const float* src, int64_t ld_src, int32_t d, const int6
                          float* table_grad, int64_t ld, int64_t n_table_rows, int32_t mode,
                          void* workspace, size_t workspace_bytes, gcf_stream_t stream);
 
+/* Layout conversion around the collectives of the feature-sharded multi-GPU trainers (the reference has
+ * no distributed code).  `blocked` = [n_slices][n_rows][w] fp32 -- what an all-gather / all-to-all of per-rank
+ * [n_rows, w] column slices delivers -- and `rows` = the row-major [n_rows, n_slices * w] table (leading dimension
+ * ld_rows) that the fused loss kernels gather from.  w % 4 == 0, 16-byte aligned buffers. */
+int gcf_slices_to_rows(const float* blocked, float* rows, int64_t ld_rows, int64_t n_rows, int32_t n_slices, int32_t w,
+                       gcf_stream_t stream);
+int gcf_rows_to_slices(const float* rows, int64_t ld_rows, float* blocked, int64_t n_rows, int32_t n_slices, int32_t w,
+                       gcf_stream_t stream);
+
 /* Philox4x32-10 counter-based negative sampler.  For triple t and negative slot j the
  * candidate stream is Philox(key=seed, counter=(t*n_negs+j, trial/4, offset_lo, offset_hi)),
  * candidate = mulhi32(word, n_items).  Without a positives CSR (pos_row_ptr == NULL) the

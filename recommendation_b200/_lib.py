@@ -66,6 +66,8 @@ _SIGNATURES = {
     "gcf_scatter_add_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
     "gcf_scatter_add_rows": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32,
                                        c_void_p, c_size_t, c_void_p]),
+    "gcf_slices_to_rows": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p]),
+    "gcf_rows_to_slices": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     "gcf_sample_negatives": (c_int32, [c_uint64, c_uint64, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p,
                                        c_int32, c_void_p, c_void_p]),
     "gcf_philox_keys": (c_int32, [c_int64, c_uint64, c_uint64, c_void_p, c_void_p]),

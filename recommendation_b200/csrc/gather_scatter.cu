@@ -182,3 +182,56 @@ extern "C" int gcf_scatter_add_rows(const float* src, int64_t ld_src, int32_t d,
   }
   return GCF_OK;
 }
+
+// ---- column-slice <-> row-major layout conversion around the collectives of the feature-sharded trainers ----
+// `blocked` is [n_slices][n_rows][w] (what an all-gather / all-to-all of per-rank [n_rows, w] column slices delivers),
+// `rows` is the row-major [n_rows, n_slices * w] table the fused loss kernels read.  One pass, 128-bit accesses on both
+// sides (w % 4 == 0), grid-stride over the float4 elements of the row-major side.
+namespace gcf {
+
+template <bool TO_ROWS>
+__global__ void __launch_bounds__(256)
+slices_rows_kernel(float4* __restrict__ blocked, float4* __restrict__ rows, long long ld4, long long n_rows, int n_slices,
+                   int w4) {
+  const long long d4 = (long long)n_slices * w4;
+  const long long total = n_rows * d4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / d4;
+    const int q = (int)(i - r * d4);
+    const int g = q / w4, qq = q - g * w4;
+    float4* b = blocked + ((long long)g * n_rows + r) * w4 + qq;
+    float4* x = rows + r * ld4 + q;
+    if (TO_ROWS) *x = __ldcs(b); else *b = __ldcs(x);
+  }
+}
+
+static int slices_rows(bool to_rows, const float* blocked, const float* rows, int64_t ld_rows, int64_t n_rows, int32_t n_slices,
+                       int32_t w, gcf_stream_t stream, const char* who) {
+  GCF_REQUIRE(blocked != nullptr && rows != nullptr, "%s: null pointer", who);
+  GCF_REQUIRE(n_rows >= 0 && n_slices >= 1 && w >= 4 && (w & 3) == 0, "%s: need n_slices >= 1 and w %% 4 == 0 (w=%d)", who, w);
+  GCF_REQUIRE(ld_rows >= (int64_t)n_slices * w && (ld_rows & 3) == 0, "%s: ld_rows too small or not a multiple of 4", who);
+  GCF_REQUIRE((reinterpret_cast<uintptr_t>(blocked) & 15u) == 0 && (reinterpret_cast<uintptr_t>(rows) & 15u) == 0,
+              "%s: buffers must be 16-byte aligned", who);
+  if (n_rows == 0) return GCF_OK;
+  const long long total = (long long)n_rows * n_slices * (w / 4);
+  const int blocks = (int)std::min<long long>(cdiv(total, 256), (long long)sm_count() * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float4* b4 = reinterpret_cast<float4*>(const_cast<float*>(blocked));
+  float4* r4 = reinterpret_cast<float4*>(const_cast<float*>(rows));
+  if (to_rows) slices_rows_kernel<true><<<blocks, 256, 0, st>>>(b4, r4, ld_rows / 4, n_rows, n_slices, w / 4);
+  else slices_rows_kernel<false><<<blocks, 256, 0, st>>>(b4, r4, ld_rows / 4, n_rows, n_slices, w / 4);
+  GCF_LAUNCH_CHECK("slices_rows_kernel");
+  return GCF_OK;
+}
+
+}  // namespace gcf
+
+extern "C" int gcf_slices_to_rows(const float* blocked, float* rows, int64_t ld_rows, int64_t n_rows, int32_t n_slices,
+                                  int32_t w, gcf_stream_t stream) {
+  return gcf::slices_rows(true, blocked, rows, ld_rows, n_rows, n_slices, w, stream, "gcf_slices_to_rows");
+}
+
+extern "C" int gcf_rows_to_slices(const float* rows, int64_t ld_rows, float* blocked, int64_t n_rows, int32_t n_slices,
+                                  int32_t w, gcf_stream_t stream) {
+  return gcf::slices_rows(false, blocked, rows, ld_rows, n_rows, n_slices, w, stream, "gcf_rows_to_slices");
+}

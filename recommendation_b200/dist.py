@@ -348,6 +348,47 @@ def feature_slice(d: int, world: int, rank: int) -> Tuple[int, int]:
     return rank * dg, (rank + 1) * dg
 
 
+@dataclass(frozen=True)
+class UserBlockPlan:
+    """Contiguous user blocks with balanced numbers of training triples (pure index arithmetic, CPU-testable).
+
+    The triples are kept user-major; rank r evaluates the loss on the triples of users [cuts[r], cuts[r+1]), i.e. on
+    positions [triple_cuts[r], triple_cuts[r+1]) of the sorted list.  Cuts fall on user boundaries, so a user's row and
+    its gradient live on exactly one rank."""
+
+    cuts: Tuple[int, ...]
+    triple_cuts: Tuple[int, ...]
+
+    @property
+    def world(self) -> int:
+        return len(self.cuts) - 1
+
+    def block(self, rank: int) -> Tuple[int, int]:
+        return self.cuts[rank], self.cuts[rank + 1]
+
+    def block_sizes(self) -> List[int]:
+        return [self.cuts[r + 1] - self.cuts[r] for r in range(self.world)]
+
+    def triple_range(self, rank: int) -> Tuple[int, int]:
+        return self.triple_cuts[rank], self.triple_cuts[rank + 1]
+
+    @staticmethod
+    def build(sorted_users: torch.Tensor, n_users: int, world: int) -> "UserBlockPlan":
+        """sorted_users: the user id of every triple, ascending (int64, any device)."""
+        e = int(sorted_users.numel())
+        cuts, tcuts = [0], [0]
+        for r in range(1, world):
+            if e == 0:
+                cuts.append(cuts[-1]); tcuts.append(0)
+                continue
+            u = int(sorted_users[min(r * e // world, e - 1)].item())   # the user that owns the ideal cut position ...
+            u = max(u, cuts[-1])
+            t = int(torch.searchsorted(sorted_users, torch.tensor([u], dtype=sorted_users.dtype, device=sorted_users.device))[0].item())
+            cuts.append(u); tcuts.append(t)                            # ... starts the next block with ALL its triples
+        cuts.append(n_users); tcuts.append(e)
+        return UserBlockPlan(tuple(cuts), tuple(tcuts))
+
+
 class FeatureShardedLightGCNTrainer:
     """The same full-batch step, parallelised over the embedding dimension.
 
@@ -364,13 +405,30 @@ class FeatureShardedLightGCNTrainer:
     Costs: the CSR (int32 structure + fp32 values, 1.6 GB at cfg 5) and the triple index arrays are replicated, every
     rank walks all nnz / all triples (with d/G-wide rows: 32 B at d = 64, G = 8), and the three row gathers of the loss
     are done twice (score pass, gradient pass).  Negatives are drawn with the same Philox (seed, step) on every rank.
+    That is loss_layout="scores".
+
+    loss_layout="rows" (default) keeps the propagation as above but evaluates the loss on FULL-width rows, each rank on
+    the triples of one contiguous user block (UserBlockPlan), with the single-GPU fused forward+backward BPR kernel:
+
+        item slices  [I, d/G]  --all-gather-->        [G, I, d/G]  --gcf_slices_to_rows--> item table [I, d]
+        user slices  [U, d/G]  --all-to-all(blocks)-> [G, Ub, d/G] --gcf_slices_to_rows--> my users   [Ub, d]
+        gcf_bpr_fwd_bwd on E/G triples (rows gathered once, gradients produced in the same pass)
+        item grads [I, d]  --gcf_rows_to_slices--> [G, I, d/G]  --reduce-scatter--> my columns of dL/d(final items)
+        user grads [Ub, d] --gcf_rows_to_slices--> [G, Ub, d/G] --all-to-all-->     my columns of dL/d(final users)
+
+    2 x (I + U/G) x d x 4 x (G-1)/G bytes cross the links per rank and step (2.8 GB at cfg 5, G = 8 -- against 7 x 3.4 GB
+    in the row-sharded layout) and every rank gathers 3 x E/G full rows once instead of 3 x E narrow rows twice: measured
+    one-rank cost of the loss part at d/G = 8 in the "scores" layout 17.9 ms of a 44.5 ms step (profiles/r01_exp_l2_window.md).
     """
 
     def __init__(self, users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int, *, d: int = 64,
                  n_layers: int = 3, lr: float = 0.01, reg_weight: float = 1e-4, seed: int = 0,
-                 init_table: Optional[torch.Tensor] = None):
+                 init_table: Optional[torch.Tensor] = None, loss_layout: str = "rows"):
         if not dist.is_initialized():
             raise RuntimeError("FeatureShardedLightGCNTrainer needs an initialised torch.distributed process group")
+        if loss_layout not in ("rows", "scores"):
+            raise ValueError("loss_layout must be 'rows' or 'scores'")
+        self.loss_layout = loss_layout
         if not users.is_cuda:
             raise RuntimeError("FeatureShardedLightGCNTrainer: tensors must be on the rank's CUDA device")
         self.lib = _lib.load()
@@ -398,7 +456,6 @@ class FeatureShardedLightGCNTrainer:
         self.order = torch.argsort(pos_u * n_items + pos_i) if self.n_triples > 1 else None  # user-major (see lightgcn.py)
         if self.order is not None:
             pos_u, pos_i = pos_u[self.order], pos_i[self.order]
-        self.pos_u, self.pos_i = pos_u.contiguous(), pos_i.contiguous()
         new = lambda: torch.empty(n, dg, device=dev)
         self.layers = [new() for _ in range(n_layers - 1)] + [None]
         self.final, self.g_final = new(), new()
@@ -406,31 +463,49 @@ class FeatureShardedLightGCNTrainer:
         self.ping = new() if n_layers > 1 else None
         self.pong = new() if n_layers > 1 else None
         self.exp_avg, self.exp_avg_sq = torch.zeros(n, dg, device=dev), torch.zeros(n, dg, device=dev)
-        self.neg = torch.empty(max(self.n_triples, 1), dtype=torch.int64, device=dev)
-        self.scores = torch.empty(max(self.n_triples, 1), dtype=torch.float32, device=dev)
-        self.coef = torch.empty(max(self.n_triples, 1), dtype=torch.float32, device=dev)
         self.loss_reg = torch.zeros((), dtype=torch.float32, device=dev)
         self.loss_pt = torch.zeros((), dtype=torch.float32, device=dev)
-        self.bpr_ws_bytes = self.lib.gcf_bpr_workspace_bytes(self.n_triples)
-        self.bpr_ws = torch.empty(self.bpr_ws_bytes, dtype=torch.uint8, device=dev)
         self.ws, self.ws_bytes = self.graph.workspace(dg)
         self.step_count = 0
-        # K fwd + K bwd SpMM (Adam fused into the last), sampler, score pass + reduce, coef + reduce, gradient pass
-        self.launches_per_step = 2 * n_layers + 6
-        self.collectives_per_step = 2  # E-float score all-reduce + scalar loss all-reduce
+        if loss_layout == "scores":
+            self.pos_u, self.pos_i = pos_u.contiguous(), pos_i.contiguous()
+            self.n_local = self.n_triples
+            self.neg = torch.empty(max(self.n_triples, 1), dtype=torch.int64, device=dev)
+            self.scores = torch.empty(max(self.n_triples, 1), dtype=torch.float32, device=dev)
+            self.coef = torch.empty(max(self.n_triples, 1), dtype=torch.float32, device=dev)
+            self.bpr_ws_bytes = self.lib.gcf_bpr_workspace_bytes(self.n_triples)
+            self.bpr_ws = torch.empty(self.bpr_ws_bytes, dtype=torch.uint8, device=dev)
+            # K fwd + K bwd SpMM (Adam fused into the last), sampler, score pass + reduce, coef + reduce, gradient pass
+            self.launches_per_step = 2 * n_layers + 6
+            self.collectives_per_step = 2  # E-float score all-reduce + scalar loss all-reduce
+        else:
+            G = self.world
+            self.blocks = UserBlockPlan.build(pos_u, n_users, G)
+            self.block_rows = self.blocks.block_sizes()
+            u_lo, u_hi = self.blocks.block(self.rank)
+            t_lo, t_hi = self.blocks.triple_range(self.rank)
+            self.t_lo, self.t_hi, self.ub = t_lo, t_hi, u_hi - u_lo
+            self.n_local = t_hi - t_lo
+            self.loc_u = (pos_u[t_lo:t_hi] - u_lo).contiguous()       # row inside my user block
+            self.loc_i = pos_i[t_lo:t_hi].contiguous()
+            del pos_u, pos_i
+            ub = self.ub
+            self.item_blk = torch.empty(G, n_items, dg, device=dev)    # all-gather target / reduce-scatter source
+            self.item_full = torch.empty(n_items, d, device=dev)
+            self.g_item_full = torch.empty(n_items, d, device=dev)
+            self.user_blk = torch.empty(G * ub, dg, device=dev)        # [G, Ub, d/G]: all-to-all target / source
+            self.user_full = torch.empty(ub, d, device=dev)
+            self.g_user_full = torch.empty(ub, d, device=dev)
+            self.neg = torch.empty(max(self.n_local, 1), dtype=torch.int64, device=dev)
+            self.bpr_ws_bytes = self.lib.gcf_bpr_workspace_bytes(self.n_local)
+            self.bpr_ws = torch.empty(self.bpr_ws_bytes, dtype=torch.uint8, device=dev)
+            # K fwd + K bwd SpMM (Adam fused into the last), sampler, 2 + 2 layout conversions, fused BPR + its reduction
+            self.launches_per_step = 2 * n_layers + 7
+            self.collectives_per_step = 5  # item all-gather, user all-to-all, item reduce-scatter, user all-to-all, loss all-reduce
 
-    def step(self, neg_items: Optional[torch.Tensor] = None, marks: Optional[list] = None) -> torch.Tensor:
-        """One optimisation step; returns the (global) loss.  neg_items: optional pre-drawn item ids for ALL triples in
-        their original order (parity tests), identical on every rank."""
-        lib, st, g, dg, K, u = self.lib, _lib.current_stream(), self.graph, self.dg, self.k, self.n_users
-        self.step_count += 1
-        if marks is not None:
-            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
-            e0.record()
-        _lib.check(lib.gcf_propagate_fwd(g.struct_ref(), dg, K, _lib.ptr(self.table), _lib.ptr_array(self.layers),
-                                         _lib.ptr(self.final), 1.0, _lib.ptr(self.ws), self.ws_bytes, st), "gcf_propagate_fwd")
-        if marks is not None:
-            e1.record()
+    def _loss_on_scores(self, neg_items: Optional[torch.Tensor]) -> torch.Tensor:
+        """loss_layout="scores": partial scores on the local columns, one all-reduce of E floats, local gradient pass."""
+        lib, st, dg, u = self.lib, _lib.current_stream(), self.dg, self.n_users
         if neg_items is None:
             _lib.check(lib.gcf_sample_negatives(self.seed, self.step_count, None, self.n_triples, 1, self.n_items, None, None, 1,
                                                 _lib.ptr(self.neg), st), "gcf_sample_negatives")
@@ -455,6 +530,75 @@ class FeatureShardedLightGCNTrainer:
         self.g_final.zero_()
         _lib.check(lib.gcf_bpr_bwd(*args, _lib.ptr(self.coef), None, self.reg, self.reg, 0.0, _lib.ptr(self.g_final[:u]), dg,
                                    _lib.ptr(self.g_final[u:]), dg, st), "gcf_bpr_bwd")
+        return self.loss_pt / self.world + self.loss_reg   # the pointwise part is replicated: count it once over the ranks
+
+    def _loss_on_rows(self, neg_items: Optional[torch.Tensor]) -> torch.Tensor:
+        """loss_layout="rows": exchange column slices for full rows, fused BPR on this rank's user block, gradients back
+        to column slices.  Fills self.g_final ([N, d/G]); returns this rank's share of the global loss."""
+        lib, st, dg, d, G, u, ub = self.lib, _lib.current_stream(), self.dg, self.d_full, self.world, self.n_users, self.ub
+        fin_u, fin_i = self.final[:u], self.final[u:]
+        # both exchanges are queued on NCCL's stream; the sampler and the gradient memsets below run meanwhile
+        w_items = dist.all_gather_into_tensor(self.item_blk.view(-1), fin_i.reshape(-1), async_op=True)
+        w_users = dist.all_to_all_single(self.user_blk, fin_u, output_split_sizes=[ub] * G, input_split_sizes=self.block_rows,
+                                         async_op=True)
+        if neg_items is None:
+            # one Philox stream per (seed, rank, step): rank in the high word of `offset`, step in the low word
+            if self.n_local > 0:
+                _lib.check(lib.gcf_sample_negatives(self.seed, (self.rank << 32) | self.step_count, None, self.n_local, 1,
+                                                    self.n_items, None, None, 1, _lib.ptr(self.neg), st), "gcf_sample_negatives")
+            neg = self.neg
+        else:
+            neg = neg_items.to(torch.int64).reshape(-1)
+            if self.order is not None:
+                neg = neg[self.order]
+            neg = neg[self.t_lo:self.t_hi].contiguous()
+        self.g_item_full.zero_()
+        self.g_user_full.zero_()
+        self.loss_pt.zero_()
+        w_items.wait()
+        _lib.check(lib.gcf_slices_to_rows(_lib.ptr(self.item_blk), _lib.ptr(self.item_full), d, self.n_items, G, dg, st),
+                   "gcf_slices_to_rows")
+        w_users.wait()
+        if ub > 0:
+            _lib.check(lib.gcf_slices_to_rows(_lib.ptr(self.user_blk), _lib.ptr(self.user_full), d, ub, G, dg, st),
+                       "gcf_slices_to_rows")
+        w = 1.0 / max(self.n_triples, 1)
+        if self.n_local > 0:
+            # per-rank partial of the global mean: reduction = sum, loss and gradients scaled by 1/E (as in the row layout)
+            _lib.check(lib.gcf_bpr_fwd_bwd(_lib.ptr(self.user_full), d, _lib.ptr(self.item_full), d, d, _lib.ptr(self.loc_u),
+                                           _lib.ptr(self.loc_i), _lib.ptr(neg), self.n_local, 1, _lib.BPR_SOFTPLUS, 0.0,
+                                           _lib.REDUCE_SUM, self.reg / w, self.reg / w, 0.0, w, _lib.ptr(self.loss_pt), None,
+                                           _lib.ptr(self.g_user_full), d, _lib.ptr(self.g_item_full), d,
+                                           _lib.ptr(self.bpr_ws), self.bpr_ws_bytes, st), "gcf_bpr_fwd_bwd")
+        _lib.check(lib.gcf_rows_to_slices(_lib.ptr(self.g_item_full), d, _lib.ptr(self.item_blk), self.n_items, G, dg, st),
+                   "gcf_rows_to_slices")
+        w_items = dist.reduce_scatter_tensor(self.g_final[u:].reshape(-1), self.item_blk.view(-1), op=dist.ReduceOp.SUM,
+                                             async_op=True)
+        if ub > 0:   # converted while the reduce-scatter is on the wire
+            _lib.check(lib.gcf_rows_to_slices(_lib.ptr(self.g_user_full), d, _lib.ptr(self.user_blk), ub, G, dg, st),
+                       "gcf_rows_to_slices")
+        w_users = dist.all_to_all_single(self.g_final[:u], self.user_blk, output_split_sizes=self.block_rows,
+                                         input_split_sizes=[ub] * G, async_op=True)
+        w_items.wait()
+        w_users.wait()
+        return self.loss_pt * w
+
+    def step(self, neg_items: Optional[torch.Tensor] = None, marks: Optional[list] = None) -> torch.Tensor:
+        """One optimisation step; returns the (global) loss.  neg_items: optional pre-drawn item ids for ALL triples in
+        their original order (parity tests), identical on every rank."""
+        lib, st, g, dg, K, u = self.lib, _lib.current_stream(), self.graph, self.dg, self.k, self.n_users
+        self.step_count += 1
+        if marks is not None:
+            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            e0.record()
+        _lib.check(lib.gcf_propagate_fwd(g.struct_ref(), dg, K, _lib.ptr(self.table), _lib.ptr_array(self.layers),
+                                         _lib.ptr(self.final), 1.0, _lib.ptr(self.ws), self.ws_bytes, st), "gcf_propagate_fwd")
+        if marks is not None:
+            e1.record()
+        if self.loss_layout == "rows":
+            loss_local = self._loss_on_rows(neg_items)
+        else:
+            loss_local = self._loss_on_scores(neg_items)
         if marks is not None:
             e2.record()
         # the Adam update of the local [N, d/G] slice rides in the epilogue of the last backward SpMM
@@ -466,9 +610,9 @@ class FeatureShardedLightGCNTrainer:
             e3.record()
             marks.append((e0, e1, K))
             marks.append((e2, e3, K))
-        reg = self.loss_reg.clone()
-        dist.all_reduce(reg, op=dist.ReduceOp.SUM)
-        return self.loss_pt + reg
+        loss = loss_local.clone()
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM)   # every rank holds 1/G of the global value ("scores") or its block's share ("rows")
+        return loss
 
     def gathered_table(self) -> torch.Tensor:
         """[N, d] table on every rank (for checks / evaluation)."""

@@ -243,7 +243,7 @@ def test_feature_slices_and_score_allreduce_gloo_world2():
     np.testing.assert_allclose(got, float(want), rtol=1e-10)
 
 
-def _nccl_feature_worker(rank, world, port, n_users, n_items, users, items, table0, negs, k, out_q):
+def _nccl_feature_worker(rank, world, port, n_users, n_items, users, items, table0, negs, k, out_q, loss_layout="rows"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -253,7 +253,7 @@ def _nccl_feature_worker(rank, world, port, n_users, n_items, users, items, tabl
 
         users_t, items_t = torch.from_numpy(users).to(dev), torch.from_numpy(items).to(dev)
         tr = FeatureShardedLightGCNTrainer(users_t, items_t, n_users, n_items, d=table0.shape[1], n_layers=k, lr=0.01,
-                                           reg_weight=1e-4, init_table=torch.from_numpy(table0))
+                                           reg_weight=1e-4, init_table=torch.from_numpy(table0), loss_layout=loss_layout)
         losses = [float(tr.step(neg_items=torch.from_numpy(negs[s]).to(dev)).item()) for s in range(negs.shape[0])]
         table = tr.gathered_table().cpu().numpy()
         if rank == 0:
@@ -263,7 +263,8 @@ def _nccl_feature_worker(rank, world, port, n_users, n_items, users, items, tabl
 
 
 @pytest.mark.gpu
-def test_feature_sharded_trainer_matches_single_gpu():
+@pytest.mark.parametrize("loss_layout", ["rows", "scores"])
+def test_feature_sharded_trainer_matches_single_gpu(loss_layout):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 CUDA devices")
     from recommendation_b200.graph import CSRGraph
@@ -284,8 +285,8 @@ def test_feature_sharded_trainer_matches_single_gpu():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_feature_worker, args=(r, world, port, U, I, inter.users, inter.items, table0, negs, k, q))
-             for r in range(world)]
+    procs = [ctx.Process(target=_nccl_feature_worker, args=(r, world, port, U, I, inter.users, inter.items, table0, negs, k, q,
+                                                            loss_layout)) for r in range(world)]
     for p in procs:
         p.start()
     got_losses, got_table = q.get(timeout=300)
@@ -294,3 +295,93 @@ def test_feature_sharded_trainer_matches_single_gpu():
         assert p.exitcode == 0
     np.testing.assert_allclose(got_losses, want_losses, rtol=1e-4)
     _tables_close(got_table, ref.table.cpu().numpy())
+
+
+# ---------------------------------------------------------------------------------------------- rows-layout loss
+def test_user_block_plan():
+    from recommendation_b200.dist import UserBlockPlan
+
+    users = torch.tensor([0, 0, 0, 1, 2, 2, 5, 5, 5, 5, 7, 9], dtype=torch.int64)
+    plan = UserBlockPlan.build(users, 10, 3)
+    assert plan.cuts[0] == 0 and plan.cuts[-1] == 10 and plan.triple_cuts[0] == 0 and plan.triple_cuts[-1] == 12
+    assert list(plan.cuts) == sorted(plan.cuts) and list(plan.triple_cuts) == sorted(plan.triple_cuts)
+    for r in range(3):                      # every triple of a block's users, and only those, is in the block's range
+        (u0, u1), (t0, t1) = plan.block(r), plan.triple_range(r)
+        inside = (users >= u0) & (users < u1)
+        assert torch.equal(torch.nonzero(inside).flatten(), torch.arange(t0, t1))
+    assert sum(plan.block_sizes()) == 10
+    # one hub owning most triples: blocks may be empty but still partition users and triples
+    hub = torch.tensor([3] * 50 + [4, 6], dtype=torch.int64)
+    p2 = UserBlockPlan.build(hub, 8, 4)
+    assert p2.cuts[0] == 0 and p2.cuts[-1] == 8 and sum(p2.block_sizes()) == 8
+    assert sum(t1 - t0 for t0, t1 in (p2.triple_range(r) for r in range(4))) == 52
+    empty = UserBlockPlan.build(torch.empty(0, dtype=torch.int64), 5, 2)
+    assert empty.block_sizes() == [0, 5] and empty.triple_range(0) == (0, 0)
+
+
+def _rows_loss_gloo_worker(rank, world, port, n_users, n_items, users, items, negs, x, reg, out_q):
+    """The collective choreography of FeatureShardedLightGCNTrainer._loss_on_rows on gloo; torch permutes stand in for
+    gcf_slices_to_rows / gcf_rows_to_slices and fp64 autograd for the fused BPR kernel."""
+    from recommendation_b200.dist import UserBlockPlan, feature_slice
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        G, d = world, x.shape[1]
+        lo, hi = feature_slice(d, G, rank)
+        dg = hi - lo
+        final = torch.from_numpy(x[:, lo:hi]).double().contiguous()           # this rank's column slice of all rows
+        order = np.argsort(users * n_items + items, kind="stable")
+        su, si, sn = (torch.from_numpy(a[order]) for a in (users, items, negs))
+        plan = UserBlockPlan.build(su, n_users, G)
+        rows = plan.block_sizes()
+        (u0, u1), (t0, t1) = plan.block(rank), plan.triple_range(rank)
+        ub = u1 - u0
+        item_blk = torch.empty(G * n_items * dg, dtype=torch.float64)
+        dist.all_gather_into_tensor(item_blk, final[n_users:].reshape(-1))
+        user_blk = torch.empty(G * ub, dg, dtype=torch.float64)
+        dist.all_to_all_single(user_blk, final[:n_users].contiguous(), output_split_sizes=[ub] * G, input_split_sizes=rows)
+        to_rows = lambda blk, n: blk.view(G, n, dg).permute(1, 0, 2).reshape(n, d)
+        to_slices = lambda r, n: r.view(n, G, dg).permute(1, 0, 2).contiguous()
+        item_full = to_rows(item_blk, n_items).clone().requires_grad_(True)
+        user_full = to_rows(user_blk, ub).clone().requires_grad_(True)
+        e = users.shape[0]
+        u, p, n = user_full[su[t0:t1] - u0], item_full[si[t0:t1]], item_full[sn[t0:t1]]
+        loss = torch.nn.functional.softplus(-(u * (p - n)).sum(1)).sum() / e + reg * (u.pow(2).sum() + p.pow(2).sum())
+        loss.backward()
+        g_final = torch.empty_like(final)
+        dist.reduce_scatter_tensor(g_final[n_users:].reshape(-1), to_slices(item_full.grad, n_items).reshape(-1))
+        dist.all_to_all_single(g_final[:n_users], to_slices(user_full.grad, ub).reshape(G * ub, dg), output_split_sizes=rows,
+                               input_split_sizes=[ub] * G)
+        total = loss.detach().clone()
+        dist.all_reduce(total)
+        parts = [torch.empty_like(g_final) for _ in range(G)]
+        dist.all_gather(parts, g_final)
+        if rank == 0:
+            out_q.put((float(total), torch.cat(parts, dim=1).numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rows_layout_loss_exchange_gloo_world2():
+    from oracle import losses_ref
+
+    rng = np.random.default_rng(5)
+    U, I, E, d, reg = 40, 60, 700, 16, 1e-3
+    users, items, negs = rng.integers(0, U, E), rng.integers(0, I, E), rng.integers(0, I, E)
+    x = (rng.standard_normal((U + I, d)) * 0.3).astype(np.float32)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rows_loss_gloo_worker, args=(r, 2, port, U, I, users, items, negs, x, reg, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got_loss, got_grad = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    want = losses_ref.bpr_lightgcn(xt[:U], xt[U:], torch.from_numpy(users), torch.from_numpy(items), torch.from_numpy(negs), reg)
+    want.backward()
+    np.testing.assert_allclose(got_loss, float(want), rtol=1e-10)
+    np.testing.assert_allclose(got_grad, xt.grad.numpy(), rtol=1e-9, atol=1e-12)

@@ -146,6 +146,22 @@ def test_spmm_variants_agree(cuda, d, variant):
     assert torch.equal(y0, y1)  # same summation order in every variant
 
 
+@pytest.mark.parametrize("shape", [(1000, 8, 8), (777, 4, 16), (5, 2, 32), (300, 1, 64), (64, 8, 4)])
+def test_slices_rows_layout_conversion(cuda, shape):
+    """gcf_slices_to_rows / gcf_rows_to_slices: [G][n][w] column slices <-> row-major [n, G*w] (pure data movement: bit-exact)."""
+    n, G, w = shape
+    lib, st = _lib.load(), _lib.current_stream()
+    blocked = torch.randn(G, n, w, device=cuda)
+    rows = torch.full((n, G * w + 4), -7.0, device=cuda)            # leading dimension larger than the row
+    _lib.check(lib.gcf_slices_to_rows(_lib.ptr(blocked), _lib.ptr(rows), rows.stride(0), n, G, w, st), "gcf_slices_to_rows")
+    want = blocked.permute(1, 0, 2).reshape(n, G * w)
+    assert torch.equal(rows[:, : G * w], want) and bool((rows[:, G * w:] == -7.0).all())
+    back = torch.empty_like(blocked)
+    _lib.check(lib.gcf_rows_to_slices(_lib.ptr(rows), rows.stride(0), _lib.ptr(back), n, G, w, st), "gcf_rows_to_slices")
+    assert torch.equal(back, blocked)
+    assert lib.gcf_slices_to_rows(_lib.ptr(blocked), _lib.ptr(rows), 4, n, G, w, st) != 0   # ld too small is rejected
+
+
 def test_spmm_epilogues(cuda):
     rng = np.random.default_rng(2)
     n, d = 600, 64
