@@ -317,6 +317,32 @@ int gcf_directau_bwd(const float* x, int64_t ldx, const float* y, int64_t ldy, i
                      const float* out3, const float* w3, float* gx, int64_t ldgx, float* gy, int64_t ldgy,
                      void* workspace, size_t workspace_bytes, gcf_stream_t stream);
 
+/* ---- sparse x sparse products for the motif-induced adjacency matrices ----------------------
+ * univariate/mhcn.py:340-368 (build_hyper_adj_mats): sixteen (P.dot(Q)).multiply(M) terms plus Y.dot(Y.T), evaluated
+ * by scipy on the host in the reference.  All operands are canonical CSR (rows sorted, columns ascending, int32 indices).
+ * The long-row schedule fields of gcf_csr_t are ignored here. */
+
+/* out[e] = X[i_e, j_e] for every stored entry e = (i_e, j_e) of the pattern P, 0 where X stores nothing.
+ * With it: S.multiply(S.T) = S.vals * sample(S^T, S); S - B on S's pattern; alignment of two matrices on one pattern. */
+int gcf_csr_sample(const gcf_csr_t* X, const gcf_csr_t* P, float* out, gcf_stream_t stream);
+
+/* (A . B).multiply(M) on M's pattern without forming A . B:
+ *   out[e] = M.vals[e] * sum_k A[i_e, k] * B[k, j_e],   B given by the CSR of its transpose (Bt: row j = column j of B).
+ * A: [m, K], Bt: [n, K], mask: [m, n]; out: float[mask.nnz]. */
+int gcf_spgemm_masked(const gcf_csr_t* A, const gcf_csr_t* Bt, const gcf_csr_t* mask, float* out, gcf_stream_t stream);
+
+/* Full product C = A . B by expand-sort-compress, over the stored entries [entry_begin, entry_end) of A (cut at row
+ * boundaries by the caller to bound memory):
+ *   gcf_spgemm_count   *n_products (device int64) = number of scalar products; their offsets stay in the workspace;
+ *   gcf_spgemm_expand  writes them as COO (row of A, column of B, a * b) in emission order -- requires
+ *                      *n_products < 2^32 (split the range otherwise); feed the COO to gcf_coo_to_csr_stable, which
+ *                      sums duplicates in that order (scipy's Y.dot(Y.T) up to fp32 summation order; exact for integer data). */
+size_t gcf_spgemm_workspace_bytes(int64_t n_entries);
+int gcf_spgemm_count(const gcf_csr_t* A, const gcf_csr_t* B, int64_t entry_begin, int64_t entry_end, int64_t* n_products,
+                     void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+int gcf_spgemm_expand(const gcf_csr_t* A, const gcf_csr_t* B, int64_t entry_begin, int64_t entry_end, int64_t* rows_out,
+                      int64_t* cols_out, float* vals_out, void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+
 /* ---- batched evaluation ---------------------------------------------------
  *
  * scores [n_queries, n_items] fp32 (ld elements per row) is the dense score block user_emb[q] . item_emb^T -- a plain

@@ -92,6 +92,12 @@ _SIGNATURES = {
     "gcf_infonce_bwd": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32, c_float,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "gcf_csr_sample": (c_int32, [POINTER(CsrStruct), POINTER(CsrStruct), c_void_p, c_void_p]),
+    "gcf_spgemm_masked": (c_int32, [POINTER(CsrStruct), POINTER(CsrStruct), POINTER(CsrStruct), c_void_p, c_void_p]),
+    "gcf_spgemm_workspace_bytes": (c_size_t, [c_int64]),
+    "gcf_spgemm_count": (c_int32, [POINTER(CsrStruct), POINTER(CsrStruct), c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gcf_spgemm_expand": (c_int32, [POINTER(CsrStruct), POINTER(CsrStruct), c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_size_t, c_void_p]),
     "gcf_masked_topn": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_void_p,
                                   c_void_p, c_void_p]),
     "gcf_ranking_hits": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,

@@ -503,3 +503,70 @@ def test_ncl_training_iteration_runs_and_learns(cuda):
             first = parts["rec"].item() if first is None else first
             last = parts["rec"].item()
     assert last < first            # the ranking loss goes down
+
+
+# ------------------------------------------------------------------------------------------ MHCN motif matrices (8f row 4)
+def _rand_sparse(rng, n_rows, n_cols, nnz, integer=True):
+    r, c = rng.integers(0, n_rows, nnz), rng.integers(0, n_cols, nnz)
+    v = rng.integers(1, 4, nnz).astype(np.float32) if integer else rng.standard_normal(nnz).astype(np.float32)
+    m = sp.coo_matrix((v, (r, c)), shape=(n_rows, n_cols)).tocsr()
+    m.sum_duplicates(); m.sort_indices()
+    return m
+
+
+def _to_scipy(g):
+    m = sp.csr_matrix((g.vals.cpu().numpy(), g.col_idx.cpu().numpy(), g.row_ptr.cpu().numpy()), shape=(g.n_rows, g.n_cols))
+    m.sort_indices()
+    return m
+
+
+@pytest.mark.parametrize("shape", [(60, 45, 70, 400), (500, 300, 400, 9000), (7, 5, 9, 0)])
+def test_sparse_product_kernels_vs_scipy(cuda, shape):
+    """gcf_csr_sample, gcf_spgemm_masked and the expand-sort-compress product against scipy (integer-valued operands:
+    bit-exact values, identical patterns; rectangular shapes, empty rows, an empty operand)."""
+    from recommendation_b200 import motifs
+
+    m, k, n, nnz = shape
+    rng = np.random.default_rng(m)
+    A, B, M = _rand_sparse(rng, m, k, nnz), _rand_sparse(rng, k, n, nnz), _rand_sparse(rng, m, n, nnz)
+    gA, gB, gM = (CSRGraph.from_scipy(x, device=cuda) for x in (A, B, M))
+    # masked product on M's pattern
+    got = motifs.masked_product(gA, gB.transpose(), gM).cpu().numpy()
+    want = np.asarray((A @ B).multiply(M).todense())
+    dense = np.zeros((m, n), np.float32)
+    rows = motifs.entry_rows(gM).cpu().numpy()
+    dense[rows, gM.col_idx.cpu().numpy()] = got
+    assert np.array_equal(dense, want)
+    # sampling one matrix at another's pattern
+    X = _rand_sparse(rng, m, n, nnz)
+    s = motifs.csr_sample(CSRGraph.from_scipy(X, device=cuda), gM).cpu().numpy()
+    assert np.array_equal(s, np.asarray(X.todense())[rows, gM.col_idx.cpu().numpy()])
+    # full product, whole and in forced row blocks (budget = the largest single row, so every split is at a row boundary)
+    W = (A @ B).tocsr(); W.sort_indices()
+    per_row = np.asarray((A != 0).astype(np.int64) @ np.diff(B.indptr).astype(np.int64)).ravel() if nnz else np.zeros(1, np.int64)
+    for max_products in (1 << 27, int(per_row.max()) + 5):
+        C = _to_scipy(motifs.spgemm(gA, gB, max_products=max_products))
+        assert np.array_equal(C.indptr, W.indptr) and np.array_equal(C.indices, W.indices) and np.array_equal(C.data, W.data)
+    if per_row.max() > 1:   # a single row above the budget is reported, not truncated
+        with pytest.raises(RuntimeError, match="max_products"):
+            motifs.spgemm(gA, gB, max_products=1)
+
+
+def test_hyper_adj_mats_match_reference_fixture(cuda, golden):
+    """motifs.build_hyper_adj_mats on the GPU against the reference's own build_hyper_adj_mats (mhcn.py:340-368) on the same
+    S / Y: identical sparsity patterns, values within 2 ulp; and the matrices drive MHCNModel."""
+    from recommendation_b200 import motifs, social
+
+    z = golden("mhcn_motifs")
+    S, Y = _csr(z, "S"), _csr(z, "Y")
+    got = motifs.build_hyper_adj_mats(CSRGraph.from_scipy(S, device=cuda), CSRGraph.from_scipy(Y, device=cuda))
+    for g, name in zip(got, ("Hs", "Hj", "Hp")):
+        want = _csr(z, name); want.eliminate_zeros(); want.sort_indices()
+        h = _to_scipy(g)
+        assert h.nnz == want.nnz > 0, name
+        assert np.array_equal(h.indptr, want.indptr) and np.array_equal(h.indices, want.indices), name   # bit-exact structure
+        np.testing.assert_allclose(h.data, want.data, rtol=3e-7, atol=0)
+    R = CSRGraph.from_scipy(Y, norm="row", device=cuda)
+    model = social.MHCNModel(S.shape[0], Y.shape[1], 16, 2, 0.01, got[0], got[1], got[2], R)
+    out = model([0, 1, 2, 3], [0, 1, 2, 3], [4, 5, 6, 7])
+    assert all(torch.isfinite(o).all() for o in out)

@@ -307,3 +307,36 @@ def test_buir_nb_matches_reference(golden):
     _check(loss, (ou, oi, W, b), z["loss"], (z["g_user"], z["g_item"], z["g_pred_w"], z["g_pred_b"]), rtol=1e-4)
     t1 = z["target_user0"].copy(); t1[z["users"]] = z["target_user0"][z["users"]] * mom + z["online_user"][z["users"]] * (1 - mom)
     np.testing.assert_allclose(t1, z["target_user1"], rtol=1e-6, atol=1e-7)
+
+
+def _golden_csr(z, prefix):
+    import scipy.sparse as sp
+
+    shape = tuple(int(x) for x in z[f"{prefix}_shape"])
+    m = sp.csr_matrix((z[f"{prefix}_data"], z[f"{prefix}_indices"], z[f"{prefix}_indptr"]), shape=shape)
+    m.sort_indices()
+    return m
+
+
+def test_motif_oracle_matches_reference_fixture(golden):
+    """oracle/motif_ref.py against the reference's own MHCN.build_hyper_adj_mats (mhcn.py:340-368) run on the same S / Y
+    (tests/golden/make_golden_motifs.py): identical sparsity pattern, values within 1 ulp."""
+    from oracle import motif_ref
+
+    z = golden("mhcn_motifs")
+    S, Y = _golden_csr(z, "S"), _golden_csr(z, "Y")
+    got = motif_ref.build_hyper_adj_mats(S, Y)
+    for h, name in zip(got, ("Hs", "Hj", "Hp")):
+        want = _golden_csr(z, name)
+        want.eliminate_zeros()
+        h.sort_indices()
+        assert h.nnz == want.nnz > 0, name
+        assert np.array_equal(h.indptr, want.indptr) and np.array_equal(h.indices, want.indices), name
+        np.testing.assert_allclose(h.data, want.data, rtol=2e-7, atol=0)
+    # the terms themselves: counts are non-negative integers, A1..A5, A8..A10 symmetric
+    terms, B, U = motif_ref.motif_terms(S, Y)
+    assert (B != B.T).nnz == 0 and B.multiply(U).nnz == 0
+    for k, a in terms.items():
+        assert np.all(a.data == np.round(a.data)) and np.all(a.data >= 0), k
+        if k not in ("A6", "A7"):
+            assert (a != a.T).nnz == 0, k
