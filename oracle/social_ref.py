@@ -2,7 +2,8 @@
 
   mhcn_forward     univariate/mhcn.py:404-505 (self_gating, channel_attention, forward, hierarchical_self_supervision)
   diffnet_forward  univariate/diffnet.py:1124-1132
-Pinned against tests/golden/{mhcn_model,diffnet_model}.npz, which the reference's own classes produced.
+  sept_social_views / sept_social_iteration   univariate/sept_social.py:361-420 and the loop body of 431-461
+Pinned against tests/golden/{mhcn_model,diffnet_model,sept_social}.npz, which the reference's own classes produced.
 """
 from __future__ import annotations
 
@@ -59,3 +60,64 @@ def diffnet_forward(user_w, item_w, weights, S, A):
     for w in weights:
         user = torch.relu(torch.cat([S @ user, user], dim=1) @ w)
     return user + A @ item_w
+
+
+# ------------------------------------------------------------------------------------------ sept_social.py
+def sept_social_views(S, Y):
+    """[social_matrix, sharing_matrix] of sept_social.py:361-368 (scipy): (S.S) o S + I and (Y.Y^T) o S + I, each
+    normalised with D^-1/2 . D^-1/2 on its ROW sums (normalize_graph_mat, sept_social.py:86-101)."""
+    import numpy as np
+    import scipy.sparse as sp
+
+    def sym_norm(m):
+        m = sp.csr_matrix(m, dtype=np.float32)
+        rs = np.asarray(m.sum(1), dtype=np.float32).ravel()
+        with np.errstate(divide="ignore"):
+            dinv = np.power(rs, -0.5).astype(np.float32)
+        dinv[np.isinf(dinv)] = 0.0
+        return sp.diags(dinv).dot(m).dot(sp.diags(dinv)).tocsr().astype(np.float32)
+
+    S = sp.csr_matrix(S, dtype=np.float32)
+    Y = sp.csr_matrix(Y, dtype=np.float32)
+    eye = sp.eye(S.shape[0], dtype=np.float32)
+    return [sym_norm((S @ S).multiply(S) + eye), sym_norm((Y @ Y.T).multiply(S) + eye)]
+
+
+def _sept_layers_sum(emb, adj, n_layers):
+    """sept_social.py:370-385: the normalised layer output is what the next layer propagates."""
+    out = [emb]
+    for _ in range(n_layers):
+        emb = F.normalize(adj @ emb)
+        out.append(emb)
+    return torch.stack(out, 0).sum(0)
+
+
+def sept_social_iteration(user_w, item_w, adj, social, sharing, n_layers, ss_rate, ins_cnt, reg, u_idx, p_idx, n_idx, labels=None):
+    """One iteration of sept_social.py:431-461 with aug_mat = norm_adj (dense fp64 operators).  labels: optional (f_pos, sh_pos,
+    r_pos) to use instead of the top-K of this run.  Returns a dict of every intermediate the fixture stores."""
+    nu = user_w.shape[0]
+    ego = torch.cat([user_w, item_w], 0)
+    rec = _sept_layers_sum(ego, adj, n_layers)
+    rec_u, rec_i = rec[:nu], rec[nu:]
+    aug_u = rec_u
+    sharing_v, friend_v = _sept_layers_sum(user_w, sharing, n_layers), _sept_layers_sum(user_w, social, n_layers)
+    x = (rec_u[u_idx] * rec_i[p_idx]).sum(1) - (rec_u[u_idx] * rec_i[n_idx]).sum(1)
+    rec_loss = -F.logsigmoid(x).mean() + reg * (user_w.norm(2).pow(2) + item_w.norm(2).pow(2))
+    uniq = torch.unique(u_idx)
+
+    def predict(emb):                                       # label_prediction, :394-399
+        return F.softmax(F.normalize(emb[uniq]) @ F.normalize(aug_u[uniq]).T, dim=1)
+
+    def discriminate(positive, emb):                        # neighbor_discrimination, :408-420
+        e, a = F.normalize(emb[uniq]), F.normalize(aug_u[uniq])
+        pos = (e.unsqueeze(1) * a[positive]).sum(2)
+        return -torch.sum(torch.log(torch.exp(pos / 0.1).sum(1) / torch.exp(e @ a.T / 0.1).sum(1)))
+
+    soc_p, sha_p, rec_p = predict(friend_v), predict(sharing_v), predict(rec_u)
+    topk = lambda a, b: torch.topk((a + b) / 2, ins_cnt, dim=1).indices   # generate_pesudo_labels, :401-406
+    f_pos, sh_pos, r_pos = labels if labels is not None else (topk(sha_p, rec_p), topk(soc_p, rec_p), topk(soc_p, sha_p))
+    nd_f, nd_s, nd_r = discriminate(f_pos, friend_v), discriminate(sh_pos, sharing_v), discriminate(r_pos, rec_u)
+    total = rec_loss + ss_rate * (nd_f + nd_s + nd_r)
+    return dict(rec_user=rec_u, rec_item=rec_i, sharing_view=sharing_v, friend_view=friend_v, rec_loss=rec_loss,
+                social_prediction=soc_p, sharing_prediction=sha_p, rec_prediction=rec_p, f_pos=f_pos, sh_pos=sh_pos, r_pos=r_pos,
+                nd_f=nd_f, nd_s=nd_s, nd_r=nd_r, total=total)

@@ -570,3 +570,49 @@ def test_hyper_adj_mats_match_reference_fixture(cuda, golden):
     model = social.MHCNModel(S.shape[0], Y.shape[1], 16, 2, 0.01, got[0], got[1], got[2], R)
     out = model([0, 1, 2, 3], [0, 1, 2, 3], [4, 5, 6, 7])
     assert all(torch.isfinite(o).all() for o in out)
+
+
+# ------------------------------------------------------------------------------------------ sept_social.py (8f row 3)
+def test_sept_social_fixture(cuda, golden):
+    """SEPTSocial against the reference's own SEPT (sept_social.py) on the same parameters / batch: view matrices (identical
+    pattern), encoder outputs, predictions, pseudo-labels, losses and parameter gradients."""
+    from recommendation_b200 import sept_social
+
+    z = golden("sept_social")
+    U, I = int(z["user_num"]), int(z["item_num"])
+    adj = sp.coo_matrix((z["adj_data"], (z["adj_row"], z["adj_col"])), shape=(U + I, U + I))   # raw, duplicates kept
+    data = SimpleNamespace(user_num=U, item_num=I, norm_adj=adj, interaction_mat=_csr(z, "Y"))
+    m = sept_social.SEPTSocial(data, _csr(z, "bi"), emb_size=z["user_w"].shape[1], n_layers=int(z["n_layers"]),
+                               ss_rate=float(z["ss_rate"]), ins_cnt=int(z["ins_cnt"]), reg=float(z["reg"]))
+    assert sorted(m.state_dict().keys()) == ["item_embeddings", "user_embeddings"]
+    m.load_state_dict({"user_embeddings": torch.from_numpy(z["user_w"]), "item_embeddings": torch.from_numpy(z["item_w"])})
+    m.build()
+    for g, name in ((m.social_mat, "social"), (m.sharing_mat, "sharing")):
+        want = _csr(z, name); want.sort_indices()
+        h = _to_scipy(g)
+        assert np.array_equal(h.indptr, want.indptr) and np.array_equal(h.indices, want.indices), name
+        np.testing.assert_allclose(h.data, want.data, rtol=5e-7)
+    labels = tuple(z[k] for k in ("f_pos", "sh_pos", "r_pos"))
+    rec_loss, nd, total = m.iteration_losses(z["user_idx"], z["pos_idx"], z["neg_idx"], labels=labels)
+    _close(m.rec_user_embeddings, z["rec_user"]); _close(m.rec_item_embeddings, z["rec_item"])
+    _close(m.sharing_view_embeddings, z["sharing_view"]); _close(m.friend_view_embeddings, z["friend_view"])
+    for got, key in zip(m.last_predictions, ("social_prediction", "sharing_prediction", "rec_prediction")):
+        _close(got, z[key], rtol=1e-3, atol=1e-6)
+    for got, key, mk in zip(m.last_labels, ("f_pos", "sh_pos", "r_pos"), ("f_margin", "sh_margin", "r_margin")):
+        clear = z[mk] > 1e-5                               # rows whose K-th and (K+1)-th probabilities are not fp32-close
+        assert clear.mean() > 0.9
+        assert np.array_equal(np.sort(got.cpu().numpy()[clear], 1), np.sort(z[key][clear], 1)), key
+    np.testing.assert_allclose(rec_loss.item(), float(z["rec_loss"]), rtol=1e-3)
+    # the B_u x B_u denominators run on bf16 tensor-core logits: north-star tolerance 2e-2
+    np.testing.assert_allclose(nd.item(), float(z["nd_f"]) + float(z["nd_s"]) + float(z["nd_r"]), rtol=2e-2)
+    np.testing.assert_allclose(total.item(), float(z["total"]), rtol=2e-2)
+    total.backward()
+    for p, key in ((m.user_embeddings, "g_user"), (m.item_embeddings, "g_item")):
+        got, want = p.grad.cpu().numpy(), z[key]
+        assert np.abs(got - want).max() <= 2e-2 * np.abs(want).max() + 1e-7, key
+        assert np.abs(got - want).sum() <= 1e-2 * np.abs(want).sum(), key
+    # training path: own pseudo-labels, augmented operator from the edge-dropout augmentor
+    from recommendation_b200.sept import GraphAugmentor
+    aug = GraphAugmentor.edge_dropout(adj, 0.3, seed=3)
+    out = m.iteration_losses(z["user_idx"], z["pos_idx"], z["neg_idx"], aug_adj=aug)
+    assert all(torch.isfinite(t) for t in out)

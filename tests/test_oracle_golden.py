@@ -340,3 +340,37 @@ def test_motif_oracle_matches_reference_fixture(golden):
         assert np.all(a.data == np.round(a.data)) and np.all(a.data >= 0), k
         if k not in ("A6", "A7"):
             assert (a != a.T).nnz == 0, k
+
+
+def test_sept_social_oracle_matches_reference(golden):
+    """oracle/social_ref.py (sept_social part) against the reference's own SEPT class (tests/golden/make_golden_sept_social.py)."""
+    import scipy.sparse as sp
+    from oracle import social_ref
+
+    z = golden("sept_social")
+    bi, Y = _golden_csr(z, "bi"), _golden_csr(z, "Y")
+    views = social_ref.sept_social_views(bi, Y)
+    for got, name in zip(views, ("social", "sharing")):
+        want = _golden_csr(z, name)
+        got.sort_indices()
+        assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices), name
+        np.testing.assert_allclose(got.data, want.data, rtol=3e-7)
+    U, I = int(z["user_num"]), int(z["item_num"])
+    adj = torch.from_numpy(sp.coo_matrix((z["adj_data"], (z["adj_row"], z["adj_col"])), shape=(U + I, U + I)).toarray()).double()
+    dense = lambda name: torch.from_numpy(_golden_csr(z, name).toarray()).double()
+    uw = torch.from_numpy(z["user_w"]).double().requires_grad_(True)
+    iw = torch.from_numpy(z["item_w"]).double().requires_grad_(True)
+    t = lambda k: torch.from_numpy(z[k])
+    out = social_ref.sept_social_iteration(uw, iw, adj, dense("social"), dense("sharing"), int(z["n_layers"]), float(z["ss_rate"]),
+                                           int(z["ins_cnt"]), float(z["reg"]), t("user_idx"), t("pos_idx"), t("neg_idx"))
+    for k in ("rec_user", "rec_item", "sharing_view", "friend_view", "social_prediction", "sharing_prediction", "rec_prediction"):
+        np.testing.assert_allclose(out[k].detach().numpy(), z[k], rtol=2e-4, atol=2e-6, err_msg=k)
+    for k, mk in (("f_pos", "f_margin"), ("sh_pos", "sh_margin"), ("r_pos", "r_margin")):
+        clear = z[mk] > 1e-6                                # rows whose K-th / (K+1)-th probabilities are not fp32-close
+        assert clear.mean() > 0.9
+        assert np.array_equal(np.sort(out[k].numpy()[clear], 1), np.sort(z[k][clear], 1)), k
+    for k in ("rec_loss", "nd_f", "nd_s", "nd_r", "total"):
+        np.testing.assert_allclose(float(out[k]), float(z[k]), rtol=2e-4, err_msg=k)
+    out["total"].backward()
+    np.testing.assert_allclose(uw.grad.numpy(), z["g_user"], rtol=2e-3, atol=2e-6)
+    np.testing.assert_allclose(iw.grad.numpy(), z["g_item"], rtol=2e-3, atol=2e-6)
