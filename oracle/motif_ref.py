@@ -66,3 +66,17 @@ def build_hyper_adj_mats(S, Y, p_threshold: float = 3.0):
     hj = a["A8"] + a["A9"]
     hp = a["A10"].multiply(a["A10"] > p_threshold)
     return [row_normalise(hs), row_normalise(hj), row_normalise(hp)]
+
+
+def build_motif_induced_adjacency_matrix(S, Y, p_threshold: float = 5.0):
+    """ESRF's single high-order adjacency, univariate/esrf.py:1067-1096: S + A1..A7 + A8 + A9 (one-sided) + A10 with
+    A10 = Y.Y^T minus its diagonal, kept where > p_threshold; rows divided by their sums."""
+    a, B, U = motif_terms(S, Y)
+    S = sp.csr_matrix(S, dtype=np.float32)
+    Y = sp.csr_matrix(Y, dtype=np.float32)
+    yy = (Y @ Y.T).tocsr()
+    a9 = yy.multiply(U).tocsr()                              # esrf.py:1087 (not symmetrised there)
+    a10 = yy - sp.diags(yy.diagonal())                       # esrf.py:1089-1090
+    a10 = a10.multiply(a10 > p_threshold)                    # esrf.py:1092
+    total = S + sum(a[k] for k in ("A1", "A2", "A3", "A4", "A5", "A6", "A7", "A8")) + a9 + a10
+    return row_normalise(total)                              # esrf.py:1095-1096

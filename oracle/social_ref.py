@@ -121,3 +121,52 @@ def sept_social_iteration(user_w, item_w, adj, social, sharing, n_layers, ss_rat
     return dict(rec_user=rec_u, rec_item=rec_i, sharing_view=sharing_v, friend_view=friend_v, rec_loss=rec_loss,
                 social_prediction=soc_p, sharing_prediction=sha_p, rec_prediction=rec_p, f_pos=f_pos, sh_pos=sh_pos, r_pos=r_pos,
                 nd_f=nd_f, nd_s=nd_s, nd_r=nd_r, total=total)
+
+
+# ------------------------------------------------------------------------------------------ esrf.py
+def esrf_generator(relation, selector, A, n_layers, segment, noise):
+    """ESRF.Generator.forward (esrf.py:1127-1149) with the uniform draws of gumbel_softmax (esrf.py:1003-1008) given."""
+    n = relation.shape[0]
+    embs, x = [relation], relation
+    for _ in range(n_layers):
+        x = A @ x                                            # the raw product feeds the next layer
+        embs.append(F.normalize(x, p=2, dim=1))
+    emb = torch.stack(embs, 0).mean(0)
+    end = min(segment + 100, n)
+    feats = emb[segment:end] @ emb.T
+    eps = 1e-10
+    rows = []
+    for r in range(feats.shape[0]):
+        alpha = feats[r].unsqueeze(0) * selector
+        g = -torch.log(-torch.log(noise[r] + eps) + eps)
+        rows.append(F.softmax((torch.log(alpha + eps) + g) / 0.2, dim=-1).sum(0))
+    alt = torch.zeros(n, n, dtype=relation.dtype)
+    alt[segment:end] = torch.stack(rows)
+    return alt
+
+
+def esrf_discriminator(user_w, item_w, adj, alt, n_layers, is_social, K):
+    """ESRF.Discriminator.forward (esrf.py:1168-1198)."""
+    nu = user_w.shape[0]
+    ego = torch.cat([user_w, item_w], 0)
+    embs = [ego]
+    for _ in range(n_layers):
+        if is_social:
+            ego = torch.cat([ego[:nu] + (alt @ ego[:nu]) / K, ego[nu:]], 0)
+        else:
+            ego = adj @ ego
+        embs.append(F.normalize(ego, p=2, dim=1))
+    total = torch.stack(embs, 0).sum(0)
+    return total[:nu], total[nu:]
+
+
+def esrf_losses(user_emb, item_emb, alt, u_idx, i_idx, j_idx, K, reg_u):
+    """(pairwise, reg, adversarial, g_adv) of esrf.py:1231-1236 and 1296-1309."""
+    ue, ve, ne = user_emb[u_idx], item_emb[i_idx], item_emb[j_idx]
+    y_ui, y_uj = (ue * ve).sum(1), (ue * ne).sum(1)
+    pair = -torch.sum(torch.log(torch.sigmoid(y_ui - y_uj) + 1e-10))
+    reg = reg_u * (torch.norm(ue) + torch.norm(ve) + torch.norm(ne))
+    y_vi = ((alt[u_idx] @ user_emb) / K * ve).sum(1)
+    adv = -torch.sum(torch.log(torch.sigmoid(y_ui - y_vi) + 1e-10))
+    g_adv = -torch.sum(torch.log(torch.sigmoid(y_vi - y_ui) + 1e-10))
+    return pair, reg, adv, g_adv

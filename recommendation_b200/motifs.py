@@ -107,46 +107,72 @@ def spgemm(a: CSRGraph, b: CSRGraph, *, max_products: int = MAX_PRODUCTS_PER_CHU
     return from_coo_sum(pieces, a.n_rows, b.n_cols, dev)
 
 
+class MotifTerms:
+    """The terms every motif-based social model of the reference sums (mhcn.py:343-359 = esrf.py:1072-1088), as COO lists:
+    social = the terms of A1..A7 (A1, A2, A3, A5 already symmetrised), a8 = (Y.Y^T) o B, a9 = (Y.Y^T) o U (NOT symmetrised),
+    B / U = reciprocal / one-way part of S."""
+
+    def __init__(self, S: CSRGraph, Y: CSRGraph):
+        if S.n_rows != S.n_cols or Y.n_rows != S.n_rows:
+            raise ValueError("MotifTerms: S must be [U, U] and Y [U, I]")
+        n, dev = S.n_rows, S.device
+        self.n, self.device, self.S, self.Y = n, dev, S, Y
+        St = S.transpose()
+        b_vals = S.vals * csr_sample(St, S)                       # B = S o S^T on S's pattern          (mhcn.py:343)
+        self.B = B = from_coo_sum([to_coo(S, b_vals)], n, n, dev)
+        self.U = U = from_coo_sum([to_coo(S, S.vals - b_vals)], n, n, dev)   # U = S - B                 (mhcn.py:344)
+        Ut = U.transpose()
+        Bt = B.transpose()                                        # B is symmetric; kept general
+
+        def term(p: CSRGraph, qt: CSRGraph, m: CSRGraph) -> Coo:  # (P . Q) o M with Q given by its transpose
+            return to_coo(m, masked_product(p, qt, m))
+
+        sym = lambda t: [t, transpose_coo(t)]                     # C + C^T
+        c1 = [term(U, Ut, Ut)]                                                   # (U.U) o U^T                     :345
+        c2 = [term(B, Ut, Ut), term(U, Bt, Ut), term(U, Ut, B)]                  #                                 :347
+        c3 = [term(B, Bt, U), term(B, Ut, B), term(U, Bt, B)]                    #                                 :349
+        a4 = [term(B, Bt, B)]                                                    #                                 :351
+        c5 = [term(U, Ut, U), term(U, U, U), term(Ut, Ut, U)]                    # (U.U)oU + (U.U^T)oU + (U^T.U)oU :352
+        a6 = [term(U, Bt, U), term(B, U, Ut), term(Ut, Ut, B)]                   # (U.B)oU + (B.U^T)oU^T + (U^T.U)oB :354
+        a7 = [term(Ut, Bt, Ut), term(B, Ut, U), term(U, U, B)]                   # (U^T.B)oU^T + (B.U)oU + (U.U^T)oB :355
+        self.social: List[Coo] = a4 + a6 + a7
+        for c in (c1, c2, c3, c5):                                               # A1, A2, A3, A5 = C + C^T        :346-353
+            for t in c:
+                self.social += sym(t)
+        self.a8 = term(Y, Y, B)                                                  # (Y.Y^T) o B   (Q = Y^T, Q^T = Y) :356
+        self.a9 = term(Y, Y, U)                                                  # (Y.Y^T) o U                     :357
+
+    def co_purchase(self, max_products: int = MAX_PRODUCTS_PER_CHUNK) -> CSRGraph:
+        """Y . Y^T (mhcn.py:359, esrf.py:1088)."""
+        return spgemm(self.Y, self.Y.transpose(), max_products=max_products)
+
+
 def build_hyper_adj_mats(S: CSRGraph, Y: CSRGraph, *, p_threshold: float = 3.0,
                          max_products: int = MAX_PRODUCTS_PER_CHUNK) -> List[CSRGraph]:
     """[H_s, H_j, H_p] of mhcn.py:340-368 from the directed social matrix S [U, U] and the interaction matrix Y [U, I]
     (canonical CSR operators on the GPU, `CSRGraph.from_scipy(...)` of `social_data.get_social_mat()` /
     `data.interaction_mat`).  Row-normalised like the reference; H_p keeps co-purchase counts > p_threshold."""
-    if S.n_rows != S.n_cols or Y.n_rows != S.n_rows:
-        raise ValueError("build_hyper_adj_mats: S must be [U, U] and Y [U, I]")
-    n, dev = S.n_rows, S.device
-    St = S.transpose()
-    b_vals = S.vals * csr_sample(St, S)                       # B = S o S^T on S's pattern          (mhcn.py:343)
-    B = from_coo_sum([to_coo(S, b_vals)], n, n, dev)
-    U = from_coo_sum([to_coo(S, S.vals - b_vals)], n, n, dev)  # U = S - B                           (mhcn.py:344)
-    Ut = U.transpose()
-    Bt = B.transpose()                                        # B is symmetric; kept general
-
-    def term(p: CSRGraph, qt: CSRGraph, m: CSRGraph) -> Coo:  # (P . Q) o M with Q given by its transpose
-        return to_coo(m, masked_product(p, qt, m))
-
-    sym = lambda t: [t, transpose_coo(t)]                     # C + C^T
-    c1 = [term(U, Ut, Ut)]                                                   # (U.U) o U^T                     :345
-    c2 = [term(B, Ut, Ut), term(U, Bt, Ut), term(U, Ut, B)]                  #                                 :347
-    c3 = [term(B, Bt, U), term(B, Ut, B), term(U, Bt, B)]                    #                                 :349
-    a4 = [term(B, Bt, B)]                                                    #                                 :351
-    c5 = [term(U, Ut, U), term(U, U, U), term(Ut, Ut, U)]                    # (U.U)oU + (U.U^T)oU + (U^T.U)oU :352
-    a6 = [term(U, Bt, U), term(B, U, Ut), term(Ut, Ut, B)]                   # (U.B)oU + (B.U^T)oU^T + (U^T.U)oB :354
-    a7 = [term(Ut, Bt, Ut), term(B, Ut, U), term(U, U, B)]                   # (U^T.B)oU^T + (B.U)oU + (U.U^T)oB :355
-    hs_terms: List[Coo] = a4 + a6 + a7
-    for c in (c1, c2, c3, c5):                                               # A1, A2, A3, A5 = C + C^T        :346-353
-        for t in c:
-            hs_terms += sym(t)
-    H_s = from_coo_sum(hs_terms, n, n, dev, norm="row")                      # sum + row normalisation         :361-362
-
-    a8 = term(Y, Y, B)                                                       # (Y.Y^T) o B   (Q = Y^T, Q^T = Y) :356
-    a9 = sym(term(Y, Y, U))                                                  # (Y.Y^T) o U, + transpose        :357-358
-    H_j = from_coo_sum([a8] + a9, n, n, dev, norm="row")                     #                                 :363-364
-
-    yy = spgemm(Y, Y.transpose(), max_products=max_products)                 # Y.Y^T                            :359
-    neg = lambda t: (t[0], t[1], -t[2])
-    a10 = from_coo_sum([to_coo(yy, drop_zeros=False), neg(a8)] + [neg(t) for t in a9], n, n, dev)
+    t = MotifTerms(S, Y)
+    n, dev = t.n, t.device
+    H_s = from_coo_sum(t.social, n, n, dev, norm="row")                      # sum + row normalisation         :361-362
+    a9 = [t.a9, transpose_coo(t.a9)]                                         # A9 = A9 + A9^T                  :358
+    H_j = from_coo_sum([t.a8] + a9, n, n, dev, norm="row")                   #                                 :363-364
+    yy = t.co_purchase(max_products)
+    neg = lambda c: (c[0], c[1], -c[2])
+    a10 = from_coo_sum([to_coo(yy, drop_zeros=False), neg(t.a8)] + [neg(c) for c in a9], n, n, dev)   # :359
     r, c, v = to_coo(a10)
     keep = v > p_threshold                                                   # H_p o (H_p > 3)                 :365-366
     H_p = from_coo_sum([(r[keep], c[keep], v[keep])], n, n, dev, norm="row")  #                                :367
     return [H_s, H_j, H_p]
+
+
+def build_motif_induced_adjacency_matrix(S: CSRGraph, Y: CSRGraph, *, p_threshold: float = 5.0,
+                                         max_products: int = MAX_PRODUCTS_PER_CHUNK) -> CSRGraph:
+    """ESRF's single high-order adjacency (univariate/esrf.py:1067-1096): S + A1..A7 + A8 + A9 + A10 with A9 left one-sided,
+    A10 = Y.Y^T without its diagonal and only where > p_threshold common purchases, every row divided by its sum."""
+    t = MotifTerms(S, Y)
+    n, dev = t.n, t.device
+    r, c, v = to_coo(t.co_purchase(max_products))
+    keep = (r != c) & (v > p_threshold)                                      # esrf.py:1089-1092
+    a10 = (r[keep], c[keep], v[keep])
+    return from_coo_sum([to_coo(S)] + t.social + [t.a8, t.a9, a10], n, n, dev, norm="row")   # esrf.py:1094-1096

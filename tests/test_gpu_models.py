@@ -616,3 +616,58 @@ def test_sept_social_fixture(cuda, golden):
     aug = GraphAugmentor.edge_dropout(adj, 0.3, seed=3)
     out = m.iteration_losses(z["user_idx"], z["pos_idx"], z["neg_idx"], aug_adj=aug)
     assert all(torch.isfinite(t) for t in out)
+
+
+# ------------------------------------------------------------------------------------------ esrf.py (8f row 3)
+def test_esrf_fixture(cuda, golden):
+    """recommendation_b200.esrf against the reference's own ESRF pieces: motif adjacency (identical pattern), joint adjacency,
+    Generator (replayed uniform draws), Discriminator in both modes, the loss lines of trainModel and their gradients."""
+    from recommendation_b200 import esrf
+
+    z = golden("esrf")
+    K, seg, regU, beta = int(z["K"]), int(z["segment"]), float(z["regU"]), float(z["beta"])
+    U, I = _csr(z, "Y").shape
+    gS, gY = CSRGraph.from_scipy(_csr(z, "S"), device=cuda), CSRGraph.from_scipy(_csr(z, "Y"), device=cuda)
+    A = esrf.build_motif_induced_adjacency_matrix(gS, gY)
+    want = _csr(z, "A"); want.eliminate_zeros(); want.sort_indices()
+    h = _to_scipy(A)
+    assert np.array_equal(h.indptr, want.indptr) and np.array_equal(h.indices, want.indices)      # bit-exact structure
+    np.testing.assert_allclose(h.data, want.data, rtol=3e-7)
+    joint = esrf.create_joint_sparse_adjacency(torch.from_numpy(z["users"]).to(cuda), torch.from_numpy(z["items"]).to(cuda), U, I)
+    wj = _csr(z, "joint"); wj.sort_indices()
+    hj = _to_scipy(joint)
+    assert np.array_equal(hj.indptr, wj.indptr) and np.array_equal(hj.indices, wj.indices)
+    np.testing.assert_allclose(hj.data, wj.data, rtol=3e-7)
+
+    d = z["gen_relation"].shape[1]
+    gen = esrf.Generator(U, d, int(z["n_layers_G"]), K)
+    dis = esrf.Discriminator(U, I, d, int(z["n_layers_D"]))
+    assert sorted(gen.state_dict().keys()) == list(z["gen_state_keys"]) and sorted(dis.state_dict().keys()) == list(z["dis_state_keys"])
+    with torch.no_grad():
+        gen.relation_embeddings.copy_(torch.from_numpy(z["gen_relation"])); gen.projection_head.copy_(torch.from_numpy(z["gen_projection"]))
+        gen.c_selector.copy_(torch.from_numpy(z["gen_selector"]))
+        dis.user_embeddings.copy_(torch.from_numpy(z["dis_user"])); dis.item_embeddings.copy_(torch.from_numpy(z["dis_item"]))
+    alt = gen(A, seg, noise=torch.from_numpy(z["noise"]).to(cuda))
+    _close(alt, z["alt"], rtol=2e-3, atol=1e-6)
+    # pretraining pass
+    pu, pi = dis(joint, None, False, 0, K)
+    _close(pu, z["pre_user"]); _close(pi, z["pre_item"])
+    pair, reg = esrf.pairwise_losses(pu, pi, z["user_idx"], z["i_idx"], z["j_idx"], regU)
+    np.testing.assert_allclose([pair.item(), reg.item()], [float(z["pre_pair"]), float(z["pre_reg"])], rtol=1e-3)
+    g = torch.autograd.grad(pair + reg, (dis.user_embeddings, dis.item_embeddings))
+    for got, key in zip(g, ("g_pre_user", "g_pre_item")):
+        np.testing.assert_allclose(got.cpu().numpy(), z[key], rtol=5e-3, atol=1e-5 * np.abs(z[key]).max())
+    # adversarial pass
+    su, si = dis(joint, alt, True, 0, K)
+    _close(su, z["soc_user"]); _close(si, z["soc_item"])
+    pair, reg = esrf.pairwise_losses(su, si, z["user_idx"], z["i_idx"], z["j_idx"], regU)
+    adv, g_adv = esrf.adversarial_losses(su, si, alt, z["user_idx"], z["i_idx"], K)
+    np.testing.assert_allclose([pair.item(), reg.item(), adv.item(), beta * g_adv.item()],
+                               [float(z["pair"]), float(z["reg"]), float(z["adv"]), float(z["g_loss"])], rtol=1e-3)
+    gd = torch.autograd.grad(pair + reg + beta * adv, (dis.user_embeddings, dis.item_embeddings), retain_graph=True)
+    for got, key in zip(gd, ("g_d_user", "g_d_item")):
+        np.testing.assert_allclose(got.cpu().numpy(), z[key], rtol=5e-3, atol=1e-5 * np.abs(z[key]).max())
+    gg = torch.autograd.grad(beta * g_adv, (gen.relation_embeddings, gen.c_selector))
+    for got, key in zip(gg, ("g_g_relation", "g_g_selector")):
+        np.testing.assert_allclose(got.cpu().numpy(), z[key], rtol=1e-2, atol=1e-4 * np.abs(z[key]).max())
+    assert torch.isfinite(gen(A, 0)).all()      # training path: own noise

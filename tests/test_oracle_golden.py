@@ -374,3 +374,43 @@ def test_sept_social_oracle_matches_reference(golden):
     out["total"].backward()
     np.testing.assert_allclose(uw.grad.numpy(), z["g_user"], rtol=2e-3, atol=2e-6)
     np.testing.assert_allclose(iw.grad.numpy(), z["g_item"], rtol=2e-3, atol=2e-6)
+
+
+def test_esrf_oracle_matches_reference(golden):
+    """oracle restatements of esrf.py (motif adjacency, generator, discriminator, losses) against the reference's own
+    functions / modules (tests/golden/make_golden_esrf.py)."""
+    from oracle import motif_ref, social_ref
+
+    z = golden("esrf")
+    S, Y = _golden_csr(z, "S"), _golden_csr(z, "Y")
+    A = motif_ref.build_motif_induced_adjacency_matrix(S, Y)
+    want = _golden_csr(z, "A"); want.eliminate_zeros()
+    A.sort_indices()
+    assert np.array_equal(A.indptr, want.indptr) and np.array_equal(A.indices, want.indices)
+    np.testing.assert_allclose(A.data, want.data, rtol=3e-7)
+    K, seg, regU, beta = int(z["K"]), int(z["segment"]), float(z["regU"]), float(z["beta"])
+    dn = lambda name: torch.from_numpy(_golden_csr(z, name).toarray()).double()
+    t = lambda k: torch.from_numpy(z[k])
+    rel = t("gen_relation").double().requires_grad_(True); sel = t("gen_selector").double().requires_grad_(True)
+    uw = t("dis_user").double().requires_grad_(True); iw = t("dis_item").double().requires_grad_(True)
+    alt = social_ref.esrf_generator(rel, sel, dn("A"), int(z["n_layers_G"]), seg, t("noise").double())
+    np.testing.assert_allclose(alt.detach().numpy(), z["alt"], rtol=2e-3, atol=1e-6)
+    pu, pi = social_ref.esrf_discriminator(uw, iw, dn("joint"), None, int(z["n_layers_D"]), False, K)
+    np.testing.assert_allclose(pu.detach().numpy(), z["pre_user"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(pi.detach().numpy(), z["pre_item"], rtol=1e-4, atol=1e-6)
+    pair, reg, _, _ = social_ref.esrf_losses(pu, pi, alt.detach(), t("user_idx"), t("i_idx"), t("j_idx"), K, regU)
+    np.testing.assert_allclose([float(pair), float(reg)], [float(z["pre_pair"]), float(z["pre_reg"])], rtol=1e-4)
+    g = torch.autograd.grad(pair + reg, (uw, iw))
+    np.testing.assert_allclose(g[0].numpy(), z["g_pre_user"], rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(g[1].numpy(), z["g_pre_item"], rtol=2e-3, atol=1e-6)
+    su, si = social_ref.esrf_discriminator(uw, iw, dn("joint"), alt, int(z["n_layers_D"]), True, K)
+    np.testing.assert_allclose(su.detach().numpy(), z["soc_user"], rtol=1e-4, atol=1e-6)
+    pair, reg, adv, g_adv = social_ref.esrf_losses(su, si, alt, t("user_idx"), t("i_idx"), t("j_idx"), K, regU)
+    np.testing.assert_allclose([float(pair), float(reg), float(adv), float(beta * g_adv)],
+                               [float(z["pair"]), float(z["reg"]), float(z["adv"]), float(z["g_loss"])], rtol=1e-4)
+    gd = torch.autograd.grad(pair + reg + beta * adv, (uw, iw), retain_graph=True)
+    np.testing.assert_allclose(gd[0].numpy(), z["g_d_user"], rtol=2e-3, atol=2e-6)
+    np.testing.assert_allclose(gd[1].numpy(), z["g_d_item"], rtol=2e-3, atol=2e-6)
+    gg = torch.autograd.grad(beta * g_adv, (rel, sel))
+    np.testing.assert_allclose(gg[0].numpy(), z["g_g_relation"], rtol=5e-3, atol=1e-6 * np.abs(z["g_g_relation"]).max())
+    np.testing.assert_allclose(gg[1].numpy(), z["g_g_selector"], rtol=5e-3, atol=1e-6 * np.abs(z["g_g_selector"]).max())
