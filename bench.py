@@ -341,6 +341,12 @@ def run_ours(args):
     value = E * args.steps / (total_ms * 1e-3)
     spmm_avg_us = sum(spmm_us) / max(len(spmm_us), 1)
     alg_bytes = spmm_algorithmic_bytes(spmm_rows, n, nnz, spmm_d)  # per launch on ONE rank
+    alg_note = "SURVEY 8(d) B_spmm = nnz*8 + (N_r+1)*4 + N_c*d*4 + N_r*d*4"
+    if getattr(trainer, "fused_adam", False):
+        # the timed pair brackets the whole forward propagation, whose last launch also writes the layer sum:
+        # SURVEY 8(d) "propagate fwd (K layers + mean) = K * B_spmm + N*d*4", averaged over its K launches
+        alg_bytes += spmm_rows * spmm_d * 4 // K
+        alg_note = "SURVEY 8(d) forward propagation (K * B_spmm + N_r*d*4) / K launches"
     achieved = alg_bytes / (spmm_avg_us * 1e-6) / 1e9 if spmm_avg_us > 0 else 0.0
     traffic = ncu_traffic(args.workload) if world == 1 else None  # DRAM bytes actually moved per launch (ncu capture)
 
@@ -417,7 +423,7 @@ def run_ours(args):
                          "dram_rate_frac_of_peak": (traffic / (spmm_avg_us * 1e-6) / 1e9 / peak) if traffic and spmm_avg_us > 0 else None,
                          "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
                          "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": spmm_avg_us,
+                         "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_note": alg_note, "avg_launch_us": spmm_avg_us,
                          "launches_timed": len(spmm_us) * K,
                          "launches_note": "forward-propagation SpMM launches of the timed steps (the last one carries the layer-sum epilogue)"},
             "cpu_baseline": cpu_baseline,
