@@ -495,14 +495,17 @@ def test_ncl_training_iteration_runs_and_learns(cuda):
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     k = ncl_mod.e_step(model, ncl, 20)
     assert k == max(2, min(20, U // 39)) and ncl.user_2cluster.shape == (U,) and ncl.item_centroids.shape[1] == 64
-    first = last = None
-    for epoch in range(3):
+    import random
+    random.seed(0); np.random.seed(0)
+    per_epoch = []
+    for epoch in range(4):
+        rec = []
         for n, batch in enumerate(sampling.next_batch_pairwise(data, 512)):
             total, parts = ncl_mod.ncl_step(model, ncl, opt, batch, 1e-4, 512, 1, k=k, refresh_clusters=(n % 8 == 0))
             assert torch.isfinite(total) and all(torch.isfinite(v) for v in parts.values())
-            first = parts["rec"].item() if first is None else first
-            last = parts["rec"].item()
-    assert last < first            # the ranking loss goes down
+            rec.append(parts["rec"].item())
+        per_epoch.append(float(np.mean(rec)))
+    assert per_epoch[-1] < per_epoch[0], per_epoch      # the ranking loss goes down (epoch means: single batches are noisy)
 
 
 # ------------------------------------------------------------------------------------------ MHCN motif matrices (8f row 4)
