@@ -343,6 +343,32 @@ int gcf_spgemm_count(const gcf_csr_t* A, const gcf_csr_t* B, int64_t entry_begin
 int gcf_spgemm_expand(const gcf_csr_t* A, const gcf_csr_t* B, int64_t entry_begin, int64_t entry_end, int64_t* rows_out,
                       int64_t* cols_out, float* vals_out, void* workspace, size_t workspace_bytes, gcf_stream_t stream);
 
+/* ---- text ingest -----------------------------------------------------------------------------
+ * `user item rating` text files -> id arrays -> dense indices, for the loaders of the reference: load_data
+ * (ncl.py:542-543: `line.strip().split()[:2]`, blank lines skipped), Interaction._build (ncl.py:55-70: ids numbered by
+ * sorted() of the id STRINGS; selfcf.py:281-288: by first appearance) and lightgcn.py:29-33 (integer ids, pandas).
+ * `text` is the file content in device memory.  A record is a line with at least one non-blank byte. */
+
+/* *n_records (device int64) = number of records; per-segment record numbers stay in the workspace for the parse. */
+size_t gcf_text_workspace_bytes(int64_t n_bytes);
+int gcf_text_count_records(const uint8_t* text, int64_t n_bytes, int64_t* n_records, void* workspace, size_t workspace_bytes,
+                           gcf_stream_t stream);
+/* first[r], second[r] = the first two whitespace-separated tokens of record r as keys.
+ *   mode 0: string keys -- up to 8 bytes, left-aligned big-endian, zero padded: unsigned key order == byte-wise
+ *           lexicographic order of the ids (what Python's sorted() gives for ASCII strings: "10" < "2");
+ *   mode 1: unsigned decimal integers (lightgcn.py's integer ids).
+ * *status (device int32) collects bit 1 = a record with fewer than two tokens, bit 2 = a token outside the key format. */
+int gcf_text_parse_pairs(const uint8_t* text, int64_t n_bytes, int32_t mode, uint64_t* first, uint64_t* second,
+                         int32_t* status, void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+/* uniq[0 .. *n_uniq) = the distinct keys in ascending order (stable LSD radix sort + run heads);
+ * first_pos[j] (nullable) = position in `keys` of the first occurrence of uniq[j]. */
+size_t gcf_sort_unique_workspace_bytes(int64_t n);
+int gcf_sort_unique_u64(const uint64_t* keys, int64_t n, uint64_t* uniq, int64_t* first_pos, int64_t* n_uniq,
+                        void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+/* idx[i] = position of keys[i] in the ascending table, -1 when absent (ids that only occur in the test file). */
+int gcf_lookup_sorted_u64(const uint64_t* table, int64_t n_table, const uint64_t* keys, int64_t n, int64_t* idx,
+                          gcf_stream_t stream);
+
 /* ---- batched evaluation ---------------------------------------------------
  *
  * scores [n_queries, n_items] fp32 (ld elements per row) is the dense score block user_emb[q] . item_emb^T -- a plain

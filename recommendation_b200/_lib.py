@@ -98,6 +98,12 @@ _SIGNATURES = {
     "gcf_spgemm_count": (c_int32, [POINTER(CsrStruct), POINTER(CsrStruct), c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gcf_spgemm_expand": (c_int32, [POINTER(CsrStruct), POINTER(CsrStruct), c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_size_t, c_void_p]),
+    "gcf_text_workspace_bytes": (c_size_t, [c_int64]),
+    "gcf_text_count_records": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gcf_text_parse_pairs": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gcf_sort_unique_workspace_bytes": (c_size_t, [c_int64]),
+    "gcf_sort_unique_u64": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gcf_lookup_sorted_u64": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "gcf_masked_topn": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_void_p,
                                   c_void_p, c_void_p]),
     "gcf_ranking_hits": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,

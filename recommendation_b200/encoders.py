@@ -36,7 +36,8 @@ def _graph_of(data) -> CSRGraph:
     cached on the data object so that several encoders over the same data share it."""
     g = getattr(data, "_gcf_graph", None)
     if g is None:
-        g = CSRGraph.from_scipy(data.norm_adj, norm="none", device=_device())
+        adj = data.norm_adj
+        g = adj if isinstance(adj, CSRGraph) else CSRGraph.from_scipy(adj, norm="none", device=_device())
         try:
             data._gcf_graph = g
         except AttributeError:

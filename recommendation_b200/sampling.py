@@ -59,6 +59,7 @@ def next_batch_pairwise(data, batch_size: int, n_negs: int = 1):
     """Reference signature.  The sampler state (device pairs, positives CSR, epoch counter) is cached on `data`."""
     s = getattr(data, "_gcf_sampler", None)
     if s is None:
-        s = PairwiseSampler.from_data(data)
+        # ingest.DeviceInteraction already holds the dense index tensors; the reference's Interaction needs its dictionaries walked
+        s = data.sampler() if hasattr(data, "sampler") else PairwiseSampler.from_data(data)
         data._gcf_sampler = s
     yield from s.batches(batch_size, n_negs)

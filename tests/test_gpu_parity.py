@@ -624,3 +624,66 @@ def test_c_abi_reports_errors_instead_of_crashing(cuda):
     assert bad.nnz == 2
     torch.cuda.synchronize()   # nothing above left a sticky CUDA error behind
     assert torch.isfinite(F_.spmm(bad, torch.ones(3, 16, device=cuda))).all()
+
+
+# ====================================================================== text ingest
+def _ingest_files(tmp_path, z, prefix=""):
+    tr, te = tmp_path / "train.txt", tmp_path / "test.txt"
+    tr.write_bytes(z[f"{prefix}train_bytes"].tobytes()); te.write_bytes(z[f"{prefix}test_bytes"].tobytes())
+    return str(tr), str(te)
+
+
+@pytest.mark.parametrize("order", ["sorted", "appearance"])
+def test_ingest_matches_reference_loaders(cuda, golden, tmp_path, order):
+    """ingest.DeviceInteraction on the file bytes the reference's own load_data + Interaction read (ncl.py / selfcf.py):
+    id dictionaries, dense training / test indices and the adjacency, all bit-exact."""
+    import scipy.sparse as sp
+    from recommendation_b200 import ingest
+
+    z = golden("ingest")
+    d = ingest.DeviceInteraction.from_files(*_ingest_files(tmp_path, z), id_order=order)
+    assert d.user_ids() == list(z[f"{order}_user_ids"]) and d.item_ids() == list(z[f"{order}_item_ids"])
+    assert d.user_num == len(z[f"{order}_user_ids"]) and d.item_num == len(z[f"{order}_item_ids"])
+    for got, key in ((d.users, "users"), (d.items, "items"), (d.test_users, "test_users"), (d.test_items, "test_items")):
+        assert np.array_equal(got.cpu().numpy(), z[f"{order}_{key}"]), key
+    n = d.user_num + d.item_num
+    if order == "sorted":        # raw adjacency of ncl.py:76-85: duplicates kept in the COO, summed by the CSR build
+        want = sp.coo_matrix((z["sorted_adj_data"], (z["sorted_adj_row"], z["sorted_adj_col"])), shape=(n, n)).tocsr()
+        got = d.norm_adj
+    else:                        # selfcf.py: D^-1/2 (R + R^T) D^-1/2
+        want = sp.csr_matrix((z["appearance_adj_data"], z["appearance_adj_indices"], z["appearance_adj_indptr"]), shape=(n, n))
+        got = d.normalized_adj()
+    want.sum_duplicates(); want.sort_indices()
+    assert np.array_equal(got.row_ptr.cpu().numpy(), want.indptr) and np.array_equal(got.col_idx.cpu().numpy(), want.indices)
+    np.testing.assert_allclose(got.vals.cpu().numpy(), want.data, rtol=3e-7)
+    u, i, j = next(iter(d.sampler().batches(64)))              # the device sampler runs on the ingested pairs
+    assert u.numel() == 64 and int(j.max()) < d.item_num
+
+
+def test_ingest_numeric_ids_and_errors(cuda, golden, tmp_path):
+    from recommendation_b200 import ingest
+
+    z = golden("ingest")
+    d = ingest.DeviceInteraction.from_files(*_ingest_files(tmp_path, z, "num_"), id_order="numeric")   # lightgcn.py:29-33
+    assert np.array_equal(d.users.cpu().numpy(), z["num_users"]) and np.array_equal(d.items.cpu().numpy(), z["num_items"])
+    assert (d.user_num, d.item_num) == (int(z["num_user_count"]), int(z["num_item_count"]))
+    assert d.edge_index().shape == (2, 2 * d.users.numel())
+    t = lambda s: torch.frombuffer(bytearray(s.encode()), dtype=torch.uint8).to(cuda)
+    with pytest.raises(ValueError, match="8 bytes"):
+        ingest.parse_pairs(t("user_123456 7 1\n"))
+    with pytest.raises(ValueError, match="fewer than two"):
+        ingest.parse_pairs(t("a b 1\nlonely\n"))
+    with pytest.raises(ValueError, match="decimal"):
+        ingest.parse_pairs(t("12 x7 1\n"), numeric=True)
+    a, b = ingest.parse_pairs(torch.empty(0, dtype=torch.uint8, device=cuda))
+    assert a.numel() == 0 and b.numel() == 0
+    # a large random file against the oracle: record count, keys and numbering
+    from oracle import ingest_ref
+    rng = np.random.default_rng(9)
+    rows = [f"{rng.integers(0, 50000)}\t{rng.integers(0, 9000)} 1" + ("\r" if k % 7 == 0 else "") for k in range(200000)]
+    blob = ("\n".join(rows) + "\n").encode()
+    di = ingest.DeviceInteraction(torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(cuda), id_order="sorted")
+    pairs = ingest_ref.load_pairs(blob)
+    um, im = ingest_ref.number_ids([p[0] for p in pairs], "sorted"), ingest_ref.number_ids([p[1] for p in pairs], "sorted")
+    assert di.users.numel() == len(pairs) and di.user_num == len(um) and di.item_num == len(im)
+    assert np.array_equal(di.users.cpu().numpy(), [um[p[0]] for p in pairs]) and np.array_equal(di.items.cpu().numpy(), [im[p[1]] for p in pairs])

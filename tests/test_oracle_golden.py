@@ -414,3 +414,26 @@ def test_esrf_oracle_matches_reference(golden):
     gg = torch.autograd.grad(beta * g_adv, (rel, sel))
     np.testing.assert_allclose(gg[0].numpy(), z["g_g_relation"], rtol=5e-3, atol=1e-6 * np.abs(z["g_g_relation"]).max())
     np.testing.assert_allclose(gg[1].numpy(), z["g_g_selector"], rtol=5e-3, atol=1e-6 * np.abs(z["g_g_selector"]).max())
+
+
+def test_ingest_oracle_matches_reference_loaders(golden):
+    """oracle/ingest_ref.py against the reference's own load_data + Interaction (ncl.py: sorted string ids; selfcf.py: first
+    appearance) on the same file bytes; and the packed-key order equals Python's string order."""
+    from oracle import ingest_ref
+
+    z = golden("ingest")
+    train = ingest_ref.load_pairs(z["train_bytes"].tobytes())
+    test = ingest_ref.load_pairs(z["test_bytes"].tobytes())
+    assert len(train) == int(z["n_records"])
+    for order in ("sorted", "appearance"):
+        umap = ingest_ref.number_ids([u for u, _ in train], order)
+        imap = ingest_ref.number_ids([i for _, i in train], order)
+        assert [s for s, _ in sorted(umap.items(), key=lambda kv: kv[1])] == list(z[f"{order}_user_ids"])
+        assert [s for s, _ in sorted(imap.items(), key=lambda kv: kv[1])] == list(z[f"{order}_item_ids"])
+        assert np.array_equal([umap[u] for u, _ in train], z[f"{order}_users"]) and np.array_equal([imap[i] for _, i in train], z[f"{order}_items"])
+        assert np.array_equal([umap.get(u, -1) for u, _ in test], z[f"{order}_test_users"])
+        assert np.array_equal([imap.get(i, -1) for _, i in test], z[f"{order}_test_items"])
+    ids = sorted({u for u, _ in train})
+    assert sorted(ids, key=ingest_ref.pack_key) == ids
+    with pytest.raises(ValueError):
+        ingest_ref.pack_key("123456789")
