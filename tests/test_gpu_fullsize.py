@@ -1,4 +1,4 @@
-"""Full-size checks at the BASELINE.json config shapes (cfg 2, 3, 4).  The CPU oracle is too slow at these sizes, so the
+"""Full-size checks at the BASELINE.json config shapes (cfg 2, 3, 4, 5).  The CPU oracle is too slow at these sizes, so the
 checks are size-independent properties and comparisons with plain fp32 torch on the same GPU."""
 import numpy as np
 import pytest
@@ -86,3 +86,89 @@ def test_cfg4_social_operators_at_full_size(cuda):
         F_.spmm_raw(op.transpose(), y, y=aty)
         torch.testing.assert_close(x.grad, aty, rtol=1e-5, atol=1e-6)
         torch.testing.assert_close((ax.detach() * y).sum().double(), (aty * x.detach()).sum().double(), rtol=1e-4, atol=1e-2)
+
+
+def test_cfg5_graph_propagation_and_loss_properties_at_full_size(cuda):
+    """The headline configuration (10 M users x 5 M items, 100 M interactions, d = 64, K = 3) on one GPU: no oracle runs at this
+    size, so the adjacency build is checked through exact integer invariants and the kernels through size-independent identities."""
+    if torch.cuda.get_device_properties(cuda).total_memory < 60 * 2**30:
+        pytest.skip("needs ~50 GB of device memory")
+    from recommendation_b200 import _lib
+
+    U, I, E, d, K = synth.CONFIGS["cfg5"]
+    n = U + I
+    users, items = synth.power_law_bipartite_torch(U, I, E, seed=1005, device=cuda)
+    g = CSRGraph.from_pairs(users, items, U, I, norm="sym")
+    # ---- integer invariants of the normalised-adjacency build (bit-exact by construction) ----
+    assert g.n_rows == n and g.nnz == 2 * E                                  # the generator emits distinct pairs
+    row_len = (g.row_ptr[1:] - g.row_ptr[:-1]).to(torch.int64)
+    deg = torch.bincount(torch.cat([users, items + U]), minlength=n)         # degree of every node, computed independently
+    assert torch.equal(row_len, deg)
+    assert int(g.row_ptr[0]) == 0 and int(g.row_ptr[-1]) == g.nnz
+    rows_of = torch.repeat_interleave(torch.arange(n, device=cuda), row_len)
+    key = rows_of * n + g.col_idx.to(torch.int64)
+    assert bool((key[1:] > key[:-1]).all())                                  # rows ascending, columns strictly ascending inside a row
+    assert bool((g.col_idx[: E] >= U).all()) and bool((g.col_idx[E:] < U).all())   # bipartite: user rows hold item columns and vice versa
+    del key, rows_of
+    gt = CSRGraph(g.row_ptr, g.col_idx, g.vals, n, n).transpose()            # forced (non-cached) transpose of a symmetric operator
+    assert torch.equal(gt.row_ptr, g.row_ptr) and torch.equal(gt.col_idx, g.col_idx) and torch.equal(gt.vals, g.vals)
+    del gt
+    assert torch.equal(g.rowsum.to(torch.int64), deg)                        # row sums of the 0/1 matrix are the degrees, exactly
+    # ---- sqrt(deg) is the eigenvector of D^-1/2 A D^-1/2 with eigenvalue 1 ----
+    root = deg.to(torch.float32).sqrt()
+    x = torch.zeros(n, d, device=cuda); x[:, 0] = root; x[:, 1] = -2 * root
+    y = torch.empty_like(x)
+    F_.spmm_raw(g, x, y=y)
+    # (hub rows sum up to ~10^6 fp32 terms chunk by chunk: a few 1e-5 of relative rounding error; a wrong scaling would be O(1) off)
+    torch.testing.assert_close(y[:, 0], root, rtol=5e-4, atol=1e-5)
+    torch.testing.assert_close(y[:, 1], -2 * root, rtol=5e-4, atol=1e-5)
+    assert float(((y[:, 0] - root).abs() / root.clamp_min(1)).median()) < 1e-6
+    assert bool((y[:, 2:] == 0).all())
+    # ---- linearity and self-adjointness on random data (fp64 accumulation of the checksums) ----
+    gen = torch.Generator(device=cuda).manual_seed(5)
+    a = torch.randn(n, d, device=cuda, generator=gen); b = torch.randn(n, d, device=cuda, generator=gen)
+    ya, yb, yc = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
+    F_.spmm_raw(g, a, y=ya); F_.spmm_raw(g, b, y=yb)
+    F_.spmm_raw(g, 0.5 * a - 3.0 * b, y=yc)
+    torch.testing.assert_close(yc, 0.5 * ya - 3.0 * yb, rtol=1e-4, atol=1e-4)
+    dot = lambda p, q: float((p.double() * q.double()).sum())
+    lhs, rhs = dot(ya, b), dot(a, yb)                                        # <A a, b> = <a, A b>
+    assert abs(lhs - rhs) <= 1e-6 * (ya.double().norm() * b.double().norm()).item()
+    del ya, yb, yc, a, b, x, y
+    # ---- K-layer propagation: forward against K single launches, backward = the same operator (adjoint identity) ----
+    x0 = torch.randn(n, d, device=cuda, generator=gen).requires_grad_(True)
+    final = F_.propagate(g, x0, K, mode="sum")
+    cur, acc = x0.detach(), x0.detach().clone()
+    for _ in range(K):
+        nxt = torch.empty_like(cur); F_.spmm_raw(g, cur, y=nxt); acc += nxt; cur = nxt
+    torch.testing.assert_close(final.detach(), acc, rtol=1e-4, atol=1e-4)
+    w = torch.randn(n, d, device=cuda, generator=gen)
+    final.backward(w)
+    with torch.no_grad():
+        gw = F_.propagate(g, w, K, mode="sum")                               # (I + A + A^2 + A^3) is symmetric: grad = P w
+    torch.testing.assert_close(x0.grad, gw, rtol=1e-4, atol=1e-4)
+    del final, cur, acc, nxt, w, gw, x0
+    # ---- Philox negatives: deterministic, in range, uniform ----
+    neg = F_.sample_negatives(E, I, seed=11, offset=3, device=cuda)
+    assert torch.equal(neg, F_.sample_negatives(E, I, seed=11, offset=3, device=cuda))
+    assert not torch.equal(neg, F_.sample_negatives(E, I, seed=11, offset=4, device=cuda))
+    assert int(neg.min()) >= 0 and int(neg.max()) < I
+    assert abs(float(neg.double().mean()) / ((I - 1) / 2) - 1) < 1e-3
+    # ---- fused BPR (forward + backward in one pass) against the split forward / backward kernels ----
+    lib, st = _lib.load(), _lib.current_stream()
+    table = torch.randn(n, d, device=cuda, generator=gen) * 0.1
+    order = torch.argsort(users * I + items)
+    pu, pi = users[order].contiguous(), items[order].contiguous()
+    del order
+    ws_bytes = lib.gcf_bpr_workspace_bytes(E); ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cuda)
+    loss_f, loss_s = torch.zeros((), device=cuda), torch.zeros((), device=cuda)
+    g_f, g_s, coef = torch.zeros(n, d, device=cuda), torch.zeros(n, d, device=cuda), torch.empty(E, device=cuda)
+    args = (_lib.ptr(table[:U]), d, _lib.ptr(table[U:]), d, d, _lib.ptr(pu), _lib.ptr(pi), _lib.ptr(neg), E, 1)
+    _lib.check(lib.gcf_bpr_fwd_bwd(*args, _lib.BPR_SOFTPLUS, 0.0, _lib.REDUCE_MEAN, 1e-4, 1e-4, 0.0, 1.0, _lib.ptr(loss_f), None,
+                                   _lib.ptr(g_f[:U]), d, _lib.ptr(g_f[U:]), d, _lib.ptr(ws), ws_bytes, st), "gcf_bpr_fwd_bwd")
+    _lib.check(lib.gcf_bpr_fwd(*args, _lib.BPR_SOFTPLUS, 0.0, _lib.REDUCE_MEAN, 1e-4, 1e-4, 0.0, _lib.ptr(loss_s), _lib.ptr(coef),
+                               _lib.ptr(ws), ws_bytes, st), "gcf_bpr_fwd")
+    _lib.check(lib.gcf_bpr_bwd(*args, _lib.ptr(coef), None, 1e-4, 1e-4, 0.0, _lib.ptr(g_s[:U]), d, _lib.ptr(g_s[U:]), d, st), "gcf_bpr_bwd")
+    np.testing.assert_allclose(loss_f.item(), loss_s.item(), rtol=1e-6)
+    assert float((g_f - g_s).abs().max()) <= 1e-4 * float(g_s.abs().max()) + 1e-9     # atomic summation order differs
+    assert torch.isfinite(g_f).all()
