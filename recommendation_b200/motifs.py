@@ -70,6 +70,8 @@ def spgemm(a: CSRGraph, b: CSRGraph, *, max_products: int = MAX_PRODUCTS_PER_CHU
     """C = A . B (expand-sort-compress), row blocks of A sized to at most `max_products` scalar products each."""
     if a.n_cols != b.n_rows:
         raise ValueError(f"spgemm: inner dimensions differ ({a.n_cols} vs {b.n_rows})")
+    if not 0 < max_products < 2 ** 32:
+        raise ValueError("spgemm: max_products must be in (0, 2^32): product offsets inside a row block are 32-bit")
     lib, st, dev = _lib.load(), _lib.current_stream(), a.device
     row_ptr = a.row_ptr.cpu().tolist()
     n_prod = torch.zeros(1, dtype=torch.int64, device=dev)
