@@ -261,13 +261,15 @@ def run_ours(args):
             args.loss_layout = "scores" if world <= 2 else "rows"
         if F == world:
             trainer = FeatureShardedLightGCNTrainer(users, items, U, I, d=d, n_layers=K, lr=0.01, reg_weight=1e-4, seed=1234,
-                                                    loss_layout=args.loss_layout)
+                                                    loss_layout=args.loss_layout, overlap=args.overlap_exchange)
             nnz, spmm_rows, spmm_d = trainer.local_nnz, n, trainer.dg
             parallelism = (f"feature-sharded over {world} GPUs: every rank owns d/G = {trainer.dg} columns of all [N, d] tables, "
                            f"propagation / Adam without any collective; ")
             if args.loss_layout == "rows":
                 parallelism += ("loss on full-width rows of one user block per rank: item slices all-gathered, user slices "
-                                "all-to-all'ed, fused BPR on E/G triples, gradients returned by one reduce-scatter + one all-to-all")
+                                "all-to-all'ed, fused BPR on E/G triples, gradients returned by one reduce-scatter + one all-to-all"
+                                + ("; exchanges overlapped with item-row / user-row blocks of the adjacent propagation layers"
+                                   if trainer.overlap else ""))
             else:
                 parallelism += "ONE NCCL all-reduce of E fp32 partial scores per step"
         else:
@@ -445,6 +447,9 @@ def main():
     ap.add_argument("--loss-layout", choices=("auto", "rows", "scores"), default=os.environ.get("GCF_BENCH_LOSS_LAYOUT", "auto"),
                     help="feature-sharded layout only: where the BPR loss is evaluated (see dist.FeatureShardedLightGCNTrainer); "
                          "auto = measured default: all-reduced scores on 2 GPUs (60.5 vs 61.6 ms), full-width rows from 4 GPUs on")
+    ap.add_argument("--overlap-exchange", action="store_true",
+                    help="feature-sharded layout, loss on rows: overlap the exchanges with row blocks of the adjacent propagation "
+                         "layers (measured neutral on cfg5 at 2 and 4 GPUs)")
     ap.add_argument("--feature-shards", type=int, default=int(os.environ.get("GCF_BENCH_FEATURE_SHARDS", "0")),
                     help="N > 1 only: F feature shards x N/F row shards (1 = row-sharded, N = feature-sharded, 0 = measured default)")
     ap.add_argument("--no-e2e", action="store_true")

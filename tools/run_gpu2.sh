@@ -1,6 +1,15 @@
-# 2-GPU check: nccl parity tests, then cfg5 bench with the loss on rows / on all-reduced scores.
+# 2-GPU check: nccl parity tests of the feature-sharded trainer, then cfg5 bench with the loss on rows, overlapped / serial exchanges.
 mkdir -p gpurun_out
-python -m pytest tests/test_dist.py tests/test_gpu_parity.py -m gpu -q -k "dist or slices or feature or sharded" 2>&1 | grep -v "^\s*$" | tail -15
-for mode in rows scores; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --loss-layout $mode > gpurun_out/bench_n2_loss_$mode.json 2> gpurun_out/bench_n2_loss_$mode.err; echo "rc=$?"; cat gpurun_out/bench_n2_loss_$mode.json | cut -c1-400; grep -B2 -A12 "Traceback" gpurun_out/bench_n2_loss_$mode.err | head -40
+python -m pytest tests/test_dist.py -m gpu -q -k "feature_sharded" 2>&1 | grep -v "^\s*$" | tail -15
+for mode in overlap serial; do
+extra=""; if [ $mode = overlap ]; then extra="--overlap-exchange"; fi
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --loss-layout rows $extra > gpurun_out/bench_n2_rows_$mode.json 2> gpurun_out/bench_n2_rows_$mode.err; echo "$mode rc=$?"; python - <<PY
+import json
+try:
+    j=json.loads([l for l in open('gpurun_out/bench_n2_rows_$mode.json') if l.startswith('{')][-1])
+    print('  ms/step %.2f  edges/s %.3e  spmm_us %.0f  launches %d' % (j['ms_per_step'], j['value'], j['roofline']['avg_launch_us'], j['gpu_launches']))
+except Exception as e:
+    print('  ERR', e)
+PY
+grep -B2 -A14 "Traceback" gpurun_out/bench_n2_rows_$mode.err | head -40
 done
