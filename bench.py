@@ -213,7 +213,7 @@ def run_ours(args):
 
     from recommendation_b200 import _lib
     from recommendation_b200.graph import CSRGraph
-    from recommendation_b200.lightgcn import FusedLightGCNTrainer, LightGCN, build_edge_index, train_step
+    from recommendation_b200.lightgcn import FusedLightGCNTrainer, LightGCN, build_edge_index
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

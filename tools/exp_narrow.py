@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-from recommendation_b200 import _lib, functional as F_, synth  # noqa: E402
+from recommendation_b200 import functional as F_, synth  # noqa: E402
 from recommendation_b200.graph import CSRGraph  # noqa: E402
 
 cudart = ctypes.CDLL("/usr/local/cuda/lib64/libcudart.so.12")  # same primary context as torch's own runtime copy
