@@ -437,3 +437,17 @@ def test_ingest_oracle_matches_reference_loaders(golden):
     assert sorted(ids, key=ingest_ref.pack_key) == ids
     with pytest.raises(ValueError):
         ingest_ref.pack_key("123456789")
+
+
+def test_packed_key_round_trip_on_the_host():
+    """ingest.decode_keys (host side of the GPU ingest path) inverts the oracle's key packing, also for keys whose top bit is set
+    when read as signed 64-bit integers."""
+    from oracle import ingest_ref
+    from recommendation_b200 import ingest
+
+    ids = ["1", "10", "2", "u9", "u10", "it07", "abcdefgh", "~zz"]
+    keys = np.array([ingest_ref.pack_key(s) for s in ids], dtype=np.uint64)
+    t = torch.from_numpy(keys.view(np.int64).copy())
+    assert ingest.decode_keys(t) == ids
+    order = np.argsort(keys, kind="stable")
+    assert [ids[k] for k in order] == sorted(ids)               # unsigned key order == Python's string order
