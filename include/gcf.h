@@ -108,6 +108,19 @@ typedef struct gcf_csr {
   const int32_t* long_rows;      /* [n_long] row ids */
   const int32_t* long_chunk_ptr; /* [n_long+1] first chunk of each long row */
   const int32_t* chunk_long;     /* [n_chunks] index into long_rows */
+  /* flat-stream schedule (optional, n_tiles = 0: none).  The rows that are neither long nor empty are cut into tiles
+   * of consecutive rows holding about tile_nnz entries each; one sub-warp streams a tile's entries in fixed batches,
+   * so the number of row gathers in flight does not depend on the row lengths.  Tiles are expressed in the COMPACT
+   * numbering of the non-empty rows: nz_rows[k] is the id of the k-th non-empty row and nz_row_ptr[k] its first
+   * entry (nz_row_ptr[n_rows - n_empty] = nnz); both may be NULL when n_empty = 0 (compact = plain numbering).
+   * Empty rows receive the epilogue of a zero sum.  Requires the long-row schedule above whenever a row exceeds
+   * `chunk` entries. */
+  const int32_t* tiles;          /* [2 * n_tiles]: first row, one-past-last row of each tile (compact numbering) */
+  int32_t n_tiles;
+  int32_t n_empty;
+  const int32_t* empty_rows;     /* [n_empty] */
+  const int32_t* nz_row_ptr;     /* [n_rows - n_empty + 1] */
+  const int32_t* nz_rows;        /* [n_rows - n_empty] */
 } gcf_csr_t;
 
 #define GCF_MAX_ADDENDS 8

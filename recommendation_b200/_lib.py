@@ -32,6 +32,8 @@ class CsrStruct(ctypes.Structure):
         ("row_ptr", c_void_p), ("col_idx", c_void_p), ("vals", c_void_p),
         ("chunk", c_int32), ("n_long", c_int32), ("n_chunks", c_int32),
         ("long_rows", c_void_p), ("long_chunk_ptr", c_void_p), ("chunk_long", c_void_p),
+        ("tiles", c_void_p), ("n_tiles", c_int32), ("n_empty", c_int32), ("empty_rows", c_void_p),
+        ("nz_row_ptr", c_void_p), ("nz_rows", c_void_p),
     ]
 
 

@@ -15,8 +15,21 @@
 //     occupy the lowest block ids so they are scheduled first.
 //   * epilogue fused: optional raw store, optional row-L2-normalise, linear combination
 //     with up to 8 addend matrices (layer mean / sum, backward residual terms).
+//
+// r02 -- flat-stream kernel (spmm_flat_kernel, the default whenever the operator carries a tile schedule):
+//   The r01 kernel walked row by row: row_ptr -> (col, val) -> <= 8 gathers, three dependent round trips for a
+//   ~13-entry row, and it ran at 22 G gathers/s while a bare gather of the same index stream sustains 25-38 G/s
+//   (tools/lab/gather_lab.cu: random 256-byte rows stream from HBM at the full copy rate, 6.5 TB/s, through plain
+//   LDG.128; cp.async.bulk / TMA gather4 rings are no faster and lose the L1 hits on hub rows).  What was missing is
+//   issue continuity, not a different data path.  So the short rows are cut into TILES of consecutive rows holding
+//   ~tile_nnz entries; one sub-warp streams a tile's entries in fixed batches of LPR, always UNR gathers in flight,
+//   the (col, val) pairs of batch b+1 requested before the gathers of batch b are issued, and row ends are detected
+//   by comparing the running entry index with a register-cached window of row_ptr (segmented sum; empty rows fall
+//   out of the same comparison).  Columns and values are broadcast through two 128-byte shared-memory slabs per warp,
+//   four per LDS.128, instead of two SHFL per entry.  Hub rows (degree > chunk) keep the chunked path above.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace gcf {
 
@@ -156,13 +169,15 @@ __device__ __forceinline__ void accumulate_multi(const int* __restrict__ col_idx
 
 template <int LPR, int VPL, bool GUARD>
 __device__ __forceinline__ void finish_row(const Epi& ep, long long row, int sl, unsigned mask, int dvec,
-                                           float4 (&acc)[VPL]) {
+                                           float4 (&acc)[VPL], bool active = true) {
+  // `active` = false: the lane only takes part in the shuffles (warp-synchronous callers whose sub-warps hold
+  // different numbers of finished rows); `row` may then be anything
   if (ep.Y != nullptr) {
     float4* y = reinterpret_cast<float4*>(ep.Y + row * ep.ldy);
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int idx = sl + k * LPR;
-      if (!GUARD || idx < dvec) y[idx] = acc[k];
+      if ((!GUARD || idx < dvec) && active) y[idx] = acc[k];
     }
   }
   if (ep.O != nullptr || ep.ad_p != nullptr) {
@@ -180,8 +195,9 @@ __device__ __forceinline__ void finish_row(const Epi& ep, long long row, int sl,
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int idx = sl + k * LPR;
-      if (!GUARD || idx < dvec) {
+      if ((!GUARD || idx < dvec) && active) {
         float4 r = f4_zero();
+#pragma unroll 1
         for (int q = 0; q < ep.n_add; ++q) {
           const float4 z = __ldg(reinterpret_cast<const float4*>(ep.add[q] + row * ep.ldo) + idx);
           f4_fma(r, ep.beta[q], z);
@@ -320,6 +336,206 @@ static int launch(const gcf_csr_t* A, const float* X, long long ldx, int dvec, c
   return GCF_OK;
 }
 
+// ---- flat-stream kernel ------------------------------------------------------------------------------------------
+struct TilePlan { const int2* tiles; int n_tiles; const int* rp; const int* ids; const int* empty_rows; int n_empty; };
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// The epilogue of a row reads rows of other matrices (addends; parameter and moments for the fused Adam).  Waiting for
+// them would stall the warp -- both of its sub-warps -- for a DRAM round trip per output row, so they are requested
+// into L1 when the row is stashed, one group of gathers before the epilogue runs.
+__device__ __forceinline__ void prefetch_epilogue(const Epi& ep, long long row, int sl) {
+  const long long off = row * ep.ldo + sl * 4;
+#pragma unroll 1
+  for (int q = 0; q < ep.n_add; ++q) prefetch_l1(ep.add[q] + off);
+  if (ep.ad_p != nullptr) { prefetch_l1(ep.ad_p + off); prefetch_l1(ep.ad_m + off); prefetch_l1(ep.ad_v + off); }
+}
+
+// Rows are addressed in the COMPACT numbering of the non-empty rows (tp.rp = their row pointer, tp.ids = their row
+// ids, NULL when no row is empty): every row of a tile then has at least one entry, so at most LPR rows end inside a
+// batch of LPR entries and they all sit in one LPR-wide window of tp.rp: lane t of a sub-warp looks at row k + t and,
+// if that row ends inside the batch, writes "row id + 1" at the batch position of its last entry (mark slab).  The
+// window of the NEXT batch is requested as soon as the number of rows ending in this one is known (a ballot), i.e.
+// a whole batch before it is needed; the same holds for the (col, val) pairs.  Nothing the gathers depend on is ever
+// waited for: per batch the sub-warp exposes one memory round trip per group of UNR gathers and nothing else.
+//
+// The kernel is warp-synchronous: the RPW sub-warps of a warp stream different tiles but run the same number of
+// batches (the longer tile's; tiles hold tile_nnz .. tile_nnz + chunk entries), so every barrier and shuffle uses the
+// full mask.
+//
+// STASH = false: the epilogue is a plain store of the row (Y only) and is issued on the spot.
+// STASH = true : completed rows are parked in shared memory (each lane keeps its own float4 slice) and the full
+//                epilogue -- linear combination with addends, row-L2-normalise, fused Adam -- runs between two groups
+//                of gathers, where no gathered row is live in registers; at most UNR rows complete per group.
+template <int LPR, int UNR, bool GUARD, bool STASH, int MINB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
+spmm_flat_kernel(const int* __restrict__ col_idx, const float* __restrict__ vals, const float* __restrict__ X,
+                 long long ldx, int dvec, const __grid_constant__ Epi ep, LongPlan lp, const int* __restrict__ row_ptr,
+                 int long_blocks, int tile_blocks, TilePlan tp) {
+  constexpr int RPW = 32 / LPR;
+  constexpr int SLOTS = STASH ? UNR : 1;
+  constexpr unsigned kFull = 0xffffffffu;
+  static_assert(LPR % UNR == 0 && UNR % 4 == 0, "batches are consumed UNR gathers at a time, four columns per LDS.128");
+  __shared__ __align__(16) int col_slab[kWarpsPerBlock][32];
+  __shared__ __align__(16) float val_slab[kWarpsPerBlock][32];
+  __shared__ __align__(16) int mark_slab[kWarpsPerBlock][32];
+  __shared__ __align__(16) float4 stash[STASH ? kWarpsPerBlock : 1][SLOTS][32];
+  __shared__ int stash_row[STASH ? kWarpsPerBlock : 1][SLOTS][RPW];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR;
+  const int sl = lane % LPR;
+  const unsigned mask = (LPR == 32) ? kFull : (((1u << LPR) - 1u) << (sub * LPR));
+
+  if ((int)blockIdx.x < long_blocks) {
+    float4 acc[1] = {f4_zero()};
+    long_chunk_path<LPR, 1, (UNR > 8 ? 8 : UNR), GUARD, 1>(row_ptr, col_idx, vals, X, ldx, dvec, ep, lp, warp, lane, sub, sl, mask, acc);
+    return;
+  }
+  if ((int)blockIdx.x >= long_blocks + tile_blocks) {
+    // rows without entries: the epilogue of a zero sum
+    const int q = (((int)blockIdx.x - long_blocks - tile_blocks) * kWarpsPerBlock + warp) * RPW + sub;
+    if (q >= tp.n_empty) return;
+    float4 acc[1] = {f4_zero()};
+    finish_row<LPR, 1, GUARD>(ep, __ldg(tp.empty_rows + q), sl, mask, dvec, acc);
+    return;
+  }
+  const int tile = (((int)blockIdx.x - long_blocks) * kWarpsPerBlock + warp) * RPW + sub;
+  const bool has_tile = tile < tp.n_tiles;
+  int k = 0, k1 = 0, j = 0, jend = 0;      // running / last compact row, running / last entry
+  if (has_tile) {
+    const int2 kk = __ldg(tp.tiles + tile);
+    k = kk.x;
+    k1 = kk.y;
+    j = __ldg(tp.rp + k);
+    jend = __ldg(tp.rp + k1);
+  }
+  int nb = (jend - j + LPR - 1) / LPR;     // batches of this sub-warp; the warp runs the longest
+  if (RPW > 1) nb = __reduce_max_sync(kFull, nb);
+  const int* cs = &col_slab[warp][sub * LPR];
+  const float* vs = &val_slab[warp][sub * LPR];
+  const int* ms = &mark_slab[warp][sub * LPR];
+  const bool col_ok = !GUARD || sl < dvec;
+  const float4* Xl = reinterpret_cast<const float4*>(X) + sl;   // this lane's float4 column of X
+  const unsigned ldx4 = (unsigned)(ldx >> 2);   // 32 x 32 -> 64-bit address products (one IMAD.WIDE.U32 each)
+  const unsigned ldy4 = (unsigned)(ep.ldy >> 2);
+  const bool renumbered = tp.ids != nullptr;
+
+  // (col, val) of batch 0 and the row window of batch 0.  Slots past the tile's last entry repeat its last column
+  // with weight 0: their gathers hit L1 and cannot bring a non-finite value into a row that does not already hold it.
+  int c = 0, my_end = 0, my_row = 0;
+  float v = 0.f;
+  if (has_tile) {
+    const int jj = min(j + sl, jend - 1);
+    c = ld_stream_i32(col_idx + jj);
+    if (j + sl < jend) v = ld_stream_f32(vals + jj);
+    my_end = __ldg(tp.rp + min(k + 1 + sl, k1));
+    my_row = renumbered ? __ldg(tp.ids + min(k + sl, k1 - 1)) : k + sl;
+  }
+  float4 acc = f4_zero();
+  for (int b = 0; b < nb; ++b, j += LPR) {
+    const int cnt = max(0, min(LPR, jend - j));
+    __syncwarp();                          // the previous batch has been read out of the slabs
+    col_slab[warp][lane] = c;
+    val_slab[warp][lane] = v;
+    mark_slab[warp][lane] = 0;
+    __syncwarp();
+    v = 0.f;
+    if (j + LPR < jend) {                  // (col, val) of the next batch
+      const int jj = min(j + LPR + sl, jend - 1);
+      c = ld_stream_i32(col_idx + jj);
+      if (j + LPR + sl < jend) v = ld_stream_f32(vals + jj);
+    }
+    float4 x[UNR];
+#pragma unroll
+    for (int t0 = 0; t0 < LPR; t0 += UNR) {
+      if (t0 < cnt) {
+#pragma unroll
+        for (int u = 0; u < UNR; u += 4) {
+          const int4 cc = *reinterpret_cast<const int4*>(cs + t0 + u);   // four columns per broadcast LDS.128
+          x[u + 0] = col_ok ? __ldg(Xl + (unsigned long long)(unsigned)cc.x * ldx4) : f4_zero();
+          x[u + 1] = col_ok ? __ldg(Xl + (unsigned long long)(unsigned)cc.y * ldx4) : f4_zero();
+          x[u + 2] = col_ok ? __ldg(Xl + (unsigned long long)(unsigned)cc.z * ldx4) : f4_zero();
+          x[u + 3] = col_ok ? __ldg(Xl + (unsigned long long)(unsigned)cc.w * ldx4) : f4_zero();
+        }
+      }
+      if (t0 == 0) {
+        // with the first gathers in flight: rows that end inside this batch, and the window of the next one
+        const int pos = my_end - 1 - j;
+        const bool ends_here = has_tile && k + sl < k1 && pos < LPR;
+        if (ends_here) mark_slab[warp][sub * LPR + pos] = my_row + 1;
+        const unsigned done = __ballot_sync(kFull, ends_here) & mask;
+        k += __popc(done);
+        if (has_tile) {
+          my_end = __ldg(tp.rp + min(k + 1 + sl, k1));
+          my_row = renumbered ? __ldg(tp.ids + min(k + sl, k1 - 1)) : k + sl;
+        }
+        __syncwarp();
+      }
+      int ns = 0;                          // rows parked in the stash by this group
+      if (t0 < cnt) {
+#pragma unroll
+        for (int u = 0; u < UNR; u += 4) {
+          const float4 ww = *reinterpret_cast<const float4*>(vs + t0 + u);
+          const int4 mm = *reinterpret_cast<const int4*>(ms + t0 + u);
+          const float w[4] = {ww.x, ww.y, ww.z, ww.w};
+          const int m[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            f4_fma(acc, w[q], x[u + q]);
+            if (m[q] != 0) {               // last entry of row m - 1
+              if constexpr (STASH) {
+                stash[warp][ns][lane] = acc;
+                stash_row[warp][ns][sub] = m[q] - 1;
+                if (col_ok) prefetch_epilogue(ep, m[q] - 1, sl);
+                ++ns;
+              } else {
+                if (col_ok) (reinterpret_cast<float4*>(ep.Y) + sl)[(unsigned long long)(unsigned)(m[q] - 1) * ldy4] = acc;
+              }
+              acc = f4_zero();
+            }
+          }
+        }
+      }
+      if constexpr (STASH) {
+        const int ns_max = (RPW > 1) ? __reduce_max_sync(kFull, ns) : ns;
+#pragma unroll 1
+        for (int i = 0; i < ns_max; ++i) {
+          const bool active = i < ns;
+          float4 a[1] = {stash[warp][active ? i : 0][lane]};
+          finish_row<LPR, 1, GUARD>(ep, stash_row[warp][active ? i : 0][sub], sl, kFull, dvec, a, active);
+        }
+      }
+    }
+  }
+}
+
+template <int LPR, int UNR, bool GUARD, bool STASH, int MINB>
+static int launch_flat(const gcf_csr_t* A, const float* X, long long ldx, int dvec, const Epi& ep, const LongPlan& lp,
+                       cudaStream_t st) {
+  constexpr int RPW = 32 / LPR;
+  const int long_blocks = (int)cdiv(lp.n_chunks, kWarpsPerBlock);
+  const long long tile_blocks = cdiv(A->n_tiles, (long long)kWarpsPerBlock * RPW);
+  const long long empty_blocks = cdiv(A->n_empty, (long long)kWarpsPerBlock * RPW);
+  const long long grid = long_blocks + tile_blocks + empty_blocks;
+  if (grid <= 0) return GCF_OK;
+  GCF_REQUIRE(grid < 2147483647LL, "gcf_spmm_csr_f32: grid too large");
+  TilePlan tp{reinterpret_cast<const int2*>(A->tiles), A->n_tiles, A->n_empty > 0 ? A->nz_row_ptr : A->row_ptr,
+              A->n_empty > 0 ? A->nz_rows : nullptr, A->empty_rows, A->n_empty};
+  static const int pad_smem = getenv("GCF_SPMM_PAD_SMEM") ? atoi(getenv("GCF_SPMM_PAD_SMEM")) : 0;   // L1-capacity probe
+  spmm_flat_kernel<LPR, UNR, GUARD, STASH, MINB><<<(unsigned)grid, kWarpsPerBlock * 32, pad_smem, st>>>(
+      A->col_idx, A->vals, X, ldx, dvec, ep, lp, A->row_ptr, long_blocks, (int)tile_blocks, tp);
+  GCF_LAUNCH_CHECK("spmm_flat_kernel");
+  return GCF_OK;
+}
+
+template <int LPR, int UNR, bool GUARD, int MINB>
+static int launch_flat_cls(bool plain, const gcf_csr_t* A, const float* X, long long ldx, int dvec, const Epi& ep,
+                           const LongPlan& lp, cudaStream_t st) {
+  if (plain) return launch_flat<LPR, UNR, GUARD, false, MINB>(A, X, ldx, dvec, ep, lp, st);
+  return launch_flat<LPR, (UNR > 8 ? 8 : UNR), GUARD, true, MINB>(A, X, ldx, dvec, ep, lp, st);   // stash: UNR slots of a row each
+}
+
 __global__ void axpby_kernel(float4* __restrict__ out, const float4* __restrict__ a, float sa,
                              const float4* __restrict__ b, float sb, long long n4) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -408,6 +624,29 @@ static int spmm_impl(const gcf_csr_t* A, int32_t d, const float* X, int64_t ldx,
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int dvec = d / 4;
+  // flat-stream kernel: default whenever the operator carries a tile schedule and a row fits one float4 per lane.
+  // variant 0 = default, 4 = the r01 row-walking kernel (kept for A/B runs), 10.. = flat-kernel tuning points
+  if (A->n_tiles > 0 && A->tiles != nullptr && d >= 36 && d <= 128 && (variant == 0 || variant >= 10)) {
+    GCF_REQUIRE(A->n_empty == 0 || (A->empty_rows != nullptr && A->nz_row_ptr != nullptr && A->nz_rows != nullptr),
+                "gcf_spmm_csr_f32: operator has empty rows but no compact row numbering");
+    const bool plain = adam == nullptr && epilogue == GCF_EPILOGUE_NONE && OUT == nullptr;   // Y = A X and nothing else
+    // measured on cfg1 / cfg5 (profiles/r02_exp_spmm_*.log): 8 gathers in flight per sub-warp at 3 CTAs / SM
+    if (d == 64) {
+      if (variant == 10) return launch_flat_cls<16, 8, false, 4>(plain, A, X, ldx, dvec, ep, lp, st);
+      if (variant == 11) return launch_flat_cls<16, 16, false, 3>(plain, A, X, ldx, dvec, ep, lp, st);
+      if (variant == 13) return launch_flat_cls<16, 4, false, 5>(plain, A, X, ldx, dvec, ep, lp, st);
+      if (variant == 14) return launch_flat_cls<16, 16, false, 2>(plain, A, X, ldx, dvec, ep, lp, st);
+      return launch_flat_cls<16, 8, false, 3>(plain, A, X, ldx, dvec, ep, lp, st);
+    }
+    if (d == 128) {
+      if (variant == 10) return launch_flat_cls<32, 8, false, 4>(plain, A, X, ldx, dvec, ep, lp, st);
+      if (variant == 11) return launch_flat_cls<32, 16, false, 3>(plain, A, X, ldx, dvec, ep, lp, st);
+      return launch_flat_cls<32, 8, false, 3>(plain, A, X, ldx, dvec, ep, lp, st);
+    }
+    if (d <= 64) return launch_flat_cls<16, 8, true, 3>(plain, A, X, ldx, dvec, ep, lp, st);
+    return launch_flat_cls<32, 8, true, 3>(plain, A, X, ldx, dvec, ep, lp, st);
+  }
+  if (variant == 4) variant = 0;
   switch (d) {
     // feature-sharded slices (d / G columns per rank).  Measured on the cfg5 graph (profiles/r01_exp_narrow_cfg5.log):
     // d=8 4.23 -> 2.55 ms, d=16 4.65 -> 3.70 ms with 8 gathers in flight per sub-warp; d=32 6.85 -> 5.59 ms at 4 CTAs/SM

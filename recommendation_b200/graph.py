@@ -61,6 +61,49 @@ def plan_long_rows(row_ptr: np.ndarray, chunk: int) -> LongRowPlan:
     return LongRowPlan(chunk, long_rows, long_chunk_ptr.astype(np.int32), chunk_long.astype(np.int32))
 
 
+def default_tile_nnz(nnz_short: int) -> int:
+    """Entries per tile of the flat-stream SpMM: ~512 on large operators (the per-tile prologue -- tile -> row_ptr ->
+    first (col, val) batch -- is amortised over 32 batches), smaller on small ones so that every SM still gets
+    several tiles per resident sub-warp (148 SMs x 4 CTAs x 16 sub-warps x 2 waves)."""
+    env = os.environ.get("GCF_SPMM_TILE")
+    if env:
+        return max(16, int(env))
+    t = nnz_short // (148 * 4 * 16 * 2)
+    return int(min(512, max(64, (t + 15) // 16 * 16)))
+
+
+def plan_tiles(row_ptr: np.ndarray, chunk: int, tile_nnz: int):
+    """Flat-stream schedule (pure numpy).  Returns (tiles, nz_rows, nz_row_ptr, empty_rows):
+
+    * nz_rows int32 [n_nz]: ids of the rows with at least one entry (the COMPACT row numbering), nz_row_ptr int32
+      [n_nz + 1] their row pointer, empty_rows int32 the other rows;
+    * tiles int32 [n_tiles, 2] = (first, one-past-last) compact row of each tile.  Tiles are runs of consecutive
+      compact rows of degree <= chunk (long rows belong to the chunk schedule and end a run); a run is cut wherever
+      the running entry count of its rows crosses a multiple of tile_nnz, so a tile holds fewer than
+      tile_nnz + chunk entries."""
+    row_ptr = np.asarray(row_ptr, dtype=np.int64)
+    deg_all = np.diff(row_ptr)
+    nz_rows = np.nonzero(deg_all > 0)[0]
+    empty_rows = np.nonzero(deg_all == 0)[0].astype(np.int32)
+    nz_row_ptr = np.concatenate((row_ptr[nz_rows], row_ptr[-1:])) if nz_rows.size else np.zeros(1, np.int64)
+    deg = deg_all[nz_rows]
+    n = deg.shape[0]
+    short = deg <= chunk
+    if n == 0 or not short.any():
+        return np.zeros((0, 2), dtype=np.int32), nz_rows.astype(np.int32), nz_row_ptr.astype(np.int32), empty_rows
+    start_short = np.concatenate(([0], np.cumsum(np.where(short, deg, 0))[:-1]))   # short entries before each row
+    bucket = start_short // max(int(tile_nnz), 1)
+    prev_short = np.concatenate(([False], short[:-1]))
+    prev_bucket = np.concatenate(([-1], bucket[:-1]))
+    is_start = short & (~prev_short | (bucket != prev_bucket))
+    starts = np.nonzero(is_start)[0]
+    # a tile ends at the next tile start or at the next long row, whichever comes first
+    stops = np.concatenate((np.nonzero(is_start | ~short)[0], [n]))
+    ends = stops[np.searchsorted(stops, starts, side="right")]
+    tiles = np.stack((starts, ends), axis=1).astype(np.int32)
+    return tiles, nz_rows.astype(np.int32), nz_row_ptr.astype(np.int32), empty_rows
+
+
 def _require_cuda(t: torch.Tensor, name: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor: recommendation_b200 has no CPU path")
@@ -71,7 +114,7 @@ class CSRGraph:
 
     def __init__(self, row_ptr: torch.Tensor, col_idx: torch.Tensor, vals: torch.Tensor, n_rows: int, n_cols: int,
                  *, symmetric: bool = False, chunk: Optional[int] = None, rowsum: Optional[torch.Tensor] = None,
-                 dinv: Optional[torch.Tensor] = None):
+                 dinv: Optional[torch.Tensor] = None, tile_nnz: Optional[int] = None):
         for name, t, dt in (("row_ptr", row_ptr, torch.int32), ("col_idx", col_idx, torch.int32), ("vals", vals, torch.float32)):
             _require_cuda(t, name)
             if t.dtype != dt or not t.is_contiguous():
@@ -87,8 +130,22 @@ class CSRGraph:
         self._transpose: Optional["CSRGraph"] = None
         self._workspaces: Dict[int, torch.Tensor] = {}
         self.chunk = DEFAULT_CHUNK if chunk is None else int(chunk)
-        plan = plan_long_rows(row_ptr.cpu().numpy(), self.chunk)
+        row_ptr_host = row_ptr.cpu().numpy()
+        plan = plan_long_rows(row_ptr_host, self.chunk)
         self.plan = plan
+        n_short = self.nnz - int(np.diff(row_ptr_host.astype(np.int64))[plan.long_rows].sum()) if plan.n_long else self.nnz
+        self.tile_nnz = default_tile_nnz(n_short) if tile_nnz is None else int(tile_nnz)
+        if self.tile_nnz > 0 and self.nnz > 0:
+            tiles, nz_rows, nz_row_ptr, empty = plan_tiles(row_ptr_host, self.chunk, self.tile_nnz)
+        else:
+            tiles, nz_rows, nz_row_ptr, empty = np.zeros((0, 2), np.int32), np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32)
+        self.n_tiles = int(tiles.shape[0])
+        self.n_empty = int(empty.shape[0]) if self.n_tiles else 0
+        self._tiles = torch.from_numpy(np.ascontiguousarray(tiles)).to(self.device)
+        self._empty_rows = torch.from_numpy(empty).to(self.device) if self.n_empty else None
+        # the compact numbering is the plain one when no row is empty
+        self._nz_rows = torch.from_numpy(nz_rows).to(self.device) if self.n_empty else None
+        self._nz_row_ptr = torch.from_numpy(nz_row_ptr).to(self.device) if self.n_empty else None
         self._long_rows = torch.from_numpy(plan.long_rows).to(self.device)
         self._long_chunk_ptr = torch.from_numpy(plan.long_chunk_ptr).to(self.device)
         self._chunk_long = torch.from_numpy(plan.chunk_long).to(self.device)
@@ -100,12 +157,15 @@ class CSRGraph:
             long_rows=self._long_rows.data_ptr() if plan.n_long else None,
             long_chunk_ptr=self._long_chunk_ptr.data_ptr() if plan.n_long else None,
             chunk_long=self._chunk_long.data_ptr() if plan.n_long else None,
+            tiles=self._tiles.data_ptr() if self.n_tiles else None, n_tiles=self.n_tiles, n_empty=self.n_empty,
+            empty_rows=_lib.ptr(self._empty_rows), nz_row_ptr=_lib.ptr(self._nz_row_ptr), nz_rows=_lib.ptr(self._nz_rows),
         )
 
     # ---- construction ---------------------------------------------------------------------
     @classmethod
     def from_coo(cls, rows: torch.Tensor, cols: torch.Tensor, vals: Optional[torch.Tensor], n_rows: int, n_cols: int,
-                 *, norm: str = "none", symmetric: bool = False, chunk: Optional[int] = None) -> "CSRGraph":
+                 *, norm: str = "none", symmetric: bool = False, chunk: Optional[int] = None,
+                 tile_nnz: Optional[int] = None) -> "CSRGraph":
         """COO (int64 indices, duplicates allowed) -> canonical CSR, then value normalisation."""
         if norm not in _NORM_CODES:
             raise ValueError(f"norm must be one of {sorted(_NORM_CODES)}")
@@ -146,11 +206,12 @@ class CSRGraph:
             _lib.check(lib.gcf_norm_values(_NORM_CODES[norm], _lib.ptr(row_ptr), _lib.ptr(col_idx), _lib.ptr(out_vals),
                                            n_rows, n_cols, _lib.ptr(normed), _lib.ptr(rowsum), _lib.ptr(dinv), stream),
                        "gcf_norm_values")
-        return cls(row_ptr, col_idx, normed, n_rows, n_cols, symmetric=symmetric, chunk=chunk, rowsum=rowsum, dinv=dinv)
+        return cls(row_ptr, col_idx, normed, n_rows, n_cols, symmetric=symmetric, chunk=chunk, rowsum=rowsum, dinv=dinv,
+                   tile_nnz=tile_nnz)
 
     @classmethod
     def from_edge_index(cls, edge_index: torch.Tensor, num_nodes: int, *, norm: str = "sym",
-                        symmetric: bool = True, chunk: Optional[int] = None) -> "CSRGraph":
+                        symmetric: bool = True, chunk: Optional[int] = None, tile_nnz: Optional[int] = None) -> "CSRGraph":
         """edge_index [2, E'] (PyG convention: message flows row -> col, out[col] += w * x[row]).
 
         The operator applied to X is therefore M with M[col, row] = w, i.e. CSR rows = edge_index[1].
@@ -159,11 +220,11 @@ class CSRGraph:
         if edge_index.dim() != 2 or edge_index.shape[0] != 2:
             raise ValueError("edge_index must have shape [2, E]")
         return cls.from_coo(edge_index[1], edge_index[0], None, num_nodes, num_nodes, norm=norm,
-                            symmetric=symmetric, chunk=chunk)
+                            symmetric=symmetric, chunk=chunk, tile_nnz=tile_nnz)
 
     @classmethod
     def from_pairs(cls, users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int, *, norm: str = "sym",
-                   chunk: Optional[int] = None) -> "CSRGraph":
+                   chunk: Optional[int] = None, tile_nnz: Optional[int] = None) -> "CSRGraph":
         """Bipartite user-item pairs -> symmetric (U+I)x(U+I) adjacency [[0,R],[R^T,0]]."""
         lib = _lib.load()
         _require_cuda(users, "users")
@@ -175,11 +236,11 @@ class CSRGraph:
         _lib.check(lib.gcf_bipartite_edge_index(_lib.ptr(users), _lib.ptr(items), e, n_users, _lib.ptr(rows), _lib.ptr(cols),
                                                 _lib.current_stream()), "gcf_bipartite_edge_index")
         n = n_users + n_items
-        return cls.from_coo(rows, cols, None, n, n, norm=norm, symmetric=True, chunk=chunk)
+        return cls.from_coo(rows, cols, None, n, n, norm=norm, symmetric=True, chunk=chunk, tile_nnz=tile_nnz)
 
     @classmethod
     def from_scipy(cls, mat, *, norm: str = "none", device: Optional[torch.device] = None,
-                   symmetric: Optional[bool] = None, chunk: Optional[int] = None) -> "CSRGraph":
+                   symmetric: Optional[bool] = None, chunk: Optional[int] = None, tile_nnz: Optional[int] = None) -> "CSRGraph":
         """Any scipy.sparse matrix (the reference's `data.norm_adj`); COO triplets are uploaded as they are
         (duplicates kept, like convert_sparse_mat_to_tensor) and canonicalised on the GPU."""
         coo = mat.tocoo()
@@ -193,7 +254,7 @@ class CSRGraph:
             if n_rows == n_cols:
                 diff = (mat - mat.T)
                 symmetric = diff.nnz == 0 or float(abs(diff).max()) == 0.0
-        return cls.from_coo(rows, cols, vals, n_rows, n_cols, norm=norm, symmetric=symmetric, chunk=chunk)
+        return cls.from_coo(rows, cols, vals, n_rows, n_cols, norm=norm, symmetric=symmetric, chunk=chunk, tile_nnz=tile_nnz)
 
     # ---- derived operators ----------------------------------------------------------------
     def transpose(self) -> "CSRGraph":

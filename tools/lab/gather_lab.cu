@@ -1,0 +1,375 @@
+// gather_lab: which data path delivers random 256-byte embedding rows fastest on a B200?
+//
+// Development probe behind the r02 SpMM redesign (not part of libgcf).  One index stream of M entries (uniform, or the
+// two halves of the cfg5 operator: Zipf(0.8) over the 5 M item rows, Zipf(0.6) over the 10 M user rows) is gathered out
+// of a [N, 64] fp32 table by
+//   ldg   : 16-lane sub-warps, UNR independent 128-bit LDG in flight (the r01 kernel's inner loop without the CSR walk)
+//   bulk  : one cp.async.bulk (256 B) per row into a shared-memory ring, mbarrier complete_tx, consumer warps read smem
+//   g4    : cp.async.bulk.tensor.2d tile::gather4 (4 rows per instruction) into the same ring
+// Every variant accumulates the gathered rows and writes one 256-byte row per 16 gathers, so the arithmetic and the
+// output stream are those of an SpMM with 16-entry rows.  A checksum guards against a path that does not move the data.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o gather_lab gather_lab.cu
+//   ./gather_lab [M millions=100] [which=all]
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include <cmath>
+
+#define CK(x)                                                                                  \
+  do {                                                                                         \
+    cudaError_t e_ = (x);                                                                      \
+    if (e_ != cudaSuccess) {                                                                   \
+      fprintf(stderr, "%s:%d %s -> %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_));     \
+      exit(1);                                                                                 \
+    }                                                                                          \
+  } while (0)
+
+constexpr int D = 64;            // floats per row
+constexpr int ROW_BYTES = D * 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* m, int c0, int r0, int r1, int r2, int r3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+          smem_u32(dst)),
+      "l"(m), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ uint64_t pol_evict_last() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t pol_evict_first() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t pol_no_alloc() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ int ld_stream_i32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void f4_acc(float4& a, const float4& x) { a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// index streams
+__device__ __forceinline__ uint64_t splitmix(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+// mode 0: uniform over [base, base+n); mode 1: continuous power law p(k) ~ k^-alpha over ranks 1..n (rank 1 = row base)
+__global__ void make_idx(int* idx, long long m, int base, int n, int mode, float alpha, uint64_t seed) {
+  const double ia = 1.0 - alpha;
+  const double top = pow((double)n, ia) - 1.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+    const uint64_t h = splitmix(seed * 0x100000001B3ull + i);
+    const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+    int k;
+    if (mode == 0) k = (int)(u * n);
+    else k = (int)(pow(u * top + 1.0, 1.0 / ia)) - 1;
+    k = min(max(k, 0), n - 1);
+    idx[i] = base + k;
+  }
+}
+__global__ void fill_table(float* x, long long n_elems) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / D;
+    x[i] = (float)((row * 2654435761ull + (i % D) * 40503ull) % 1021) * (1.0f / 1021.f);  // cheap, row-dependent
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ldg: sub-warp of 16 lanes per group of 16 gathers; UNR independent LDG.128 in flight
+template <int UNR, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_ldg(const int* __restrict__ idx, long long m, const float* __restrict__ X,
+                                                   float* __restrict__ Y) {
+  const int lane = threadIdx.x & 31, sl = lane & 15;
+  const long long n_groups = m / 16;
+  const long long sub0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const long long n_sub = ((long long)gridDim.x * blockDim.x) >> 4;
+  const unsigned mask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
+  for (long long g = sub0; g < n_groups; g += n_sub) {
+    const int c = ld_stream_i32(idx + g * 16 + sl);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t0 = 0; t0 < 16; t0 += UNR) {
+      float4 x[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int ct = __shfl_sync(mask, c, t0 + u, 16);
+        x[u] = __ldg(reinterpret_cast<const float4*>(X + (long long)ct * D) + sl);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) f4_acc(acc, x[u]);
+    }
+    reinterpret_cast<float4*>(Y + g * D)[sl] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bulk / gather4: warp 0 produces, warps 1..C consume.  A stage holds 32 rows (8 KB).
+//   MODE 0: cp.async.bulk per row     MODE 1: gather4     HINT: 0 none, 1 hub evict_last / cold evict_first, 2 all evict_first
+template <int STAGES, int PROD, int CONS, int MODE, int HINT, bool CONSUME>
+__global__ void __launch_bounds__((CONS + PROD) * 32, 1)
+k_ring(const int* __restrict__ idx, long long m, const float* __restrict__ X, float* __restrict__ Y,
+       const __grid_constant__ CUtensorMap tmap, int hub_lo, int hub_hi) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float* ring = reinterpret_cast<float*>(smem_raw);                       // STAGES * 32 * 64 floats
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * 32 * ROW_BYTES);
+  uint64_t* empty = full + STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // stage groups of 32 entries, CTA-strided
+  const long long n_groups = m / 32;
+  const long long per = (n_groups + gridDim.x - 1) / gridDim.x;
+  const long long g0 = (long long)blockIdx.x * per;
+  const long long g1 = min(n_groups, g0 + per);
+  if (g0 >= g1) return;
+  if (warp < PROD) {
+    uint64_t p_last = 0, p_first = 0;
+    if (HINT != 0) { p_last = pol_evict_last(); p_first = pol_evict_first(); }
+    if (g0 + warp >= g1) return;
+    int c_next = ld_stream_i32(idx + (g0 + warp) * 32 + lane);
+    long long it = warp;
+    for (long long g = g0 + warp; g < g1; g += PROD, it += PROD) {
+      const int s = (int)(it % STAGES);
+      const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+      const int c = c_next;
+      if (g + PROD < g1) c_next = ld_stream_i32(idx + (g + PROD) * 32 + lane);
+      if (it >= STAGES) mbar_wait(empty + s, ph ^ 1);
+      if (lane == 0) mbar_expect_tx(full + s, 32 * ROW_BYTES);
+      __syncwarp();
+      float* dst = ring + ((size_t)s * 32 + lane) * D;
+      if (MODE == 0) {
+        const float* src = X + (long long)c * D;
+        if (HINT == 0) bulk_g2s(dst, src, ROW_BYTES, full + s);
+        else if (HINT == 1) bulk_g2s_hint(dst, src, ROW_BYTES, full + s, (c >= hub_lo && c < hub_hi) ? p_last : p_first);
+        else bulk_g2s_hint(dst, src, ROW_BYTES, full + s, p_first);
+      } else {
+        const int r1 = __shfl_down_sync(0xffffffffu, c, 1);
+        const int r2 = __shfl_down_sync(0xffffffffu, c, 2);
+        const int r3 = __shfl_down_sync(0xffffffffu, c, 3);
+        if ((lane & 3) == 0) tma_gather4(dst, &tmap, 0, c, r1, r2, r3, full + s);
+      }
+    }
+  } else if (CONSUME) {
+    const int cw = warp - PROD;
+    const int sl = lane & 15, sub = lane >> 4;
+    long long it = cw;
+    for (long long g = g0 + cw; g < g1; g += CONS, it += CONS) {
+      const int s = (int)(it % STAGES);
+      const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+      mbar_wait(full + s, ph);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* base = reinterpret_cast<const float4*>(ring + ((size_t)s * 32 + sub * 16) * D) + sl;
+#pragma unroll
+      for (int t = 0; t < 16; ++t) f4_acc(acc, base[t * (D / 4)]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+      reinterpret_cast<float4*>(Y + (g * 2 + sub) * D)[sl] = acc;
+    }
+  } else {
+    // no consumer: one thread recycles the stages
+    if (warp == PROD && lane == 0) {
+      long long it = 0;
+      for (long long g = g0; g < g1; ++g, ++it) {
+        const int s = (int)(it % STAGES);
+        mbar_wait(full + s, (uint32_t)((it / STAGES) & 1));
+        mbar_arrive(empty + s);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool make_tmap(CUtensorMap* map, const float* base, long long rows) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+    return false;
+  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ROW_BYTES};
+  cuuint32_t box[2] = {(cuuint32_t)D, 1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(p)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides,
+                                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { fprintf(stderr, "cuTensorMapEncodeTiled -> %d\n", (int)r); return false; }
+  return true;
+}
+
+static int g_reps = 5;
+struct Ctx {
+  const int* idx; long long m; const float* X; float* Y; CUtensorMap tmap; int hub_lo, hub_hi; int sms;
+  double ref_sum;
+};
+
+static double checksum(const float* Y, long long rows) {
+  // sample 4096 output rows
+  std::vector<float> h(D);
+  double s = 0;
+  for (int k = 0; k < 4096; ++k) {
+    long long r = (rows / 4096) * k;
+    CK(cudaMemcpy(h.data(), Y + r * D, ROW_BYTES, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < D; ++j) s += h[j];
+  }
+  return s;
+}
+
+template <typename F>
+static void run(const char* name, Ctx& c, F launch) {
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaMemset(c.Y, 0, (size_t)(c.m / 16) * ROW_BYTES));
+  launch();
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) { printf("%-44s FAILED: %s\n", name, cudaGetErrorString(err)); fflush(stdout); exit(2); }
+  const double cs = checksum(c.Y, c.m / 16);
+  float best = 1e30f, tot = 0;
+  const int reps = g_reps;
+  for (int r = 0; r < reps; ++r) {
+    CK(cudaEventRecord(e0));
+    launch();
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms); tot += ms;
+  }
+  const double gb = (double)c.m * ROW_BYTES / 1e9;
+  printf("%-44s best %7.3f ms  mean %7.3f ms  gathered %6.0f GB/s  %5.2f Grows/s  checksum %s (%.6g)\n", name, best, tot / reps,
+         gb / (best * 1e-3), c.m / (best * 1e-3) / 1e9,
+         (c.ref_sum == 0 || fabs(cs - c.ref_sum) <= 1e-3 * fabs(c.ref_sum)) ? "ok" : "MISMATCH", cs);
+  fflush(stdout);
+  if (c.ref_sum == 0) c.ref_sum = cs;
+}
+
+template <int STAGES, int PROD, int CONS, int MODE, int HINT, bool CONSUME>
+static void run_ring(const char* name, Ctx& c, int ctas_per_sm) {
+  auto kern = k_ring<STAGES, PROD, CONS, MODE, HINT, CONSUME>;
+  const size_t smem = (size_t)STAGES * 32 * ROW_BYTES + 2 * STAGES * sizeof(uint64_t);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  char nm[128];
+  snprintf(nm, sizeof nm, "%s st=%d prod=%d cons=%d x%d/SM", name, STAGES, PROD, CONS, ctas_per_sm);
+  const double keep = c.ref_sum;
+  if (!CONSUME) c.ref_sum = 0;  // nothing is written: checksum meaningless
+  run(nm, c, [&] { kern<<<c.sms * ctas_per_sm, (CONS + PROD) * 32, smem>>>(c.idx, c.m, c.X, c.Y, c.tmap, c.hub_lo, c.hub_hi); });
+  if (!CONSUME) c.ref_sum = keep;
+}
+
+int main(int argc, char** argv) {
+  const long long M = (argc > 1 ? atoll(argv[1]) : 100) * 1000000LL / 32 * 32;
+  const char* which = argc > 2 ? argv[2] : "all";
+  if (argc > 3) g_reps = atoi(argv[3]);
+  const long long N = 15000000, U = 10000000, I = 5000000;
+  int sms = 148;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  float* X; float* Y; int* idx;
+  CK(cudaMalloc(&X, (size_t)N * ROW_BYTES));
+  CK(cudaMalloc(&Y, (size_t)(M / 16) * ROW_BYTES));
+  CK(cudaMalloc(&idx, (size_t)M * 4));
+  fill_table<<<sms * 8, 256>>>(X, N * D);
+  CK(cudaDeviceSynchronize());
+  Ctx c;
+  c.idx = idx; c.m = M; c.X = X; c.Y = Y; c.sms = sms; c.ref_sum = 0;
+  if (!make_tmap(&c.tmap, X, N)) { fprintf(stderr, "no tensor map\n"); memset(&c.tmap, 0, sizeof c.tmap); }
+  auto want = [&](const char* k) { return strcmp(which, "all") == 0 || strstr(which, k) != nullptr; };
+
+  struct Stream { const char* name; int base, n, mode; float alpha; int hub; };
+  const Stream streams[3] = {{"uniform over 15M rows (3.84 GB)", 0, (int)N, 0, 0.f, 0},
+                             {"item rows, Zipf 0.8 over 5M (1.28 GB)", (int)U, (int)I, 1, 0.8f, 300000},
+                             {"user rows, Zipf 0.6 over 10M (2.56 GB)", 0, (int)U, 1, 0.6f, 300000}};
+  for (int si = 0; si < 3; ++si) {
+    const Stream& s = streams[si];
+    char tag[8]; snprintf(tag, sizeof tag, "s%d", si);
+    const bool any_stream = strstr(which, "s0") || strstr(which, "s1") || strstr(which, "s2");
+    if (any_stream && !strstr(which, tag)) continue;
+    make_idx<<<sms * 8, 256>>>(idx, M, s.base, s.n, s.mode, s.alpha, 1234 + si);
+    CK(cudaDeviceSynchronize());
+    c.hub_lo = s.base; c.hub_hi = s.base + s.hub; c.ref_sum = 0;
+    printf("== stream %d: %s, M = %lld gathers of %d B ==\n", si, s.name, M, ROW_BYTES);
+    if (want("ldg")) {
+      run("ldg UNR=8  x4/SM (r01 inner loop)", c, [&] { k_ldg<8, 4><<<sms * 4, 256>>>(idx, M, X, Y); });
+      run("ldg UNR=16 x3/SM", c, [&] { k_ldg<16, 3><<<sms * 3, 256>>>(idx, M, X, Y); });
+      run("ldg UNR=16 x4/SM", c, [&] { k_ldg<16, 4><<<sms * 4, 256>>>(idx, M, X, Y); });
+      run("ldg UNR=8  x8/SM", c, [&] { k_ldg<8, 8><<<sms * 8, 256>>>(idx, M, X, Y); });
+    }
+    if (want("bulk")) {
+      run_ring<24, 1, 4, 0, 0, true>("bulk", c, 1);
+      run_ring<24, 2, 4, 0, 0, true>("bulk", c, 1);
+      run_ring<24, 4, 4, 0, 0, true>("bulk", c, 1);
+      run_ring<24, 8, 4, 0, 0, true>("bulk", c, 1);
+      run_ring<12, 4, 4, 0, 0, true>("bulk", c, 2);
+      run_ring<8, 2, 2, 0, 0, true>("bulk", c, 3);
+      run_ring<6, 2, 2, 0, 0, true>("bulk", c, 4);
+      run_ring<24, 4, 4, 0, 0, false>("bulk no-consume", c, 1);
+      run_ring<24, 8, 4, 0, 0, false>("bulk no-consume", c, 1);
+      if (s.hub > 0) {
+        run_ring<24, 4, 4, 0, 1, true>("bulk hub evict_last/cold evict_first", c, 1);
+        run_ring<24, 4, 4, 0, 2, true>("bulk all evict_first", c, 1);
+      }
+    }
+    if (want("g4")) {
+      run_ring<24, 1, 4, 1, 0, true>("gather4", c, 1);
+      run_ring<24, 2, 4, 1, 0, true>("gather4", c, 1);
+      run_ring<24, 4, 4, 1, 0, true>("gather4", c, 1);
+      run_ring<12, 2, 4, 1, 0, true>("gather4", c, 2);
+      run_ring<24, 2, 4, 1, 0, false>("gather4 no-consume", c, 1);
+    }
+  }
+  printf("done\n");
+  return 0;
+}
