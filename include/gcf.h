@@ -58,7 +58,8 @@ int gcf_bipartite_edge_index(const int64_t* users, const int64_t* items, int64_t
  * sorted by (row, col) with a hand-written stable LSD radix sort, duplicate (row,col)
  * entries summed in their original order.  Outputs: row_ptr int32[n_rows+1],
  * col_idx int32[capacity nnz], out_vals fp32[capacity nnz], nnz_out int64 device scalar
- * (number of distinct entries).  Replaces scipy's csr_matrix((v,(r,c))) + tmp+tmp.T
+ * (number of distinct entries; -1 when a row or column index lies outside the matrix --
+ * scipy and torch raise on such input, so must the caller).  Replaces scipy's csr_matrix((v,(r,c))) + tmp+tmp.T
  * canonicalisation (selfcf.py:297-306, ssl4rec.py:79-84) and torch's coalescing of the
  * uncoalesced COO tensors (ncl.py:76-85,203-209). */
 size_t gcf_coo_to_csr_workspace_bytes(int64_t nnz, int64_t n_rows, int64_t n_cols);

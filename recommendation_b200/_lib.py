@@ -153,11 +153,24 @@ def check(rc: int, what: str) -> None:
 
 
 def ptr(t) -> Optional[int]:
-    """Device (or host) address of a tensor, None for None."""
-    return None if t is None else t.data_ptr()
+    """Device (or host) address of a tensor, None for None.
+
+    The kernels are launched on the CURRENT device's current stream (`current_stream()`), so a tensor that lives on
+    another GPU would be dereferenced by the wrong device: refuse it here, where every pointer argument passes."""
+    if t is None:
+        return None
+    if t.is_cuda:
+        import torch
+
+        cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: select the device "
+                               "first (torch.cuda.set_device / `with torch.cuda.device(...)`), libgcf launches on the current one")
+    return t.data_ptr()
 
 
 def current_stream() -> int:
+    """cudaStream_t of the current device's current stream (see `ptr` for the device check on the arguments)."""
     import torch
 
     return torch.cuda.current_stream().cuda_stream

@@ -82,8 +82,10 @@ compact_runs_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
   }
 }
 
-__global__ void write_nnz_kernel(const uint32_t* __restrict__ total, int64_t* __restrict__ nnz_out) {
-  *nnz_out = (int64_t)(*total);
+// number of distinct entries, or -1 when a row / column index was out of range (scipy and torch raise on such input,
+// selfcf.py:297-306; the caller turns the -1 into its own error instead of building a graph with entries missing)
+__global__ void write_nnz_kernel(const uint32_t* __restrict__ total, const int* __restrict__ bad, int64_t* __restrict__ nnz_out) {
+  *nnz_out = (*bad != 0) ? -1 : (int64_t)(*total);
 }
 
 // warp per row: rowsum + scaling vector
@@ -271,7 +273,7 @@ extern "C" int gcf_coo_to_csr_stable(const int64_t* rows, const int64_t* cols, c
   rc = exclusive_scan_u32(reinterpret_cast<uint32_t*>(row_ptr), reinterpret_cast<uint32_t*>(row_ptr), n_rows + 1,
                           nullptr, ws + L.scan_ws, L.scan_bytes, st);
   if (rc != GCF_OK) return rc;
-  write_nnz_kernel<<<1, 1, 0, st>>>(total, nnz_out);
+  write_nnz_kernel<<<1, 1, 0, st>>>(total, bad, nnz_out);
   GCF_LAUNCH_CHECK("write_nnz_kernel");
   return GCF_OK;
 }

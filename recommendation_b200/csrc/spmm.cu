@@ -367,18 +367,21 @@ __device__ __forceinline__ void prefetch_epilogue(const Epi& ep, long long row, 
 // STASH = true : completed rows are parked in shared memory (each lane keeps its own float4 slice) and the full
 //                epilogue -- linear combination with addends, row-L2-normalise, fused Adam -- runs between two groups
 //                of gathers, where no gathered row is live in registers; at most UNR rows complete per group.
-template <int LPR, int UNR, bool GUARD, bool STASH, int MINB>
+// Narrow rows (d/G = 8, 16, 32 floats in the multi-GPU layouts) have LPR = 2, 4, 8 lanes per row: a batch then holds
+// BS = LPR * PPL = 16 entries, every lane carrying PPL (col, val) pairs and PPL rows of the row window.
+template <int LPR, int PPL, int UNR, bool GUARD, bool STASH, int MINB, int LONG_UNR, int LONG_PPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 spmm_flat_kernel(const int* __restrict__ col_idx, const float* __restrict__ vals, const float* __restrict__ X,
                  long long ldx, int dvec, const __grid_constant__ Epi ep, LongPlan lp, const int* __restrict__ row_ptr,
                  int long_blocks, int tile_blocks, TilePlan tp) {
   constexpr int RPW = 32 / LPR;
+  constexpr int BS = LPR * PPL;            // entries per batch of one sub-warp
   constexpr int SLOTS = STASH ? UNR : 1;
   constexpr unsigned kFull = 0xffffffffu;
-  static_assert(LPR % UNR == 0 && UNR % 4 == 0, "batches are consumed UNR gathers at a time, four columns per LDS.128");
-  __shared__ __align__(16) int col_slab[kWarpsPerBlock][32];
-  __shared__ __align__(16) float val_slab[kWarpsPerBlock][32];
-  __shared__ __align__(16) int mark_slab[kWarpsPerBlock][32];
+  static_assert(BS % UNR == 0 && UNR % 4 == 0, "batches are consumed UNR gathers at a time, four columns per LDS.128");
+  __shared__ __align__(16) int col_slab[kWarpsPerBlock][RPW * BS];
+  __shared__ __align__(16) float val_slab[kWarpsPerBlock][RPW * BS];
+  __shared__ __align__(16) int mark_slab[kWarpsPerBlock][RPW * BS];
   __shared__ __align__(16) float4 stash[STASH ? kWarpsPerBlock : 1][SLOTS][32];
   __shared__ int stash_row[STASH ? kWarpsPerBlock : 1][SLOTS][RPW];
   const int warp = threadIdx.x >> 5;
@@ -389,7 +392,7 @@ spmm_flat_kernel(const int* __restrict__ col_idx, const float* __restrict__ vals
 
   if ((int)blockIdx.x < long_blocks) {
     float4 acc[1] = {f4_zero()};
-    long_chunk_path<LPR, 1, (UNR > 8 ? 8 : UNR), GUARD, 1>(row_ptr, col_idx, vals, X, ldx, dvec, ep, lp, warp, lane, sub, sl, mask, acc);
+    long_chunk_path<LPR, 1, LONG_UNR, GUARD, LONG_PPL>(row_ptr, col_idx, vals, X, ldx, dvec, ep, lp, warp, lane, sub, sl, mask, acc);
     return;
   }
   if ((int)blockIdx.x >= long_blocks + tile_blocks) {
@@ -410,11 +413,11 @@ spmm_flat_kernel(const int* __restrict__ col_idx, const float* __restrict__ vals
     j = __ldg(tp.rp + k);
     jend = __ldg(tp.rp + k1);
   }
-  int nb = (jend - j + LPR - 1) / LPR;     // batches of this sub-warp; the warp runs the longest
+  int nb = (jend - j + BS - 1) / BS;       // batches of this sub-warp; the warp runs the longest
   if (RPW > 1) nb = __reduce_max_sync(kFull, nb);
-  const int* cs = &col_slab[warp][sub * LPR];
-  const float* vs = &val_slab[warp][sub * LPR];
-  const int* ms = &mark_slab[warp][sub * LPR];
+  int* cs = &col_slab[warp][sub * BS];
+  float* vs = &val_slab[warp][sub * BS];
+  int* ms = &mark_slab[warp][sub * BS];
   const bool col_ok = !GUARD || sl < dvec;
   const float4* Xl = reinterpret_cast<const float4*>(X) + sl;   // this lane's float4 column of X
   const unsigned ldx4 = (unsigned)(ldx >> 2);   // 32 x 32 -> 64-bit address products (one IMAD.WIDE.U32 each)
@@ -423,32 +426,44 @@ spmm_flat_kernel(const int* __restrict__ col_idx, const float* __restrict__ vals
 
   // (col, val) of batch 0 and the row window of batch 0.  Slots past the tile's last entry repeat its last column
   // with weight 0: their gathers hit L1 and cannot bring a non-finite value into a row that does not already hold it.
-  int c = 0, my_end = 0, my_row = 0;
-  float v = 0.f;
-  if (has_tile) {
-    const int jj = min(j + sl, jend - 1);
-    c = ld_stream_i32(col_idx + jj);
-    if (j + sl < jend) v = ld_stream_f32(vals + jj);
-    my_end = __ldg(tp.rp + min(k + 1 + sl, k1));
-    my_row = renumbered ? __ldg(tp.ids + min(k + sl, k1 - 1)) : k + sl;
+  int c[PPL], my_end[PPL], my_row[PPL];
+  float v[PPL];
+#pragma unroll
+  for (int p = 0; p < PPL; ++p) {
+    c[p] = 0; v[p] = 0.f; my_end[p] = 0; my_row[p] = 0;
+    if (has_tile) {
+      const int t = p * LPR + sl;
+      const int jj = min(j + t, jend - 1);
+      c[p] = ld_stream_i32(col_idx + jj);
+      if (j + t < jend) v[p] = ld_stream_f32(vals + jj);
+      my_end[p] = __ldg(tp.rp + min(k + 1 + t, k1));
+      my_row[p] = renumbered ? __ldg(tp.ids + min(k + t, k1 - 1)) : k + t;
+    }
   }
   float4 acc = f4_zero();
-  for (int b = 0; b < nb; ++b, j += LPR) {
-    const int cnt = max(0, min(LPR, jend - j));
+  for (int b = 0; b < nb; ++b, j += BS) {
+    const int cnt = max(0, min(BS, jend - j));
     __syncwarp();                          // the previous batch has been read out of the slabs
-    col_slab[warp][lane] = c;
-    val_slab[warp][lane] = v;
-    mark_slab[warp][lane] = 0;
+#pragma unroll
+    for (int p = 0; p < PPL; ++p) {
+      cs[p * LPR + sl] = c[p];
+      vs[p * LPR + sl] = v[p];
+      ms[p * LPR + sl] = 0;
+    }
     __syncwarp();
-    v = 0.f;
-    if (j + LPR < jend) {                  // (col, val) of the next batch
-      const int jj = min(j + LPR + sl, jend - 1);
-      c = ld_stream_i32(col_idx + jj);
-      if (j + LPR + sl < jend) v = ld_stream_f32(vals + jj);
+#pragma unroll
+    for (int p = 0; p < PPL; ++p) {        // (col, val) of the next batch
+      v[p] = 0.f;
+      const int t = BS + p * LPR + sl;
+      if (j + BS < jend) {
+        const int jj = min(j + t, jend - 1);
+        c[p] = ld_stream_i32(col_idx + jj);
+        if (j + t < jend) v[p] = ld_stream_f32(vals + jj);
+      }
     }
     float4 x[UNR];
 #pragma unroll
-    for (int t0 = 0; t0 < LPR; t0 += UNR) {
+    for (int t0 = 0; t0 < BS; t0 += UNR) {
       if (t0 < cnt) {
 #pragma unroll
         for (int u = 0; u < UNR; u += 4) {
@@ -461,14 +476,23 @@ spmm_flat_kernel(const int* __restrict__ col_idx, const float* __restrict__ vals
       }
       if (t0 == 0) {
         // with the first gathers in flight: rows that end inside this batch, and the window of the next one
-        const int pos = my_end - 1 - j;
-        const bool ends_here = has_tile && k + sl < k1 && pos < LPR;
-        if (ends_here) mark_slab[warp][sub * LPR + pos] = my_row + 1;
-        const unsigned done = __ballot_sync(kFull, ends_here) & mask;
-        k += __popc(done);
+        int n_done = 0;
+#pragma unroll
+        for (int p = 0; p < PPL; ++p) {
+          const int t = p * LPR + sl;
+          const int pos = my_end[p] - 1 - j;
+          const bool ends_here = has_tile && k + t < k1 && pos < BS;
+          if (ends_here) ms[pos] = my_row[p] + 1;
+          n_done += __popc(__ballot_sync(kFull, ends_here) & mask);
+        }
+        k += n_done;
         if (has_tile) {
-          my_end = __ldg(tp.rp + min(k + 1 + sl, k1));
-          my_row = renumbered ? __ldg(tp.ids + min(k + sl, k1 - 1)) : k + sl;
+#pragma unroll
+          for (int p = 0; p < PPL; ++p) {
+            const int t = p * LPR + sl;
+            my_end[p] = __ldg(tp.rp + min(k + 1 + t, k1));
+            my_row[p] = renumbered ? __ldg(tp.ids + min(k + t, k1 - 1)) : k + t;
+          }
         }
         __syncwarp();
       }
@@ -510,7 +534,7 @@ spmm_flat_kernel(const int* __restrict__ col_idx, const float* __restrict__ vals
   }
 }
 
-template <int LPR, int UNR, bool GUARD, bool STASH, int MINB>
+template <int LPR, int PPL, int UNR, bool GUARD, bool STASH, int MINB, int LONG_UNR, int LONG_PPL>
 static int launch_flat(const gcf_csr_t* A, const float* X, long long ldx, int dvec, const Epi& ep, const LongPlan& lp,
                        cudaStream_t st) {
   constexpr int RPW = 32 / LPR;
@@ -523,17 +547,26 @@ static int launch_flat(const gcf_csr_t* A, const float* X, long long ldx, int dv
   TilePlan tp{reinterpret_cast<const int2*>(A->tiles), A->n_tiles, A->n_empty > 0 ? A->nz_row_ptr : A->row_ptr,
               A->n_empty > 0 ? A->nz_rows : nullptr, A->empty_rows, A->n_empty};
   static const int pad_smem = getenv("GCF_SPMM_PAD_SMEM") ? atoi(getenv("GCF_SPMM_PAD_SMEM")) : 0;   // L1-capacity probe
-  spmm_flat_kernel<LPR, UNR, GUARD, STASH, MINB><<<(unsigned)grid, kWarpsPerBlock * 32, pad_smem, st>>>(
+  spmm_flat_kernel<LPR, PPL, UNR, GUARD, STASH, MINB, LONG_UNR, LONG_PPL><<<(unsigned)grid, kWarpsPerBlock * 32, pad_smem, st>>>(
       A->col_idx, A->vals, X, ldx, dvec, ep, lp, A->row_ptr, long_blocks, (int)tile_blocks, tp);
   GCF_LAUNCH_CHECK("spmm_flat_kernel");
   return GCF_OK;
 }
 
+// full-width rows: one (col, val) pair per lane, hub chunks on the r01 inner loop with 8 gathers in flight
 template <int LPR, int UNR, bool GUARD, int MINB>
 static int launch_flat_cls(bool plain, const gcf_csr_t* A, const float* X, long long ldx, int dvec, const Epi& ep,
                            const LongPlan& lp, cudaStream_t st) {
-  if (plain) return launch_flat<LPR, UNR, GUARD, false, MINB>(A, X, ldx, dvec, ep, lp, st);
-  return launch_flat<LPR, (UNR > 8 ? 8 : UNR), GUARD, true, MINB>(A, X, ldx, dvec, ep, lp, st);   // stash: UNR slots of a row each
+  if (plain) return launch_flat<LPR, 1, UNR, GUARD, false, MINB, 8, 1>(A, X, ldx, dvec, ep, lp, st);
+  return launch_flat<LPR, 1, (UNR > 8 ? 8 : UNR), GUARD, true, MINB, 8, 1>(A, X, ldx, dvec, ep, lp, st);   // stash: UNR slots of a row each
+}
+// narrow rows: 16-entry batches (8-entry batches at 2 lanes per row: 16 sub-warps per warp share the 48 KB)
+template <int LPR, int MINB, int LONG_UNR, int LONG_PPL>
+static int launch_flat_narrow(bool plain, const gcf_csr_t* A, const float* X, long long ldx, int dvec, const Epi& ep,
+                              const LongPlan& lp, cudaStream_t st) {
+  constexpr int PPL = LPR == 2 ? 4 : 16 / LPR;
+  if (plain) return launch_flat<LPR, PPL, 8, false, false, MINB, LONG_UNR, LONG_PPL>(A, X, ldx, dvec, ep, lp, st);
+  return launch_flat<LPR, PPL, 8, false, true, MINB, LONG_UNR, LONG_PPL>(A, X, ldx, dvec, ep, lp, st);
 }
 
 __global__ void axpby_kernel(float4* __restrict__ out, const float4* __restrict__ a, float sa,
@@ -626,10 +659,24 @@ static int spmm_impl(const gcf_csr_t* A, int32_t d, const float* X, int64_t ldx,
   const int dvec = d / 4;
   // flat-stream kernel: default whenever the operator carries a tile schedule and a row fits one float4 per lane.
   // variant 0 = default, 4 = the r01 row-walking kernel (kept for A/B runs), 10.. = flat-kernel tuning points
-  if (A->n_tiles > 0 && A->tiles != nullptr && d >= 36 && d <= 128 && (variant == 0 || variant >= 10)) {
+  if (A->n_tiles > 0 && A->tiles != nullptr && (d == 8 || d == 16 || d == 32 || (d >= 36 && d <= 128)) &&
+      (variant == 0 || variant >= 10)) {
     GCF_REQUIRE(A->n_empty == 0 || (A->empty_rows != nullptr && A->nz_row_ptr != nullptr && A->nz_rows != nullptr),
                 "gcf_spmm_csr_f32: operator has empty rows but no compact row numbering");
     const bool plain = adam == nullptr && epilogue == GCF_EPILOGUE_NONE && OUT == nullptr;   // Y = A X and nothing else
+    // feature-sharded slices; hub chunks keep the r01 narrow-row inner loops (gathers in flight x pairs per lane)
+    if (d == 8) {
+      if (variant == 10) return launch_flat_narrow<2, 4, 2, 4>(plain, A, X, ldx, dvec, ep, lp, st);
+      return launch_flat_narrow<2, 3, 2, 4>(plain, A, X, ldx, dvec, ep, lp, st);
+    }
+    if (d == 16) {
+      if (variant == 10) return launch_flat_narrow<4, 4, 4, 2>(plain, A, X, ldx, dvec, ep, lp, st);
+      return launch_flat_narrow<4, 3, 4, 2>(plain, A, X, ldx, dvec, ep, lp, st);
+    }
+    if (d == 32) {
+      if (variant == 10) return launch_flat_narrow<8, 4, 8, 1>(plain, A, X, ldx, dvec, ep, lp, st);
+      return launch_flat_narrow<8, 3, 8, 1>(plain, A, X, ldx, dvec, ep, lp, st);
+    }
     // measured on cfg1 / cfg5 (profiles/r02_exp_spmm_*.log): 8 gathers in flight per sub-warp at 3 CTAs / SM
     if (d == 64) {
       if (variant == 10) return launch_flat_cls<16, 8, false, 4>(plain, A, X, ldx, dvec, ep, lp, st);

@@ -74,16 +74,22 @@ def hits_and_dcg(topn_idx: torch.Tensor, query_users: torch.Tensor, test_pos: Tu
 
 
 def ranking_measures(topn_idx: torch.Tensor, query_users: torch.Tensor, test_pos: Tuple[torch.Tensor, torch.Tensor],
-                     top_ns: Sequence[int]) -> Dict[int, Dict[str, float]]:
+                     top_ns: Sequence[int], *, n_test: Optional[torch.Tensor] = None) -> Dict[int, Dict[str, float]]:
     """{N: {'Hit Ratio', 'Precision', 'Recall', 'NDCG'}} with the definitions (and 5-decimal rounding) of Metric
-    (ncl.py:133-162).  Every query user must have at least one test item (the reference iterates over test_set)."""
+    (ncl.py:133-162).  Every query user must have at least one test item (the reference iterates over test_set).
+
+    `n_test` [Q] overrides len(origin[u]) -- the denominators of Hit Ratio / Recall and the length of the ideal list of
+    NDCG.  The reference counts EVERY test item of the user there, also items that never occur in the training data and
+    therefore have no column to be hit in (ncl.py:144,153,160); `test_pos` can only hold the mapped ones."""
     dev = topn_idx.device
     q, n_top = topn_idx.shape
     cuts = sorted(int(n) for n in top_ns)
     hits, dcg = hits_and_dcg(topn_idx, query_users, test_pos, cuts)
     rp, ci = test_pos
     users = query_users.to(dev, torch.int64).contiguous()
-    n_test = (rp[users + 1] - rp[users]).to(torch.float64)       # len(origin[u])
+    if n_test is None:
+        n_test = rp[users + 1] - rp[users]                        # len(origin[u]) when every test item has a column
+    n_test = n_test.to(dev, torch.float64)
     idcg_table = torch.tensor([0.0] + list(np.cumsum([1.0 / math.log2(i + 2) for i in range(cuts[-1])])), dtype=torch.float64, device=dev)
     out: Dict[int, Dict[str, float]] = {}
     h64 = hits.to(torch.float64)
@@ -112,11 +118,15 @@ def evaluate_model(user_emb: torch.Tensor, item_emb: torch.Tensor, data, top_ns:
     dev = user_emb.device
     tr_u = torch.tensor([data.user[r[0]] for r in data.training_data], dtype=torch.int64, device=dev)
     tr_i = torch.tensor([data.item[r[1]] for r in data.training_data], dtype=torch.int64, device=dev)
-    te = [(data.user[u], data.item[i]) for u, its in data.test_set.items() if u in data.user for i in its if i in data.item]
+    # hits can only happen on items that have a column; the denominators count every test item (see ranking_measures)
+    te = [(data.user[u], data.item[i]) for u, its in data.test_set.items() for i in its if i in data.item]
     te_u = torch.tensor([p[0] for p in te], dtype=torch.int64, device=dev)
     te_i = torch.tensor([p[1] for p in te], dtype=torch.int64, device=dev)
     train_pos = positives_csr(tr_u, tr_i, data.user_num, data.item_num)
     test_pos = positives_csr(te_u, te_i, data.user_num, data.item_num)
-    query = torch.unique(te_u)
+    query = torch.tensor(sorted(data.user[u] for u in data.test_set), dtype=torch.int64, device=dev)   # test(): every user of test_set
+    raw_count = torch.zeros(data.user_num, dtype=torch.int64)
+    for u, its in data.test_set.items():
+        raw_count[data.user[u]] = len(its)
     idx, _ = recommend_topn(user_emb, item_emb, query, max(top_ns), train_pos=train_pos)
-    return format_measures(ranking_measures(idx, query, test_pos, top_ns))
+    return format_measures(ranking_measures(idx, query, test_pos, top_ns, n_test=raw_count.to(dev)[query]))

@@ -195,6 +195,8 @@ class CSRGraph:
                                              _lib.ptr(ws), ws_bytes, stream), "gcf_coo_to_csr_stable")
         nnz = int(nnz_out.item())
         del ws
+        if nnz < 0:
+            raise ValueError(f"COO indices out of range for a {n_rows} x {n_cols} matrix (scipy / torch raise here too)")
         if 0 < nnz < col_idx.numel():  # duplicates were merged: release the slack
             col_idx, out_vals = col_idx[:nnz].clone(), out_vals[:nnz].clone()
         elif nnz == 0:                 # keep a non-null base pointer for empty operators

@@ -674,3 +674,56 @@ def test_esrf_fixture(cuda, golden):
     for got, key in zip(gg, ("g_g_relation", "g_g_selector")):
         np.testing.assert_allclose(got.cpu().numpy(), z[key], rtol=1e-2, atol=1e-4 * np.abs(z[key]).max())
     assert torch.isfinite(gen(A, 0)).all()      # training path: own noise
+
+
+# ------------------------------------------------------------------------------------------ r02 reference-generated fixtures
+def test_dnn_encoder_reference_fixture(cuda, golden):
+    """ssl4rec.py:162-196,221-224: the reference's own DNNEncoder (eval mode), its forward, cal_cl_loss, the training-loop
+    loss and every parameter gradient (tests/golden/make_golden_r02.py)."""
+    z = golden("dnn_encoder")
+    data = SimpleNamespace(user_num=int(z["n_users"]), item_num=int(z["n_items"]))
+    m = encoders.DNNEncoder(data, int(z["emb_size"]), float(z["drop_rate"]), float(z["tau"]), int(z["n_layers"]))
+    names = [k[len("param."):] for k in z if k.startswith("param.")]
+    assert sorted(names) == sorted(m.state_dict().keys())                 # state_dict keys are part of the interface
+    m.load_state_dict({n: torch.from_numpy(z[f"param.{n}"]) for n in names})
+    m.eval()
+    u, i = z["u"].tolist(), z["i"].tolist()
+    q, k = m(u, i)
+    np.testing.assert_allclose(q.detach().cpu().numpy(), z["q"], rtol=1e-3, atol=1e-5)   # fp32 path (gather + cuBLAS towers)
+    np.testing.assert_allclose(k.detach().cpu().numpy(), z["k"], rtol=1e-3, atol=1e-5)
+    cl = m.cal_cl_loss(i)
+    rec = losses.batch_softmax_loss(q, k, float(z["tau"]))
+    total = rec + losses.l2_reg_loss(1e-4, q, k) + 0.1 * cl
+    np.testing.assert_allclose(cl.item(), float(z["cl"]), rtol=2e-2)                       # bf16 logits
+    np.testing.assert_allclose(rec.item(), float(z["rec"]), rtol=2e-2)
+    np.testing.assert_allclose(total.item(), float(z["total"]), rtol=2e-2)
+    total.backward()
+    for n, p in m.named_parameters():
+        want = z[f"grad.{n}"]
+        assert p.grad is not None, n
+        np.testing.assert_allclose(p.grad.cpu().numpy(), want, rtol=2e-2, atol=2e-2 * np.abs(want).max() + 1e-7, err_msg=n)
+
+
+def test_evaluate_model_counts_cold_test_items(cuda, golden):
+    """ncl.py:253-277 + 133-178 on the reference's own Interaction: test items that never occur in training stay in
+    test_set, so they count in len(origin[u]) (Hit Ratio / Recall denominators, ideal DCG) although they cannot be hit."""
+    from recommendation_b200 import evaluation
+
+    z = golden("eval_cold")
+    tr_u, tr_i = z["train_users"].tolist(), z["train_items"].tolist()
+    users, items = sorted(set(tr_u)), sorted(set(tr_i))                                   # Interaction._build, ncl.py:55-61
+    data = SimpleNamespace(user={u: k for k, u in enumerate(users)}, item={i: k for k, i in enumerate(items)},
+                           user_num=len(users), item_num=len(items), training_data=list(zip(tr_u, tr_i)), test_set={})
+    for u, i in zip(z["test_users"].tolist(), z["test_items"].tolist()):
+        data.test_set.setdefault(u, {})[i] = 1
+    assert any(i not in data.item for its in data.test_set.values() for i in its)         # the fixture does hold cold items
+    got = evaluation.evaluate_model(torch.from_numpy(z["user_emb"]).to(cuda), torch.from_numpy(z["item_emb"]).to(cuda), data,
+                                    [int(n) for n in z["top_ns"]])
+    want = [str(s) for s in z["strings"]]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        if ":" in w:
+            assert g.split(":")[0] == w.split(":")[0]
+            np.testing.assert_allclose(float(g.split(":")[1]), float(w.split(":")[1]), rtol=0, atol=1.1e-5)
+        else:
+            assert g == w

@@ -40,6 +40,8 @@ def main():
     variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [4, 10, 11, 12, 13, 14]
     dev = torch.device("cuda", 0)
     U, I, E, d, K = synth.CONFIGS[cfg]
+    if len(sys.argv) > 4:
+        d = int(sys.argv[4])   # row width override (feature-sharded slices)
     if E > 20_000_000:
         users, items = synth.power_law_bipartite_torch(U, I, E, seed=1005, device=dev)
     else:
@@ -86,7 +88,7 @@ def main():
             res[f"tile{g.tile_nnz}_v{v}"] = {"plain_us": t_plain * 1e3, "linear_us": t_lin * 1e3, "l2norm_us": t_full * 1e3}
         del g
     Path("gpurun_out/r02").mkdir(parents=True, exist_ok=True)
-    Path(f"gpurun_out/r02/exp_spmm_{cfg}.json").write_text(json.dumps(res, indent=1))
+    Path(f"gpurun_out/r02/exp_spmm_{cfg}_d{d}.json").write_text(json.dumps(res, indent=1))
 
 
 if __name__ == "__main__":

@@ -152,6 +152,100 @@ __global__ void __launch_bounds__(256, MINB) k_ldg(const int* __restrict__ idx, 
   }
 }
 
+// ldg with per-row L2 eviction priority (createpolicy + .L2::cache_hint; the policy operand is warp-uniform in SASS, so
+// the two priorities are two predicated LDGs).  MODE 1: hub evict_last / cold evict_first, 2: hub default / cold
+// evict_first, 3: hub evict_last / cold default, 4: like 1 and cold rows do not allocate in L1
+__device__ __forceinline__ float4 ldg_hint(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_hint_na(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+template <int UNR, int MINB, int MODE>
+__global__ void __launch_bounds__(256, MINB) k_ldg_hint(const int* __restrict__ idx, long long m, const float* __restrict__ X,
+                                                        float* __restrict__ Y, int hub_lo, int hub_hi) {
+  const int lane = threadIdx.x & 31, sl = lane & 15;
+  const long long n_groups = m / 16;
+  const long long sub0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const long long n_sub = ((long long)gridDim.x * blockDim.x) >> 4;
+  const unsigned mask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
+  const uint64_t p_last = pol_evict_last(), p_first = pol_evict_first();
+  for (long long g = sub0; g < n_groups; g += n_sub) {
+    const int c = ld_stream_i32(idx + g * 16 + sl);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t0 = 0; t0 < 16; t0 += UNR) {
+      float4 x[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int ct = __shfl_sync(mask, c, t0 + u, 16);
+        const float4* p = reinterpret_cast<const float4*>(X + (long long)ct * D) + sl;
+        const bool hub = ct >= hub_lo && ct < hub_hi;
+        if (MODE == 1) x[u] = hub ? ldg_hint(p, p_last) : ldg_hint(p, p_first);
+        else if (MODE == 2) x[u] = hub ? __ldg(p) : ldg_hint(p, p_first);
+        else if (MODE == 3) x[u] = hub ? ldg_hint(p, p_last) : __ldg(p);
+        else x[u] = hub ? ldg_hint(p, p_last) : ldg_hint_na(p, p_first);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) f4_acc(acc, x[u]);
+    }
+    reinterpret_cast<float4*>(Y + g * D)[sl] = acc;
+  }
+}
+
+// 256-bit loads (sm_100): 8 lanes per row, static .L2::evict_last / .L2::evict_first qualifiers
+__device__ __forceinline__ void ldg256(const float* a, float (&r)[8], int mode) {
+  unsigned q[8];
+  if (mode == 0)
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]) : "l"(a));
+  else if (mode == 1)
+    asm volatile("ld.global.nc.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]) : "l"(a));
+  else
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]) : "l"(a));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(q[i]);
+}
+template <int UNR, int MINB, int MODE>
+__global__ void __launch_bounds__(256, MINB) k_ldg256(const int* __restrict__ idx, long long m, const float* __restrict__ X,
+                                                      float* __restrict__ Y, int hub_lo, int hub_hi) {
+  // a group of 16 gathers is summed by one 8-lane sub-warp (so the checksum matches the 16-lane kernels)
+  const int lane = threadIdx.x & 31, sl = lane & 7;
+  const long long n_groups = m / 16;
+  const long long sub0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const long long n_sub = ((long long)gridDim.x * blockDim.x) >> 3;
+  const unsigned mask = 0xffu << (lane & 24);
+  for (long long g = sub0; g < n_groups; g += n_sub) {
+    const int c0 = ld_stream_i32(idx + g * 16 + sl);
+    const int c1 = ld_stream_i32(idx + g * 16 + 8 + sl);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t0 = 0; t0 < 16; t0 += UNR) {
+      float x[UNR][8];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int t = t0 + u;
+        const int ct = __shfl_sync(mask, t < 8 ? c0 : c1, t & 7, 8);
+        const float* p = X + (long long)ct * D + sl * 8;
+        const bool hub = ct >= hub_lo && ct < hub_hi;
+        if (MODE == 0) ldg256(p, x[u], 0);
+        else if (hub) ldg256(p, x[u], 1);
+        else ldg256(p, x[u], 2);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += x[u][i];
+    }
+    float4* y = reinterpret_cast<float4*>(Y + g * D + sl * 8);
+    y[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    y[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // bulk / gather4: warp 0 produces, warps 1..C consume.  A stage holds 32 rows (8 KB).
 //   MODE 0: cp.async.bulk per row     MODE 1: gather4     HINT: 0 none, 1 hub evict_last / cold evict_first, 2 all evict_first
@@ -346,6 +440,28 @@ int main(int argc, char** argv) {
       run("ldg UNR=16 x3/SM", c, [&] { k_ldg<16, 3><<<sms * 3, 256>>>(idx, M, X, Y); });
       run("ldg UNR=16 x4/SM", c, [&] { k_ldg<16, 4><<<sms * 4, 256>>>(idx, M, X, Y); });
       run("ldg UNR=8  x8/SM", c, [&] { k_ldg<8, 8><<<sms * 8, 256>>>(idx, M, X, Y); });
+    }
+    if (want("hint") && s.mode == 1) {
+      for (int hub : {100000, 200000, 400000}) {
+        c.hub_lo = s.base; c.hub_hi = s.base + hub;
+        char nm[96];
+        snprintf(nm, sizeof nm, "ldg hint last/first hub=%dk UNR=8 x4", hub / 1000);
+        run(nm, c, [&] { k_ldg_hint<8, 4, 1><<<sms * 4, 256>>>(idx, M, X, Y, c.hub_lo, c.hub_hi); });
+        snprintf(nm, sizeof nm, "ldg hint default/first hub=%dk UNR=8 x4", hub / 1000);
+        run(nm, c, [&] { k_ldg_hint<8, 4, 2><<<sms * 4, 256>>>(idx, M, X, Y, c.hub_lo, c.hub_hi); });
+        snprintf(nm, sizeof nm, "ldg hint last/default hub=%dk UNR=8 x4", hub / 1000);
+        run(nm, c, [&] { k_ldg_hint<8, 4, 3><<<sms * 4, 256>>>(idx, M, X, Y, c.hub_lo, c.hub_hi); });
+        snprintf(nm, sizeof nm, "ldg hint last/first+L1na hub=%dk UNR=8 x4", hub / 1000);
+        run(nm, c, [&] { k_ldg_hint<8, 4, 4><<<sms * 4, 256>>>(idx, M, X, Y, c.hub_lo, c.hub_hi); });
+        snprintf(nm, sizeof nm, "ldg256 last/first hub=%dk UNR=4 x4", hub / 1000);
+        run(nm, c, [&] { k_ldg256<4, 4, 1><<<sms * 4, 256>>>(idx, M, X, Y, c.hub_lo, c.hub_hi); });
+      }
+      c.hub_lo = s.base; c.hub_hi = s.base + s.hub;
+    }
+    if (want("hint") || want("ldg256")) {
+      run("ldg256 plain UNR=4 x4/SM", c, [&] { k_ldg256<4, 4, 0><<<sms * 4, 256>>>(idx, M, X, Y, 0, 0); });
+      run("ldg256 plain UNR=4 x6/SM", c, [&] { k_ldg256<4, 6, 0><<<sms * 6, 256>>>(idx, M, X, Y, 0, 0); });
+      run("ldg256 plain UNR=8 x3/SM", c, [&] { k_ldg256<8, 3, 0><<<sms * 3, 256>>>(idx, M, X, Y, 0, 0); });
     }
     if (want("bulk")) {
       run_ring<24, 1, 4, 0, 0, true>("bulk", c, 1);

@@ -13,6 +13,8 @@ cfg, variant, modes = sys.argv[1], int(sys.argv[2]), sys.argv[3].split(",")
 tile = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 dev = torch.device("cuda", 0)
 U, I, E, d, K = synth.CONFIGS[cfg]
+if len(sys.argv) > 5:
+    d = int(sys.argv[5])
 if E > 20_000_000:
     users, items = synth.power_law_bipartite_torch(U, I, E, seed=1005, device=dev)
 else:
