@@ -281,6 +281,21 @@ int gcf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t decoupled,
                   int64_t step, gcf_stream_t stream);
 
+/* Fused torch.optim.SGD step (selfcf.py:544, directau.py:214, univariate/selfcf_univariate.py:553: lr, momentum = 0.9):
+ *   g' = g + weight_decay*p;  buf = g' when first_step != 0, else momentum*buf + (1 - dampening)*g';
+ *   p -= lr * (nesterov ? g' + momentum*buf : buf)           (momentum = 0: p -= lr*g', momentum_buf may be NULL)
+ * one pass over param / grad / momentum_buf, same operation order as torch's single-tensor implementation. */
+int gcf_sgd_momentum_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                          float dampening, float weight_decay, int32_t nesterov, int32_t first_step, gcf_stream_t stream);
+
+/* Row-sparse Adam for the mini-batch models: only rows[0..n_rows) of param / exp_avg / exp_avg_sq
+ * ([*, d], leading dimension ld) are updated, with the gradient rows given densely in list order ([n_rows, d], ld_grad).
+ * rows must be distinct.  Same arithmetic as gcf_adam_step on the touched rows (untouched rows keep their moments:
+ * torch.optim.SparseAdam semantics, NOT the dense torch.optim.Adam the reference uses -- see DESIGN.md). */
+int gcf_adam_rows_step(float* param, int64_t ld, const float* grad_rows, int64_t ld_grad, float* exp_avg, float* exp_avg_sq,
+                       const int64_t* rows, int64_t n_rows, int32_t d, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int32_t decoupled, int64_t step, gcf_stream_t stream);
+
 /* x[0..n) *= *g (device scalar); returns without touching memory when *g == 1.  Used to apply the upstream
  * gradient to tables whose gradient was produced in the forward pass (gcf_bpr_fwd_bwd). */
 int gcf_scale_by_device_scalar(float* x, int64_t n, const float* g, gcf_stream_t stream);

@@ -88,6 +88,10 @@ _SIGNATURES = {
     "gcf_scale_by_device_scalar": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gcf_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                 c_float, c_int32, c_int64, c_void_p]),
+    "gcf_sgd_momentum_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int32,
+                                        c_int32, c_void_p]),
+    "gcf_adam_rows_step": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                     c_float, c_float, c_float, c_float, c_float, c_int32, c_int64, c_void_p]),
     "gcf_infonce_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
     "gcf_infonce_fwd": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32, c_float,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -372,6 +372,40 @@ def adam_step_(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, e
                                  _lib.current_stream()), "gcf_adam_step")
 
 
+def sgd_step_(param: torch.Tensor, grad: torch.Tensor, momentum_buf: Optional[torch.Tensor], *, lr: float, momentum: float = 0.0,
+              dampening: float = 0.0, weight_decay: float = 0.0, nesterov: bool = False, first_step: bool = False) -> None:
+    """One fused torch.optim.SGD update (selfcf.py:544, directau.py:214: momentum = 0.9).  `first_step` = the momentum
+    buffer does not exist yet (torch initialises it with the gradient); it is written, not read, on that step."""
+    lib = _lib.load()
+    tensors = [("param", param), ("grad", grad)] + ([("momentum_buf", momentum_buf)] if momentum_buf is not None else [])
+    for name, t in tensors:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise TypeError(f"sgd_step_: {name} must be a contiguous float32 CUDA tensor")
+    if momentum != 0.0 and momentum_buf is None:
+        raise ValueError("sgd_step_: momentum needs a momentum buffer")
+    _lib.check(lib.gcf_sgd_momentum_step(_lib.ptr(param), _lib.ptr(grad), _lib.ptr(momentum_buf), param.numel(), lr, momentum,
+                                         dampening, weight_decay, 1 if nesterov else 0, 1 if first_step else 0,
+                                         _lib.current_stream()), "gcf_sgd_momentum_step")
+
+
+def adam_rows_step_(param: torch.Tensor, rows: torch.Tensor, grad_rows: torch.Tensor, exp_avg: torch.Tensor,
+                    exp_avg_sq: torch.Tensor, step: int, *, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+                    weight_decay: float = 0.0, decoupled: bool = False) -> None:
+    """Row-sparse Adam: rows[r] of param / moments updated with grad_rows[r]; `rows` must be distinct.
+    torch.optim.SparseAdam semantics -- the moments of untouched rows do not decay."""
+    lib = _lib.load()
+    for name, t in (("param", param), ("grad_rows", grad_rows), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.is_contiguous()):
+            raise TypeError(f"adam_rows_step_: {name} must be a contiguous 2-D float32 CUDA tensor")
+    rows = _idx(rows, param.device, "rows")
+    if grad_rows.shape[0] != rows.numel() or grad_rows.shape[1] != param.shape[1]:
+        raise ValueError("adam_rows_step_: grad_rows must be [len(rows), d]")
+    d = param.shape[1]
+    _lib.check(lib.gcf_adam_rows_step(_lib.ptr(param), d, _lib.ptr(grad_rows), d, _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq),
+                                      _lib.ptr(rows), rows.numel(), d, lr, betas[0], betas[1], eps, weight_decay,
+                                      1 if decoupled else 0, int(step), _lib.current_stream()), "gcf_adam_rows_step")
+
+
 # =========================================================================================
 # InfoNCE family (tcgen05 tensor cores)
 # =========================================================================================

@@ -330,6 +330,64 @@ def test_adam_matches_torch(cuda, wd, decoupled):
     np.testing.assert_allclose(p.cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("momentum,wd,nesterov,dampening", [(0.9, 0.0, False, 0.0), (0.9, 1e-3, False, 0.0), (0.9, 1e-3, True, 0.0),
+                                                              (0.5, 0.0, False, 0.1), (0.0, 1e-2, False, 0.0)])
+def test_sgd_momentum_matches_torch(cuda, momentum, wd, nesterov, dampening):
+    """torch.optim.SGD(lr, momentum=0.9) of selfcf.py:544 / directau.py:214, through the drop-in optimiser class."""
+    from recommendation_b200 import optim
+    torch.manual_seed(1)
+    p0 = torch.randn(777, 33)                      # odd size: exercises the scalar tail of the vector loop
+    ref = p0.clone().requires_grad_(True)
+    kw = dict(lr=0.05, momentum=momentum, weight_decay=wd, nesterov=nesterov, dampening=dampening)
+    opt_ref = torch.optim.SGD([ref], **kw)
+    p = torch.nn.Parameter(p0.to(cuda))
+    opt = optim.SGD([p], **kw)
+    for _ in range(6):
+        g = torch.randn(777, 33)
+        ref.grad = g.clone(); opt_ref.step()
+        p.grad = g.to(cuda); opt.step()
+    np.testing.assert_allclose(p.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+    if momentum:
+        np.testing.assert_allclose(opt.state[p]["momentum_buffer"].cpu().numpy(),
+                                   opt_ref.state[ref]["momentum_buffer"].numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_adam_optimizer_class_matches_torch(cuda):
+    from recommendation_b200 import optim
+    torch.manual_seed(2)
+    p0 = torch.randn(513, 64)
+    ref = p0.clone().requires_grad_(True)
+    opt_ref = torch.optim.Adam([ref], lr=0.01)
+    p = torch.nn.Parameter(p0.to(cuda))
+    opt = optim.Adam([p], lr=0.01)
+    for _ in range(4):
+        g = torch.randn(513, 64)
+        ref.grad = g.clone(); opt_ref.step()
+        p.grad = g.to(cuda); opt.step()
+    np.testing.assert_allclose(p.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+    sd = opt.state_dict()["state"][0]
+    assert set(sd) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["step"]) == 4.0
+
+
+def test_row_sparse_adam_touches_only_listed_rows(cuda):
+    """gcf_adam_rows_step == dense Adam arithmetic on the listed rows (torch.optim.SparseAdam semantics elsewhere)."""
+    torch.manual_seed(3)
+    n, d = 1000, 64
+    p0 = torch.randn(n, d)
+    rows = torch.randperm(n)[:137]
+    p = p0.to(cuda); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    ref = p0.clone().requires_grad_(True)
+    opt_ref = torch.optim.SparseAdam([ref], lr=0.01)
+    for step in range(1, 4):
+        g_rows = torch.randn(rows.numel(), d)
+        ref.grad = torch.sparse_coo_tensor(rows[None], g_rows, (n, d)).coalesce(); opt_ref.step()
+        F_.adam_rows_step_(p, rows.to(cuda), g_rows.to(cuda), m, v, step, lr=0.01)
+    got = p.cpu()
+    np.testing.assert_allclose(got.numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+    untouched = torch.ones(n, dtype=torch.bool); untouched[rows] = False
+    assert torch.equal(got[untouched], p0[untouched])
+
+
 # ====================================================================== BPR
 def test_bpr_matches_ncl_fixture(cuda, golden):
     z = golden("ncl_losses")
