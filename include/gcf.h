@@ -215,6 +215,13 @@ int gcf_sample_negatives(uint64_t seed, uint64_t offset, const int64_t* users, i
                          int64_t n_items, const int32_t* pos_row_ptr, const int32_t* pos_col_idx,
                          int32_t max_trials, int64_t* out, gcf_stream_t stream);
 
+/* The same stream for a WINDOW of the slot numbering: local slot s of this call draws what slot slot_base + s of a
+ * call over the whole list draws (users / out are indexed locally).  A rank that owns triples [t0, t1) of the global
+ * list passes slot_base = t0 * n_negs, so the negatives do not depend on how the triples are sharded. */
+int gcf_sample_negatives_at(uint64_t seed, uint64_t offset, int64_t slot_base, const int64_t* users, int64_t n,
+                            int32_t n_negs, int64_t n_items, const int32_t* pos_row_ptr, const int32_t* pos_col_idx,
+                            int32_t max_trials, int64_t* out, gcf_stream_t stream);
+
 /* Stochastic edge dropout of a sparse operator's values (buir.py:300-309 sparse_dropout):
  *   out[j] = keep(e) ? vals[e] / (1 - rate) : 0,   e = index ? index[j] : j,
  *   keep(e) <=> Philox4x32-10(counter = (e, offset), key = seed)[0] < (1 - rate) * 2^32

@@ -72,6 +72,8 @@ _SIGNATURES = {
     "gcf_rows_to_slices": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     "gcf_sample_negatives": (c_int32, [c_uint64, c_uint64, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p,
                                        c_int32, c_void_p, c_void_p]),
+    "gcf_sample_negatives_at": (c_int32, [c_uint64, c_uint64, c_int64, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p,
+                                          c_int32, c_void_p, c_void_p]),
     "gcf_philox_keys": (c_int32, [c_int64, c_uint64, c_uint64, c_void_p, c_void_p]),
     "gcf_csr_dropout_values": (c_int32, [c_void_p, c_int64, c_void_p, c_float, c_uint64, c_uint64, c_void_p, c_void_p]),
     "gcf_bpr_workspace_bytes": (c_size_t, [c_int64]),

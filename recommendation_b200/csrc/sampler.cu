@@ -33,7 +33,8 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 __global__ void __launch_bounds__(256)
 sample_negatives_kernel(uint32_t seed_lo, uint32_t key_hi, uint32_t offset_lo, const int64_t* __restrict__ users,
                         long long n_slots, int n_negs, uint32_t n_items, const int* __restrict__ pos_row_ptr,
-                        const int* __restrict__ pos_col_idx, int max_trials, int64_t* __restrict__ out) {
+                        const int* __restrict__ pos_col_idx, int max_trials, unsigned long long slot_base,
+                        int64_t* __restrict__ out) {
   for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots;
        slot += (long long)gridDim.x * blockDim.x) {
     int ps = 0, pe = 0;
@@ -45,9 +46,10 @@ sample_negatives_kernel(uint32_t seed_lo, uint32_t key_hi, uint32_t offset_lo, c
     uint32_t cand = 0;
     uint32_t w[4];
     for (int trial = 0; trial < max_trials; ++trial) {
-      if ((trial & 3) == 0)
-        philox4x32_10((uint32_t)slot, (uint32_t)((unsigned long long)slot >> 32), offset_lo, (uint32_t)(trial >> 2),
-                      seed_lo, key_hi, w);
+      if ((trial & 3) == 0) {
+        const unsigned long long gslot = slot_base + (unsigned long long)slot;   // position in the GLOBAL slot numbering
+        philox4x32_10((uint32_t)gslot, (uint32_t)(gslot >> 32), offset_lo, (uint32_t)(trial >> 2), seed_lo, key_hi, w);
+      }
       cand = __umulhi(w[trial & 3], n_items);
       // binary search in the user's sorted positives
       int lo = ps, hi = pe;
@@ -115,10 +117,10 @@ extern "C" int gcf_csr_dropout_values(const float* vals, int64_t n, const int32_
 }
 
 
-extern "C" int gcf_sample_negatives(uint64_t seed, uint64_t offset, const int64_t* users, int64_t n, int32_t n_negs,
-                                    int64_t n_items, const int32_t* pos_row_ptr, const int32_t* pos_col_idx,
-                                    int32_t max_trials, int64_t* out, gcf_stream_t stream) {
-  GCF_REQUIRE(n >= 0 && n_negs >= 1, "gcf_sample_negatives: bad n / n_negs");
+extern "C" int gcf_sample_negatives_at(uint64_t seed, uint64_t offset, int64_t slot_base, const int64_t* users, int64_t n,
+                                       int32_t n_negs, int64_t n_items, const int32_t* pos_row_ptr, const int32_t* pos_col_idx,
+                                       int32_t max_trials, int64_t* out, gcf_stream_t stream) {
+  GCF_REQUIRE(n >= 0 && n_negs >= 1 && slot_base >= 0, "gcf_sample_negatives: bad n / n_negs / slot_base");
   GCF_REQUIRE(n_items >= 1 && n_items < 4294967296LL, "gcf_sample_negatives: n_items must be in [1, 2^32)");
   if (n == 0) return GCF_OK;
   GCF_REQUIRE(out != nullptr, "gcf_sample_negatives: null out");
@@ -129,7 +131,13 @@ extern "C" int gcf_sample_negatives(uint64_t seed, uint64_t offset, const int64_
   const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(slots, 256), (long long)sm_count() * 16));
   sample_negatives_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32), (uint32_t)offset, users, slots, n_negs,
-      (uint32_t)n_items, pos_row_ptr, pos_col_idx, max_trials, out);
+      (uint32_t)n_items, pos_row_ptr, pos_col_idx, max_trials, (unsigned long long)slot_base, out);
   GCF_LAUNCH_CHECK("sample_negatives_kernel");
   return GCF_OK;
+}
+
+extern "C" int gcf_sample_negatives(uint64_t seed, uint64_t offset, const int64_t* users, int64_t n, int32_t n_negs,
+                                    int64_t n_items, const int32_t* pos_row_ptr, const int32_t* pos_col_idx,
+                                    int32_t max_trials, int64_t* out, gcf_stream_t stream) {
+  return gcf_sample_negatives_at(seed, offset, 0, users, n, n_negs, n_items, pos_row_ptr, pos_col_idx, max_trials, out, stream);
 }

@@ -659,19 +659,23 @@ static int spmm_impl(const gcf_csr_t* A, int32_t d, const float* X, int64_t ldx,
   const int dvec = d / 4;
   // flat-stream kernel: default whenever the operator carries a tile schedule and a row fits one float4 per lane.
   // variant 0 = default, 4 = the r01 row-walking kernel (kept for A/B runs), 10.. = flat-kernel tuning points
-  if (A->n_tiles > 0 && A->tiles != nullptr && (d == 8 || d == 16 || d == 32 || (d >= 36 && d <= 128)) &&
-      (variant == 0 || variant >= 10)) {
+  // Rows of 8 / 16 floats (8- and 4-way feature-sharded slices) stay on the row-walking kernel unless a flat variant is
+  // asked for: measured on cfg5 (gpurun_out/r02/exp_narrow_b_d*.log) flat vs row-walking 3.45 vs 2.54 ms (d = 8),
+  // 4.10 vs 3.70 ms (d = 16), but 4.12 vs 5.59 ms at d = 32 and 7.02 vs 9.09 ms at d = 64.
+  const bool flat_default = d == 32 || (d >= 36 && d <= 128);
+  const bool flat_capable = flat_default || d == 8 || d == 16;
+  if (A->n_tiles > 0 && A->tiles != nullptr && ((variant == 0 && flat_default) || (variant >= 10 && flat_capable))) {
     GCF_REQUIRE(A->n_empty == 0 || (A->empty_rows != nullptr && A->nz_row_ptr != nullptr && A->nz_rows != nullptr),
                 "gcf_spmm_csr_f32: operator has empty rows but no compact row numbering");
     const bool plain = adam == nullptr && epilogue == GCF_EPILOGUE_NONE && OUT == nullptr;   // Y = A X and nothing else
     // feature-sharded slices; hub chunks keep the r01 narrow-row inner loops (gathers in flight x pairs per lane)
     if (d == 8) {
       if (variant == 10) return launch_flat_narrow<2, 4, 2, 4>(plain, A, X, ldx, dvec, ep, lp, st);
-      return launch_flat_narrow<2, 3, 2, 4>(plain, A, X, ldx, dvec, ep, lp, st);
+      return launch_flat_narrow<2, 3, 2, 4>(plain, A, X, ldx, dvec, ep, lp, st);     // variant 11..
     }
     if (d == 16) {
       if (variant == 10) return launch_flat_narrow<4, 4, 4, 2>(plain, A, X, ldx, dvec, ep, lp, st);
-      return launch_flat_narrow<4, 3, 4, 2>(plain, A, X, ldx, dvec, ep, lp, st);
+      return launch_flat_narrow<4, 3, 4, 2>(plain, A, X, ldx, dvec, ep, lp, st);     // variant 11..
     }
     if (d == 32) {
       if (variant == 10) return launch_flat_narrow<8, 4, 8, 1>(plain, A, X, ldx, dvec, ep, lp, st);

@@ -31,6 +31,7 @@ import torch.distributed as dist
 
 from . import _lib
 from .graph import CSRGraph
+from .tables import xavier_uniform_table
 
 
 @dataclass(frozen=True)
@@ -172,15 +173,10 @@ class ShardedLightGCNTrainer:
         if init_table is not None:
             self.table = shard_table(init_table.to(dev)[:, lo_c:hi_c].contiguous(), plan, self.rank).contiguous()
         else:
-            gen = torch.Generator(device=dev); gen.manual_seed(seed + 17 + 1000 * self.feat_rank)
-            bound_u = (6.0 / (n_users + d_full)) ** 0.5   # xavier_uniform_ bounds of the two reference tables
-            bound_i = (6.0 / (n_items + d_full)) ** 0.5
-            nodes = plan.local_nodes(self.rank, dev)
-            t = (torch.rand(n_loc, d, device=dev, generator=gen) * 2 - 1)
-            scale = torch.where(nodes < n_users, bound_u, bound_i).to(torch.float32)
-            t[: nodes.numel()] *= scale[:, None]
-            t[nodes.numel():] = 0
-            self.table = t
+            # a pure function of (seed, node, column): independent of the layout and of the number of ranks
+            full = xavier_uniform_table(n_users, n_items, d_full, seed=seed, device=dev, cols=(lo_c, hi_c))
+            self.table = shard_table(full, plan, self.rank).contiguous()
+            del full
         self.exp_avg = torch.zeros_like(self.table)
         self.exp_avg_sq = torch.zeros_like(self.table)
 
@@ -193,15 +189,24 @@ class ShardedLightGCNTrainer:
         self.g_x0 = torch.zeros(n_loc, d, device=dev)
 
         # ---- this rank's triples, in gathered-position space ----
+        # The canonical numbering of the triples is the user-major order of the whole list (the one FusedLightGCNTrainer and
+        # the feature-sharded trainer use): rank r takes positions [lo, hi) of it, so the Philox negatives -- keyed by that
+        # position -- and with them the whole optimisation trajectory do not depend on the layout or the number of ranks.
+        u64, i64 = users.to(torch.int64), items.to(torch.int64)
+        order_global = torch.argsort(u64 * n_items + i64) if self.n_edges > 1 else torch.arange(self.n_edges, device=dev)
         lo, hi = plan.triple_range(self.n_edges, self.rank)
         self.n_triples = hi - lo
-        pos_u = plan.gathered_pos(users[lo:hi].to(torch.int64))
-        pos_i = plan.gathered_pos(items[lo:hi].to(torch.int64) + n_users)
-        # user-major order inside the rank's slice: the fused BPR kernel keeps the user row / gradient in registers
-        # over a run (the order of the triples is free: the loss is a mean over all of them)
+        sel = order_global[lo:hi]
+        del order_global
+        pos_u = plan.gathered_pos(u64[sel])
+        pos_i = plan.gathered_pos(i64[sel] + n_users)
+        del u64, i64
+        # user-major order in gathered-position space inside the slice: the fused BPR kernel keeps the user row / gradient in
+        # registers over a run (the order of the triples is free: the loss is a mean over all of them)
         self.order = torch.argsort(pos_u * plan.n_padded + pos_i) if self.n_triples > 1 else None
         if self.order is not None:
-            pos_u, pos_i = pos_u[self.order], pos_i[self.order]
+            pos_u, pos_i, sel = pos_u[self.order], pos_i[self.order], sel[self.order]
+        self.sel = sel.contiguous()            # position in the caller's list of each local triple (externally drawn negatives)
         self.pos_u, self.pos_i = pos_u.contiguous(), pos_i.contiguous()
         self.neg_raw = torch.empty(max(self.n_triples, 1), dtype=torch.int64, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
@@ -228,10 +233,16 @@ class ShardedLightGCNTrainer:
                                         _lib.float_array(list(betas)), _lib.ptr(self.ws), self.ws_bytes, 0,
                                         _lib.current_stream()), "gcf_spmm_csr_f32")
 
-    def step(self, neg_items: Optional[torch.Tensor] = None, marks: Optional[list] = None) -> torch.Tensor:
-        """One optimisation step; returns the (global) loss.  neg_items: optional pre-drawn raw item ids for this
-        rank's triples (parity tests); otherwise Philox negatives keyed by the GLOBAL triple index, so the draw is
-        independent of the number of ranks."""
+    def index_buffers(self) -> List[torch.Tensor]:
+        """The device tensors that hold this rank's training triples -- the per-step INPUT of the step (bench.py's e2e arm
+        refills them from pinned host memory every step)."""
+        return [self.pos_u, self.pos_i]
+
+    def step(self, neg_items: Optional[torch.Tensor] = None, marks: Optional[list] = None, wait_before_loss=None) -> torch.Tensor:
+        """One optimisation step; returns the (global) loss.  wait_before_loss: optional CUDA event the loss phase waits for
+        (an asynchronous refill of index_buffers()).  neg_items: optional pre-drawn raw item ids for ALL triples in
+        the caller's order, identical on every rank (parity tests); otherwise Philox negatives keyed by the GLOBAL triple index (gcf_sample_negatives_at),
+        so the draw is independent of the number of ranks."""
         lib, st, plan, d, K = self.lib, _lib.current_stream(), self.plan, self.d, self.k
         self.step_count += 1
         ev = (lambda: torch.cuda.Event(enable_timing=True)) if marks is not None else None
@@ -260,18 +271,19 @@ class ShardedLightGCNTrainer:
         dist.all_gather_into_tensor(self.final_full, final_loc, group=rg)
 
         # ---- loss on this rank's triples ----
+        if wait_before_loss is not None:
+            torch.cuda.current_stream().wait_event(wait_before_loss)
         if neg_items is None:
-            # one Philox stream per (seed, rank, step): rank in the high word of `offset` (it perturbs the key),
-            # step in the low word (a counter word)
-            # (self.rank = the row shard: identical for the ranks of a feature group, which share the triples)
-            _lib.check(lib.gcf_sample_negatives(self.seed, (self.rank << 32) | self.step_count, None, self.n_triples, 1,
-                                                self.n_items, None, None, 1, _lib.ptr(self.neg_raw), st),
-                       "gcf_sample_negatives")
+            # Philox slot = position of the triple in the caller's (global) list: rank r draws the window [lo, hi) of the
+            # stream a single-GPU run over the same list draws, then applies its local user-major permutation
+            _lib.check(lib.gcf_sample_negatives_at(self.seed, self.step_count, self.triple_offset, None, self.n_triples, 1,
+                                                   self.n_items, None, None, 1, _lib.ptr(self.neg_raw), st),
+                       "gcf_sample_negatives_at")
+            if self.order is not None and self.n_triples > 0:
+                self.neg_raw[: self.n_triples] = self.neg_raw[: self.n_triples][self.order]
             neg_raw = self.neg_raw[: self.n_triples]
         else:
-            neg_raw = neg_items.to(torch.int64)
-            if self.order is not None:
-                neg_raw = neg_raw[self.order]
+            neg_raw = neg_items.to(torch.int64).reshape(-1)[self.sel]
         neg = plan.gathered_pos(neg_raw + self.n_users).contiguous()
         w = 1.0 / self.n_edges
         # per-rank partial of the global mean: reduction = sum, loss and gradients scaled by 1/E afterwards / inside
@@ -452,11 +464,7 @@ class FeatureShardedLightGCNTrainer:
         if init_table is not None:
             self.table = init_table.to(dev)[:, self.lo:self.hi].contiguous()
         else:
-            gen = torch.Generator(device=dev); gen.manual_seed(seed * 1000 + 17 + self.rank)
-            t = torch.rand(n, dg, device=dev, generator=gen) * 2 - 1
-            t[:n_users] *= (6.0 / (n_users + d)) ** 0.5      # xavier_uniform_ bounds of the reference's two tables
-            t[n_users:] *= (6.0 / (n_items + d)) ** 0.5
-            self.table = t
+            self.table = xavier_uniform_table(n_users, n_items, d, seed=seed, device=dev, cols=(self.lo, self.hi))
         pos_u, pos_i = users.to(torch.int64), items.to(torch.int64)
         self.n_edges = self.n_triples = int(pos_u.numel())
         self.order = torch.argsort(pos_u * n_items + pos_i) if self.n_triples > 1 else None  # user-major (see lightgcn.py)
@@ -571,10 +579,11 @@ class FeatureShardedLightGCNTrainer:
         else:
             w_items, w_users = self._exchange_items(), self._exchange_users()
         if neg_items is None:
-            # one Philox stream per (seed, rank, step): rank in the high word of `offset`, step in the low word
+            # Philox slot = position in the user-major list of ALL triples: this rank draws the window [t_lo, t_hi) of the
+            # stream the single-GPU trainer (and the "scores" layout) draws, whatever the number of ranks
             if self.n_local > 0:
-                _lib.check(lib.gcf_sample_negatives(self.seed, (self.rank << 32) | self.step_count, None, self.n_local, 1,
-                                                    self.n_items, None, None, 1, _lib.ptr(self.neg), st), "gcf_sample_negatives")
+                _lib.check(lib.gcf_sample_negatives_at(self.seed, self.step_count, self.t_lo, None, self.n_local, 1,
+                                                       self.n_items, None, None, 1, _lib.ptr(self.neg), st), "gcf_sample_negatives_at")
             neg = self.neg
         else:
             neg = neg_items.to(torch.int64).reshape(-1)
@@ -615,20 +624,28 @@ class FeatureShardedLightGCNTrainer:
         w_items.wait()
         return self.loss_pt * w
 
-    def step(self, neg_items: Optional[torch.Tensor] = None, marks: Optional[list] = None) -> torch.Tensor:
+    def index_buffers(self) -> List[torch.Tensor]:
+        """The device tensors that hold this rank's training triples -- the per-step INPUT of the step (bench.py's e2e arm
+        refills them from pinned host memory every step)."""
+        return [self.loc_u, self.loc_i] if self.loss_layout == "rows" else [self.pos_u, self.pos_i]
+
+    def step(self, neg_items: Optional[torch.Tensor] = None, marks: Optional[list] = None, wait_before_loss=None) -> torch.Tensor:
         """One optimisation step; returns the (global) loss.  neg_items: optional pre-drawn item ids for ALL triples in
-        their original order (parity tests), identical on every rank."""
+        their original order (parity tests), identical on every rank.  wait_before_loss: optional CUDA event the loss phase
+        waits for (an asynchronous refill of index_buffers())."""
         lib, st, g, dg, K, u = self.lib, _lib.current_stream(), self.graph, self.dg, self.k, self.n_users
         self.step_count += 1
         if marks is not None:
             e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
             e0.record()
         if self.overlap:
-            return self._step_overlapped(neg_items, marks, (e0, e1, e2, e3) if marks is not None else None)
+            return self._step_overlapped(neg_items, marks, (e0, e1, e2, e3) if marks is not None else None, wait_before_loss)
         _lib.check(lib.gcf_propagate_fwd(g.struct_ref(), dg, K, _lib.ptr(self.table), _lib.ptr_array(self.layers),
                                          _lib.ptr(self.final), 1.0, _lib.ptr(self.ws), self.ws_bytes, st), "gcf_propagate_fwd")
         if marks is not None:
             e1.record()
+        if wait_before_loss is not None:
+            torch.cuda.current_stream().wait_event(wait_before_loss)
         if self.loss_layout == "rows":
             loss_local = self._loss_on_rows(neg_items)
         else:
@@ -655,7 +672,7 @@ class FeatureShardedLightGCNTrainer:
                                         1.0, 1.0, len(addends), _lib.ptr_array(list(addends)), _lib.float_array([1.0] * len(addends)),
                                         _lib.ptr(ws), ws_bytes, 0, _lib.current_stream()), what)
 
-    def _step_overlapped(self, neg_items, marks, events) -> torch.Tensor:
+    def _step_overlapped(self, neg_items, marks, events, wait_before_loss=None) -> torch.Tensor:
         """The step with the exchanges of the loss hidden behind row blocks of the neighbouring propagation layers."""
         lib, st, g, dg, K, u = self.lib, _lib.current_stream(), self.graph, self.dg, self.k, self.n_users
         # ---- forward: K-1 full layers, the last one (with the layer sum) item rows first ----
@@ -672,6 +689,8 @@ class FeatureShardedLightGCNTrainer:
         w_users = self._exchange_users()
         if events is not None:
             events[1].record()
+        if wait_before_loss is not None:
+            torch.cuda.current_stream().wait_event(wait_before_loss)
         loss_local, (g_users_done, g_items_done) = self._loss_on_rows(neg_items, pending=(w_items, w_users), defer_wait=True)
         if events is not None:
             events[2].record()

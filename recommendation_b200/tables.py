@@ -63,3 +63,28 @@ class JointEmbeddingDict(nn.Module):
 
     def joint_table(self) -> torch.Tensor:
         return JoinTables.apply(self.embedding_dict["user_emb"], self.embedding_dict["item_emb"])
+
+
+def xavier_uniform_table(n_users: int, n_items: int, d: int, *, seed: int, device, cols=None, chunk_rows: int = 1 << 20) -> torch.Tensor:
+    """Joint [U+I, d] table with the reference's initialisation (nn.init.xavier_uniform_ on the [U, d] and the [I, d]
+    table separately: lightgcn.py:14-17, ncl.py:409-412), as a pure function of (seed, row, column).
+
+    Rows are generated full-width in fixed chunks of `chunk_rows`, chunk c from its own generator seeded with (seed, c), and
+    `cols` = (lo, hi) keeps only that column slice -- so every rank of a feature- or row-sharded run holds exactly the
+    values the single-GPU run holds for the same entries, whatever the world size (the per-rank seeds of the
+    sharded trainers repeated rows across shards)."""
+    lo, hi = (0, d) if cols is None else cols
+    n = n_users + n_items
+    out = torch.empty(n, hi - lo, dtype=torch.float32, device=device)
+    bound_u = (6.0 / (n_users + d)) ** 0.5
+    bound_i = (6.0 / (n_items + d)) ** 0.5
+    gen = torch.Generator(device=device)
+    for c, r0 in enumerate(range(0, n, chunk_rows)):
+        r1 = min(n, r0 + chunk_rows)
+        gen.manual_seed((int(seed) * 1_000_003 + c) & 0x7FFFFFFFFFFFFFFF)
+        t = torch.rand(r1 - r0, d, device=device, generator=gen)[:, lo:hi].mul_(2.0).sub_(1.0)
+        cut = min(max(n_users - r0, 0), r1 - r0)     # rows of this chunk that are users
+        t[:cut] *= bound_u
+        t[cut:] *= bound_i
+        out[r0:r1] = t
+    return out

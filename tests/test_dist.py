@@ -116,10 +116,9 @@ def _nccl_worker(rank, world, port, n_users, n_items, users, items, table0, negs
         users_t, items_t = torch.from_numpy(users).to(dev), torch.from_numpy(items).to(dev)
         tr = ShardedLightGCNTrainer(users_t, items_t, n_users, n_items, d=table0.shape[1], n_layers=k, lr=0.01,
                                     reg_weight=1e-4, init_table=torch.from_numpy(table0), feature_shards=feature_shards)
-        lo, hi = tr.plan.triple_range(users.shape[0], tr.rank)   # tr.rank = the row shard (== rank when feature_shards == 1)
         losses = []
         for s in range(negs.shape[0]):
-            losses.append(float(tr.step(neg_items=torch.from_numpy(negs[s, lo:hi]).to(dev)).item()))
+            losses.append(float(tr.step(neg_items=torch.from_numpy(negs[s]).to(dev)).item()))
         table = tr.gathered_table().cpu().numpy()
         if rank == 0:
             out_q.put((losses, table))
