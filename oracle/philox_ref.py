@@ -32,13 +32,15 @@ def philox4x32_10(counter, key):
     return c
 
 
-def sample_negatives(seed, offset, n, n_negs, n_items, users=None, pos_row_ptr=None, pos_col_idx=None, max_trials=1):
-    """int64 [n * n_negs]; stream definition in csrc/sampler.cu's header comment."""
+def sample_negatives(seed, offset, n, n_negs, n_items, users=None, pos_row_ptr=None, pos_col_idx=None, max_trials=1,
+                     slot_base=0):
+    """int64 [n * n_negs]; stream definition in csrc/sampler.cu's header comment.  slot_base: the window
+    [slot_base, slot_base + n * n_negs) of the global slot numbering (gcf_sample_negatives_at)."""
     seed, offset = int(seed) & (2**64 - 1), int(offset) & (2**64 - 1)
     k0 = np.uint32(seed & 0xFFFFFFFF)
     k1 = np.uint32(((seed >> 32) ^ (offset >> 32)) & 0xFFFFFFFF)
     off_lo = np.uint32(offset & 0xFFFFFFFF)
-    slots = np.arange(n * n_negs, dtype=np.uint64)
+    slots = np.arange(n * n_negs, dtype=np.uint64) + np.uint64(slot_base)
     s_lo, s_hi = (slots & MASK32).astype(np.uint32), (slots >> np.uint64(32)).astype(np.uint32)
     reject = pos_row_ptr is not None
     if not reject:

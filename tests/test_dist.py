@@ -385,3 +385,63 @@ def test_rows_layout_loss_exchange_gloo_world2():
     want.backward()
     np.testing.assert_allclose(got_loss, float(want), rtol=1e-10)
     np.testing.assert_allclose(got_grad, xt.grad.numpy(), rtol=1e-9, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------- world-size independence
+def _nccl_default_init_worker(rank, world, port, n_users, n_items, users, items, k, steps, kind, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from recommendation_b200.dist import FeatureShardedLightGCNTrainer, ShardedLightGCNTrainer
+
+        users_t, items_t = torch.from_numpy(users).to(dev), torch.from_numpy(items).to(dev)
+        kw = dict(d=64, n_layers=k, lr=0.01, reg_weight=1e-4, seed=1234)      # init_table=None, Philox negatives
+        if kind == "row-sharded":
+            tr = ShardedLightGCNTrainer(users_t, items_t, n_users, n_items, **kw)
+        else:
+            tr = FeatureShardedLightGCNTrainer(users_t, items_t, n_users, n_items, loss_layout=kind, **kw)
+        losses = [float(tr.step().item()) for _ in range(steps)]
+        table = tr.gathered_table().cpu().numpy()
+        if rank == 0:
+            out_q.put((losses, table))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["rows", "scores", "row-sharded"])
+def test_seeded_runs_do_not_depend_on_the_number_of_ranks(kind):
+    """Initial table (tables.xavier_uniform_table) and Philox negatives (gcf_sample_negatives_at) are functions of the seed and
+    of the canonical user-major triple position only: an N-GPU run reproduces the single-GPU run (bench.py's `check` block)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 CUDA devices")
+    from recommendation_b200.graph import CSRGraph
+    from recommendation_b200.lightgcn import FusedLightGCNTrainer
+    from recommendation_b200.tables import xavier_uniform_table
+
+    inter = synth.power_law_bipartite(3000, 4000, 100000, seed=9)
+    U, I, d, k, steps = 3000, 4000, 64, 3, 3
+    dev = torch.device("cuda", 0)
+    users_t, items_t = torch.from_numpy(inter.users).to(dev), torch.from_numpy(inter.items).to(dev)
+    g = CSRGraph.from_pairs(users_t, items_t, U, I, norm="sym")
+    table0 = xavier_uniform_table(U, I, d, seed=1234, device=dev)
+    assert torch.unique(table0, dim=0).shape[0] == U + I
+    ref = FusedLightGCNTrainer(g, U, I, table0.clone(), users_t, items_t, n_layers=k, lr=0.01, reg_weight=1e-4, seed=1234)
+    want_losses = [float(ref.step().item()) for _ in range(steps)]
+    world = min(torch.cuda.device_count(), 8)
+    world = 8 if world >= 8 else (4 if world >= 4 else 2)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_default_init_worker, args=(r, world, port, U, I, inter.users, inter.items, k, steps, kind, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    got_losses, got_table = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    np.testing.assert_allclose(got_losses, want_losses, rtol=1e-4)
+    _tables_close(got_table, ref.table.cpu().numpy())

@@ -484,19 +484,20 @@ def test_ncl_training_iteration_runs_and_learns(cuda):
     U, I, E = 400, 500, 12000
     u = rng.integers(0, U, E); i = (rng.zipf(1.5, E) - 1) % I
     raw = sp.coo_matrix((np.ones(2 * E, np.float32), (np.concatenate([u, i + U]), np.concatenate([i + U, u]))), shape=(U + I, U + I))
-    data = SimpleNamespace(user_num=U, item_num=I, norm_adj=raw, training_data=[[f"u{a}", f"i{b}", 1.0] for a, b in zip(u, i)],
+    # The learning check runs on the sym-normalised operator: with ncl.py's RAW adjacency (ncl.py:76-85, covered by the
+    # fixtures) activations grow by ~deg per layer (score differences ~1e5 here), the eps-sigmoid saturates and the
+    # trajectory is chaotic -- an fp32 CPU restatement of this loop moves 0.67 -> 0.26 in 4 epochs on the normalised one.
+    deg = np.asarray(raw.tocsr().sum(1)).ravel()
+    dinv = np.where(deg > 0, 1.0 / np.sqrt(np.maximum(deg, 1e-12)), 0.0)
+    norm = (sp.diags(dinv) @ raw.tocsr() @ sp.diags(dinv)).tocoo().astype(np.float32)
+    data = SimpleNamespace(user_num=U, item_num=I, norm_adj=norm, training_data=[[f"u{a}", f"i{b}", 1.0] for a, b in zip(u, i)],
                            user={f"u{a}": a for a in range(U)}, item={f"i{b}": b for b in range(I)})
     torch.manual_seed(0)
     model = encoders.LGCNEncoder(data, 64, 3)
-    with torch.no_grad():   # the raw (un-normalised) adjacency of ncl.py grows activations by ~deg per layer
-        for p in model.parameters():
-            p.mul_(0.01)
     ncl = NCLLosses(U, I, 0.1, 1e-6, 1.5, 8e-8, 512)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     k = ncl_mod.e_step(model, ncl, 20)
     assert k == max(2, min(20, U // 39)) and ncl.user_2cluster.shape == (U,) and ncl.item_centroids.shape[1] == 64
-    import random
-    random.seed(0); np.random.seed(0)
     per_epoch = []
     for epoch in range(4):
         rec = []
@@ -505,7 +506,16 @@ def test_ncl_training_iteration_runs_and_learns(cuda):
             assert torch.isfinite(total) and all(torch.isfinite(v) for v in parts.values())
             rec.append(parts["rec"].item())
         per_epoch.append(float(np.mean(rec)))
-    assert per_epoch[-1] < per_epoch[0], per_epoch      # the ranking loss goes down (epoch means: single batches are noisy)
+    assert 0.6 < per_epoch[0] < 0.72, per_epoch         # -log(sigmoid(~0)) at the start
+    assert per_epoch[-1] < 0.75 * per_epoch[0], per_epoch      # the ranking loss goes down (epoch means: single batches are noisy)
+    # the reference's raw operator: one epoch runs and stays finite (values are not meaningful in that regime, see above)
+    data_raw = SimpleNamespace(user_num=U, item_num=I, norm_adj=raw, training_data=data.training_data, user=data.user, item=data.item)
+    model_raw = encoders.LGCNEncoder(data_raw, 64, 3)
+    opt_raw = torch.optim.Adam(model_raw.parameters(), lr=1e-3)
+    ncl_mod.e_step(model_raw, ncl, 20)
+    for n, batch in enumerate(sampling.next_batch_pairwise(data_raw, 512)):
+        total, parts = ncl_mod.ncl_step(model_raw, ncl, opt_raw, batch, 1e-4, 512, 1, k=k, refresh_clusters=(n % 8 == 0))
+        assert torch.isfinite(total) and all(torch.isfinite(v) for v in parts.values())
 
 
 # ------------------------------------------------------------------------------------------ MHCN motif matrices (8f row 4)

@@ -316,6 +316,42 @@ def test_sampler_bit_exact_vs_oracle(cuda):
     assert not any((u, j) in pos for u, j in zip(users.tolist(), got.cpu().tolist()))
 
 
+def test_sampler_window_equals_slice_of_the_full_draw(cuda):
+    """gcf_sample_negatives_at: a rank that owns triples [t0, t1) draws exactly that window of the single-GPU stream."""
+    from recommendation_b200 import _lib
+    lib = _lib.load()
+    n, n_items, n_negs = 10_000, 4321, 3
+    full = F_.sample_negatives(n, n_items, seed=99, offset=7, n_negs=n_negs, device=cuda)
+    for t0, t1 in ((0, 17), (17, 5000), (5000, n)):
+        out = torch.empty((t1 - t0) * n_negs, dtype=torch.int64, device=cuda)
+        _lib.check(lib.gcf_sample_negatives_at(99, 7, t0 * n_negs, None, t1 - t0, n_negs, n_items, None, None, 1, _lib.ptr(out),
+                                               _lib.current_stream()), "gcf_sample_negatives_at")
+        assert torch.equal(out.view(-1, n_negs), full[t0:t1])
+    # the oracle's stream definition, at a window that crosses 2^32 slots
+    base = (1 << 32) - 5
+    out = torch.empty(10, dtype=torch.int64, device=cuda)
+    _lib.check(lib.gcf_sample_negatives_at(3, 1, base, None, 10, 1, 1000, None, None, 1, _lib.ptr(out), _lib.current_stream()),
+               "gcf_sample_negatives_at")
+    from oracle import philox_ref
+    want = philox_ref.sample_negatives(3, 1, 10, 1, 1000, slot_base=base)
+    assert out.cpu().tolist() == want.tolist()
+
+
+def test_xavier_table_is_a_function_of_seed_row_and_column(cuda):
+    """sharded trainers must not repeat rows across shards; any column slice equals the full table's."""
+    from recommendation_b200.tables import xavier_uniform_table
+    U, I, d = 5000, 3000, 64
+    full = xavier_uniform_table(U, I, d, seed=5, device=cuda, chunk_rows=1024)
+    for lo, hi in ((0, 8), (8, 16), (32, 64)):
+        assert torch.equal(xavier_uniform_table(U, I, d, seed=5, device=cuda, cols=(lo, hi), chunk_rows=1024), full[:, lo:hi])
+    assert torch.unique(full, dim=0).shape[0] == U + I                                  # no duplicate rows
+    bu, bi = (6.0 / (U + d)) ** 0.5, (6.0 / (I + d)) ** 0.5
+    assert float(full[:U].abs().max()) <= bu and float(full[U:].abs().max()) <= bi
+    assert float(full[:U].abs().max()) > 0.99 * bu and float(full[U:].abs().max()) > 0.99 * bi
+    assert abs(float(full[:U].std()) / (bu / 3 ** 0.5) - 1) < 0.02                          # uniform(-b, b): std = b / sqrt(3)
+    assert not torch.equal(full, xavier_uniform_table(U, I, d, seed=6, device=cuda, chunk_rows=1024))
+
+
 @pytest.mark.parametrize("wd,decoupled", [(0.0, False), (1e-2, False), (1e-2, True)])
 def test_adam_matches_torch(cuda, wd, decoupled):
     torch.manual_seed(0)
@@ -504,8 +540,9 @@ def test_train_steps_track_reference_optimisation(cuda):
 
 # ====================================================================== full-size properties (BASELINE cfg 1)
 def test_cfg1_size_properties(cuda):
-    """At the full Gowalla-shaped size the oracle is too slow for every check, so use size-independent properties:
-    structural identities of the CSR, linearity and symmetry of the operator, and a float64 spot check of rows."""
+    """Size-independent properties at the full Gowalla-shaped size (the oracle comparison at this size is
+    tests/test_gpu_fullsize_oracle.py): structural identities of the CSR, linearity and symmetry of the operator, and a
+    float64 spot check of rows."""
     inter, d, K = synth.config_graph("cfg1")
     U, I = inter.n_users, inter.n_items
     csr = CSRGraph.from_pairs(dev_t(inter.users, cuda), dev_t(inter.items, cuda), U, I, norm="sym")
