@@ -303,6 +303,17 @@ int gcf_adam_rows_step(float* param, int64_t ld, const float* grad_rows, int64_t
                        const int64_t* rows, int64_t n_rows, int32_t d, float lr, float beta1, float beta2, float eps,
                        float weight_decay, int32_t decoupled, int64_t step, gcf_stream_t stream);
 
+/* Lloyd's k-means on the device: NCL's E-step (ncl.py:339-356, faiss.Kmeans(d, k).train(x) + index.search(x, 1), which the
+ * reference runs on the CPU inside every batch, ncl.py:313,324).  x [n, d] fp32 (leading dimension ldx); centroids [k, d]
+ * fp32 contiguous, IN: the initial centroids, OUT: the trained ones.  n_iter Lloyd iterations (faiss default 25), then one
+ * more assignment pass: assign[n] (int64, nullable) = nearest centroid, dist[n] (nullable) = squared distance to it.
+ * Distances on the tcgen05 tensor cores with bf16 hi/lo split operands (~fp32 accuracy), ties to the lowest index;
+ * centroid sums in a fixed order (deterministic); empty clusters re-seeded from the largest ones, all on the device:
+ * no host synchronisation.  d % 4 == 0, d <= 1024, 1 <= k <= n. */
+size_t gcf_kmeans_workspace_bytes(int64_t n, int32_t k, int32_t d);
+int gcf_kmeans_lloyd(const float* x, int64_t ldx, int64_t n, int32_t d, int32_t k, int32_t n_iter, float* centroids,
+                     int64_t* assign, float* dist, void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+
 /* x[0..n) *= *g (device scalar); returns without touching memory when *g == 1.  Used to apply the upstream
  * gradient to tables whose gradient was produced in the forward pass (gcf_bpr_fwd_bwd). */
 int gcf_scale_by_device_scalar(float* x, int64_t n, const float* g, gcf_stream_t stream);

@@ -94,6 +94,9 @@ _SIGNATURES = {
                                         c_int32, c_void_p]),
     "gcf_adam_rows_step": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                      c_float, c_float, c_float, c_float, c_float, c_int32, c_int64, c_void_p]),
+    "gcf_kmeans_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "gcf_kmeans_lloyd": (c_int32, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_size_t, c_void_p]),
     "gcf_infonce_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
     "gcf_infonce_fwd": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32, c_float,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -6,6 +6,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <mutex>
+#include <cuda_bf16.h>
+#include "common.cuh"
 
 namespace gcf {
 namespace tc {
@@ -144,4 +147,38 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int m, int n, int a_mn_maj
 }
 
 }  // namespace tc
+
+// ---- host: TMA descriptors ----------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// bf16 row-major [rows, d_pad] matrix, box = [box_rows x 64] with the 128-byte swizzle
+inline int make_tmap(CUtensorMap* map, const void* base, long long rows, int d_pad, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return GCF_ECUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)d_pad * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return GCF_ECUDA; }
+  return GCF_OK;
+}
+
 }  // namespace gcf

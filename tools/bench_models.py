@@ -42,8 +42,13 @@ ncl = losses.NCLLosses(data.user_num, data.item_num, 0.1, 1e-6, 1.5, 8e-8, 4096)
 opt = torch.optim.Adam(model.parameters(), lr=1e-3)
 t0 = time.perf_counter(); k = ncl_mod.e_step(model, ncl, 1000); torch.cuda.synchronize()
 res["ncl_e_step_ms (k-means of 52,643 + 91,599 rows, k=%d)" % k] = (time.perf_counter() - t0) * 1e3
+torch.cuda.synchronize(); t0 = time.perf_counter(); ncl_mod.e_step(model, ncl, 1000); torch.cuda.synchronize()
+res["ncl_e_step_ms, warm (second call)"] = (time.perf_counter() - t0) * 1e3
 res["ncl_step_ms (cfg2, B=4096, 3 layers, BPR + ssl_layer + ProtoNCE + Adam)"] = timed(
     lambda b: ncl_mod.ncl_step(model, ncl, opt, b, 1e-4, 4096, 1), smp.batches(4096))
+# the reference's own iteration: e_step() after every batch (ncl.py:324)
+res["ncl_step_ms with the E-step inside every batch (ncl.py:324: refresh_clusters=True)"] = timed(
+    lambda b: ncl_mod.ncl_step(model, ncl, opt, b, 1e-4, 4096, 1, k=k, refresh_clusters=True), smp.batches(4096), warm=2, iters=10)
 del model, opt
 data, smp, d, K = data_for("cfg3", raw=True)
 model = encoders.LGCNEncoder(data, d, K)
