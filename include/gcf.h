@@ -122,6 +122,11 @@ typedef struct gcf_csr {
   const int32_t* empty_rows;     /* [n_empty] */
   const int32_t* nz_row_ptr;     /* [n_rows - n_empty + 1] */
   const int32_t* nz_rows;        /* [n_rows - n_empty] */
+  /* hub flags (optional, NULL: none): a copy of col_idx whose bit 31 marks the entries that reference a "hub" column
+   * (one of the most-referenced columns of that half of the operator).  The flat-stream kernel keeps the rows of hub
+   * columns resident in the SM's L1 / shared-memory SRAM (L1::evict_last) and lets all other gathers bypass it
+   * (L1::no_allocate): per-SM staging of the hub rows for operators whose working set is L2-resident. */
+  const int32_t* hub_col_idx;    /* [nnz] */
 } gcf_csr_t;
 
 #define GCF_MAX_ADDENDS 8
@@ -415,6 +420,24 @@ int gcf_sort_unique_u64(const uint64_t* keys, int64_t n, uint64_t* uniq, int64_t
 /* idx[i] = position of keys[i] in the ascending table, -1 when absent (ids that only occur in the test file). */
 int gcf_lookup_sorted_u64(const uint64_t* table, int64_t n_table, const uint64_t* keys, int64_t n, int64_t* idx,
                           gcf_stream_t stream);
+
+/* The same three steps for ids of up to 8 * n_words bytes (ncl.py:60-61 sorts arbitrary id strings): a key is n_words
+ * 64-bit words (left-aligned, big-endian, zero padded), stored word-major: word w of record r at keys[w * n + r]; the
+ * lexicographic order of the word tuples is the byte-wise order of the strings.
+ *   gcf_text_parse_pairs_words  first / second [n_words][n_records]; status[0]: bit 1 = a record with fewer than two fields,
+ *                               bit 2 = a token longer than 8 * n_words bytes; status[1] = length of the longest token
+ *                               (call with n_words = 1 first, widen if bit 2 is set).  Workspace: as gcf_text_parse_pairs.
+ *   gcf_sort_unique_words       stable LSD radix sort word by word + run heads: uniq [n_words][n] (word-major with stride n)
+ *                               distinct keys ascending, first_pos / n_uniq as above, rank[n] (nullable) = position of every
+ *                               input key in the distinct table (its dense "sorted" index).
+ *   gcf_lookup_sorted_words     binary search with word-tuple comparison; table is word-major with stride table_stride. */
+int gcf_text_parse_pairs_words(const uint8_t* text, int64_t n_bytes, int32_t n_words, int64_t n_records, uint64_t* first,
+                               uint64_t* second, int32_t* status, void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+size_t gcf_sort_unique_words_workspace_bytes(int64_t n);
+int gcf_sort_unique_words(const uint64_t* keys, int32_t n_words, int64_t n, uint64_t* uniq, int64_t* first_pos, int64_t* n_uniq,
+                          int64_t* rank, void* workspace, size_t workspace_bytes, gcf_stream_t stream);
+int gcf_lookup_sorted_words(const uint64_t* table, int32_t n_words, int64_t n_table, int64_t table_stride, const uint64_t* keys,
+                            int64_t n, int64_t* idx, gcf_stream_t stream);
 
 /* ---- batched evaluation ---------------------------------------------------
  *

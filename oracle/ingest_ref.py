@@ -35,3 +35,13 @@ def pack_key(s: str) -> int:
     if len(b) > 8:
         raise ValueError("id longer than 8 bytes")
     return int.from_bytes(b.ljust(8, b"\0"), "big")
+
+
+def pack_words(s: str, n_words: int) -> Tuple[int, ...]:
+    """The key tuple of an id of up to 8 * n_words bytes (gcf_text_parse_pairs_words): big-endian 64-bit words of the
+    zero-padded byte string; tuple order == byte-wise string order for ASCII ids."""
+    b = s.encode("ascii")
+    if len(b) > 8 * n_words:
+        raise ValueError("id longer than the key")
+    b = b.ljust(8 * n_words, b"\0")
+    return tuple(int.from_bytes(b[8 * w: 8 * w + 8], "big") for w in range(n_words))

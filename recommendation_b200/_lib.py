@@ -33,7 +33,7 @@ class CsrStruct(ctypes.Structure):
         ("chunk", c_int32), ("n_long", c_int32), ("n_chunks", c_int32),
         ("long_rows", c_void_p), ("long_chunk_ptr", c_void_p), ("chunk_long", c_void_p),
         ("tiles", c_void_p), ("n_tiles", c_int32), ("n_empty", c_int32), ("empty_rows", c_void_p),
-        ("nz_row_ptr", c_void_p), ("nz_rows", c_void_p),
+        ("nz_row_ptr", c_void_p), ("nz_rows", c_void_p), ("hub_col_idx", c_void_p),
     ]
 
 
@@ -115,6 +115,12 @@ _SIGNATURES = {
     "gcf_sort_unique_workspace_bytes": (c_size_t, [c_int64]),
     "gcf_sort_unique_u64": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gcf_lookup_sorted_u64": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "gcf_text_parse_pairs_words": (c_int32, [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                             c_void_p]),
+    "gcf_sort_unique_words_workspace_bytes": (c_size_t, [c_int64]),
+    "gcf_sort_unique_words": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                        c_void_p]),
+    "gcf_lookup_sorted_words": (c_int32, [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "gcf_masked_topn": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_void_p,
                                   c_void_p, c_void_p]),
     "gcf_ranking_hits": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,

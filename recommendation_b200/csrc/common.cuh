@@ -105,6 +105,18 @@ __device__ __forceinline__ float4 ldg_f4_stream(const float4* p, uint64_t pol_fi
       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol_first));
   return v;
 }
+// L1 residency by eviction priority (the SM's L1 and shared memory are one SRAM array): rows of hub columns are kept,
+// everything else passes through without allocating a line, so the L1 behaves as a demand-filled hub-row cache.
+__device__ __forceinline__ float4 ldg_f4_l1_keep(const float4* p) {
+  float4 v;
+  asm("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_f4_l1_bypass(const float4* p) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ int ld_stream_i32_hint(const int32_t* p, uint64_t pol) {
   int v;
   asm("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));

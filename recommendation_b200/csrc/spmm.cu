@@ -130,7 +130,11 @@ __device__ __forceinline__ void accumulate(const int* __restrict__ col_idx, cons
 // (col, val) request per iteration would leave just LPR row gathers in flight.  Each lane loads PPL pairs
 // (stride LPR) instead and the sub-warp keeps LPR * PPL predicated 128-bit gathers in flight; the FMA order is
 // the entry order of accumulate<>, so the result is bit-identical to it.
-template <int LPR, int PPL>
+// NA (tuning variants 5 / 6 only): gathers with L1::no_allocate.  A default (L1-allocating) load of a 32 / 64-byte row fills
+// the whole 128-byte L1 line: ncu of the d = 16 kernel shows 3.9 sectors requested from the L2 per 2-sector gather
+// (profiles/r02_ncu_narrow16.md).  Bypassing the L1 is nevertheless SLOWER (cfg5: d = 8 2.54 -> 3.39 ms, d = 16 3.70 -> 4.19 ms,
+// gpurun_out/r02/exp_narrow_na_d*.log): the neighbour row that rides along is often wanted too, so the default stays.
+template <int LPR, int PPL, bool NA = false>
 __device__ __forceinline__ void accumulate_multi(const int* __restrict__ col_idx, const float* __restrict__ vals,
                                                  int begin, int end, int stride, const float* __restrict__ X,
                                                  long long ldx, int sl, unsigned mask, float4& acc) {
@@ -158,7 +162,10 @@ __device__ __forceinline__ void accumulate_multi(const int* __restrict__ col_idx
         const int ct = __shfl_sync(mask, c[p], t, LPR);
         w[p][t] = __shfl_sync(mask, v[p], t, LPR);
         x[p][t] = f4_zero();
-        if (ct >= 0) x[p][t] = __ldg(reinterpret_cast<const float4*>(X + (long long)ct * ldx) + sl);
+        if (ct >= 0) {
+          const float4* xp = reinterpret_cast<const float4*>(X + (long long)ct * ldx) + sl;
+          x[p][t] = NA ? ldg_f4_l1_bypass(xp) : __ldg(xp);
+        }
       }
 #pragma unroll
     for (int p = 0; p < PPL; ++p)
@@ -223,7 +230,7 @@ __device__ __forceinline__ void finish_row(const Epi& ep, long long row, int sl,
 
 // Long rows (power-law hubs): one warp per chunk of `lp.chunk` entries; the last-arriving chunk of a row reduces the
 // partial sums in chunk order (deterministic) and runs the epilogue.
-template <int LPR, int VPL, int UNR, bool GUARD, int PPL>
+template <int LPR, int VPL, int UNR, bool GUARD, int PPL, bool NA = false>
 __device__ __forceinline__ void long_chunk_path(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
                                                 const float* __restrict__ vals, const float* __restrict__ X,
                                                 long long ldx, int dvec, const Epi& ep, const LongPlan& lp, int warp,
@@ -240,7 +247,7 @@ __device__ __forceinline__ void long_chunk_path(const int* __restrict__ row_ptr,
   const int s = rs + (chunk_id - c0) * lp.chunk;
   const int e = min(s + lp.chunk, re);
   if constexpr (PPL > 1)
-    accumulate_multi<LPR, PPL>(col_idx, vals, s + sub * LPR, e, LPR * RPW, X, ldx, sl, mask, acc[0]);
+    accumulate_multi<LPR, PPL, NA>(col_idx, vals, s + sub * LPR, e, LPR * RPW, X, ldx, sl, mask, acc[0]);
   else
     accumulate<LPR, VPL, UNR, GUARD>(col_idx, vals, s + sub * LPR, e, LPR * RPW, X, ldx, sl, mask, dvec, acc);
   __syncwarp();
@@ -287,7 +294,7 @@ __device__ __forceinline__ void long_chunk_path(const int* __restrict__ row_ptr,
   return;
 }
 
-template <int LPR, int VPL, int UNR, bool GUARD, int MINB, int PPL = 1>
+template <int LPR, int VPL, int UNR, bool GUARD, int MINB, int PPL = 1, bool NA = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 spmm_csr_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx, const float* __restrict__ vals,
                 long long n_rows, const float* __restrict__ X, long long ldx, int dvec, Epi ep, LongPlan lp,
@@ -304,7 +311,7 @@ spmm_csr_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx
   for (int k = 0; k < VPL; ++k) acc[k] = f4_zero();
 
   if ((int)blockIdx.x < long_blocks) {
-    long_chunk_path<LPR, VPL, UNR, GUARD, PPL>(row_ptr, col_idx, vals, X, ldx, dvec, ep, lp, warp, lane, sub, sl, mask, acc);
+    long_chunk_path<LPR, VPL, UNR, GUARD, PPL, NA>(row_ptr, col_idx, vals, X, ldx, dvec, ep, lp, warp, lane, sub, sl, mask, acc);
     return;
   }
 
@@ -314,13 +321,13 @@ spmm_csr_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx
   const int s = row_ptr[row], e = row_ptr[row + 1];
   if (lp.n_long > 0 && e - s > lp.chunk) return;  // owned by the long path
   if constexpr (PPL > 1)
-    accumulate_multi<LPR, PPL>(col_idx, vals, s, e, LPR, X, ldx, sl, mask, acc[0]);
+    accumulate_multi<LPR, PPL, NA>(col_idx, vals, s, e, LPR, X, ldx, sl, mask, acc[0]);
   else
     accumulate<LPR, VPL, UNR, GUARD>(col_idx, vals, s, e, LPR, X, ldx, sl, mask, dvec, acc);
   finish_row<LPR, VPL, GUARD>(ep, row, sl, mask, dvec, acc);
 }
 
-template <int LPR, int VPL, int UNR, bool GUARD, int MINB, int PPL = 1>
+template <int LPR, int VPL, int UNR, bool GUARD, int MINB, int PPL = 1, bool NA = false>
 static int launch(const gcf_csr_t* A, const float* X, long long ldx, int dvec, const Epi& ep, const LongPlan& lp,
                   cudaStream_t st) {
   constexpr int RPW = 32 / LPR;
@@ -330,7 +337,7 @@ static int launch(const gcf_csr_t* A, const float* X, long long ldx, int dvec, c
   if (grid <= 0) return GCF_OK;
   GCF_REQUIRE(grid < 2147483647LL, "gcf_spmm_csr_f32: grid too large");
   static_assert(PPL == 1 || (VPL == 1 && !GUARD), "multi-pair batches are for exact narrow rows");
-  spmm_csr_kernel<LPR, VPL, UNR, GUARD, MINB, PPL><<<(unsigned)grid, kWarpsPerBlock * 32, 0, st>>>(
+  spmm_csr_kernel<LPR, VPL, UNR, GUARD, MINB, PPL, NA><<<(unsigned)grid, kWarpsPerBlock * 32, 0, st>>>(
       A->row_ptr, A->col_idx, A->vals, A->n_rows, X, ldx, dvec, ep, lp, long_blocks);
   GCF_LAUNCH_CHECK("spmm_csr_kernel");
   return GCF_OK;
@@ -369,11 +376,26 @@ __device__ __forceinline__ void prefetch_epilogue(const Epi& ep, long long row, 
 //                of gathers, where no gathered row is live in registers; at most UNR rows complete per group.
 // Narrow rows (d/G = 8, 16, 32 floats in the multi-GPU layouts) have LPR = 2, 4, 8 lanes per row: a batch then holds
 // BS = LPR * PPL = 16 entries, every lane carrying PPL (col, val) pairs and PPL rows of the row window.
-template <int LPR, int PPL, int UNR, bool GUARD, bool STASH, int MINB, int LONG_UNR, int LONG_PPL>
+// HUB: the tiles read their columns from col_hub, a copy of col_idx in which bit 31 marks the entries whose column is one
+// of the most-referenced ("hub") columns of that half of the operator (graph.py: CSRGraph hub flags).  Hub rows are gathered
+// with L1::evict_last, all other rows with L1::no_allocate: the SM's L1 then holds the hub rows only -- a demand-filled,
+// per-SM staging of the hub rows in the L1 / shared-memory SRAM, shared by the CTAs resident on the SM.  Worth it when
+// the working set is L2-resident (the launch is then bound by the L2 -> SM path, not by HBM).
+template <bool HUB>
+__device__ __forceinline__ float4 gather_row(const float4* __restrict__ Xl, int c, unsigned ldx4) {
+  if constexpr (!HUB) {
+    return __ldg(Xl + (unsigned long long)(unsigned)c * ldx4);
+  } else {
+    const float4* p = Xl + (unsigned long long)((unsigned)c & 0x7fffffffu) * ldx4;
+    return c < 0 ? ldg_f4_l1_keep(p) : ldg_f4_l1_bypass(p);
+  }
+}
+
+template <int LPR, int PPL, int UNR, bool GUARD, bool STASH, int MINB, int LONG_UNR, int LONG_PPL, bool HUB = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 spmm_flat_kernel(const int* __restrict__ col_idx, const float* __restrict__ vals, const float* __restrict__ X,
                  long long ldx, int dvec, const __grid_constant__ Epi ep, LongPlan lp, const int* __restrict__ row_ptr,
-                 int long_blocks, int tile_blocks, TilePlan tp) {
+                 int long_blocks, int tile_blocks, TilePlan tp, const int* __restrict__ col_hub) {
   constexpr int RPW = 32 / LPR;
   constexpr int BS = LPR * PPL;            // entries per batch of one sub-warp
   constexpr int SLOTS = STASH ? UNR : 1;
@@ -423,6 +445,7 @@ spmm_flat_kernel(const int* __restrict__ col_idx, const float* __restrict__ vals
   const unsigned ldx4 = (unsigned)(ldx >> 2);   // 32 x 32 -> 64-bit address products (one IMAD.WIDE.U32 each)
   const unsigned ldy4 = (unsigned)(ep.ldy >> 2);
   const bool renumbered = tp.ids != nullptr;
+  const int* __restrict__ cols = HUB ? col_hub : col_idx;
 
   // (col, val) of batch 0 and the row window of batch 0.  Slots past the tile's last entry repeat its last column
   // with weight 0: their gathers hit L1 and cannot bring a non-finite value into a row that does not already hold it.
@@ -434,7 +457,7 @@ spmm_flat_kernel(const int* __restrict__ col_idx, const float* __restrict__ vals
     if (has_tile) {
       const int t = p * LPR + sl;
       const int jj = min(j + t, jend - 1);
-      c[p] = ld_stream_i32(col_idx + jj);
+      c[p] = ld_stream_i32(cols + jj);
       if (j + t < jend) v[p] = ld_stream_f32(vals + jj);
       my_end[p] = __ldg(tp.rp + min(k + 1 + t, k1));
       my_row[p] = renumbered ? __ldg(tp.ids + min(k + t, k1 - 1)) : k + t;
@@ -457,7 +480,7 @@ spmm_flat_kernel(const int* __restrict__ col_idx, const float* __restrict__ vals
       const int t = BS + p * LPR + sl;
       if (j + BS < jend) {
         const int jj = min(j + t, jend - 1);
-        c[p] = ld_stream_i32(col_idx + jj);
+        c[p] = ld_stream_i32(cols + jj);
         if (j + t < jend) v[p] = ld_stream_f32(vals + jj);
       }
     }
@@ -468,10 +491,10 @@ spmm_flat_kernel(const int* __restrict__ col_idx, const float* __restrict__ vals
 #pragma unroll
         for (int u = 0; u < UNR; u += 4) {
           const int4 cc = *reinterpret_cast<const int4*>(cs + t0 + u);   // four columns per broadcast LDS.128
-          x[u + 0] = col_ok ? __ldg(Xl + (unsigned long long)(unsigned)cc.x * ldx4) : f4_zero();
-          x[u + 1] = col_ok ? __ldg(Xl + (unsigned long long)(unsigned)cc.y * ldx4) : f4_zero();
-          x[u + 2] = col_ok ? __ldg(Xl + (unsigned long long)(unsigned)cc.z * ldx4) : f4_zero();
-          x[u + 3] = col_ok ? __ldg(Xl + (unsigned long long)(unsigned)cc.w * ldx4) : f4_zero();
+          x[u + 0] = col_ok ? gather_row<HUB>(Xl, cc.x, ldx4) : f4_zero();
+          x[u + 1] = col_ok ? gather_row<HUB>(Xl, cc.y, ldx4) : f4_zero();
+          x[u + 2] = col_ok ? gather_row<HUB>(Xl, cc.z, ldx4) : f4_zero();
+          x[u + 3] = col_ok ? gather_row<HUB>(Xl, cc.w, ldx4) : f4_zero();
         }
       }
       if (t0 == 0) {
@@ -534,7 +557,7 @@ spmm_flat_kernel(const int* __restrict__ col_idx, const float* __restrict__ vals
   }
 }
 
-template <int LPR, int PPL, int UNR, bool GUARD, bool STASH, int MINB, int LONG_UNR, int LONG_PPL>
+template <int LPR, int PPL, int UNR, bool GUARD, bool STASH, int MINB, int LONG_UNR, int LONG_PPL, bool HUB = false>
 static int launch_flat(const gcf_csr_t* A, const float* X, long long ldx, int dvec, const Epi& ep, const LongPlan& lp,
                        cudaStream_t st) {
   constexpr int RPW = 32 / LPR;
@@ -547,18 +570,18 @@ static int launch_flat(const gcf_csr_t* A, const float* X, long long ldx, int dv
   TilePlan tp{reinterpret_cast<const int2*>(A->tiles), A->n_tiles, A->n_empty > 0 ? A->nz_row_ptr : A->row_ptr,
               A->n_empty > 0 ? A->nz_rows : nullptr, A->empty_rows, A->n_empty};
   static const int pad_smem = getenv("GCF_SPMM_PAD_SMEM") ? atoi(getenv("GCF_SPMM_PAD_SMEM")) : 0;   // L1-capacity probe
-  spmm_flat_kernel<LPR, PPL, UNR, GUARD, STASH, MINB, LONG_UNR, LONG_PPL><<<(unsigned)grid, kWarpsPerBlock * 32, pad_smem, st>>>(
-      A->col_idx, A->vals, X, ldx, dvec, ep, lp, A->row_ptr, long_blocks, (int)tile_blocks, tp);
+  spmm_flat_kernel<LPR, PPL, UNR, GUARD, STASH, MINB, LONG_UNR, LONG_PPL, HUB><<<(unsigned)grid, kWarpsPerBlock * 32, pad_smem, st>>>(
+      A->col_idx, A->vals, X, ldx, dvec, ep, lp, A->row_ptr, long_blocks, (int)tile_blocks, tp, A->hub_col_idx);
   GCF_LAUNCH_CHECK("spmm_flat_kernel");
   return GCF_OK;
 }
 
 // full-width rows: one (col, val) pair per lane, hub chunks on the r01 inner loop with 8 gathers in flight
-template <int LPR, int UNR, bool GUARD, int MINB>
+template <int LPR, int UNR, bool GUARD, int MINB, bool HUB = false>
 static int launch_flat_cls(bool plain, const gcf_csr_t* A, const float* X, long long ldx, int dvec, const Epi& ep,
                            const LongPlan& lp, cudaStream_t st) {
-  if (plain) return launch_flat<LPR, 1, UNR, GUARD, false, MINB, 8, 1>(A, X, ldx, dvec, ep, lp, st);
-  return launch_flat<LPR, 1, (UNR > 8 ? 8 : UNR), GUARD, true, MINB, 8, 1>(A, X, ldx, dvec, ep, lp, st);   // stash: UNR slots of a row each
+  if (plain) return launch_flat<LPR, 1, UNR, GUARD, false, MINB, 8, 1, HUB>(A, X, ldx, dvec, ep, lp, st);
+  return launch_flat<LPR, 1, (UNR > 8 ? 8 : UNR), GUARD, true, MINB, 8, 1, HUB>(A, X, ldx, dvec, ep, lp, st);   // stash: UNR slots of a row each
 }
 // narrow rows: 16-entry batches (8-entry batches at 2 lanes per row: 16 sub-warps per warp share the 48 KB)
 template <int LPR, int MINB, int LONG_UNR, int LONG_PPL>
@@ -682,6 +705,15 @@ static int spmm_impl(const gcf_csr_t* A, int32_t d, const float* X, int64_t ldx,
       return launch_flat_narrow<8, 3, 8, 1>(plain, A, X, ldx, dvec, ep, lp, st);
     }
     // measured on cfg1 / cfg5 (profiles/r02_exp_spmm_*.log): 8 gathers in flight per sub-warp at 3 CTAs / SM
+    // hub flags present (L2-resident operators, graph.py): hub rows kept in L1, cold rows bypass it.  variant 15 = the
+    // same kernel without the flags (A/B)
+    if (A->hub_col_idx != nullptr && variant != 15) {
+      if (d == 64) {
+        if (variant == 16) return launch_flat_cls<16, 8, false, 3, true>(plain, A, X, ldx, dvec, ep, lp, st);
+        return launch_flat_cls<16, 8, false, 4, true>(plain, A, X, ldx, dvec, ep, lp, st);
+      }
+      if (d == 128) return launch_flat_cls<32, 8, false, 3, true>(plain, A, X, ldx, dvec, ep, lp, st);
+    }
     if (d == 64) {
       if (variant == 10) return launch_flat_cls<16, 8, false, 4>(plain, A, X, ldx, dvec, ep, lp, st);
       if (variant == 11) return launch_flat_cls<16, 16, false, 3>(plain, A, X, ldx, dvec, ep, lp, st);
@@ -705,11 +737,15 @@ static int spmm_impl(const gcf_csr_t* A, int32_t d, const float* X, int64_t ldx,
       if (variant == 1) return launch<2, 1, 2, false, 4>(A, X, ldx, dvec, ep, lp, st);      // 2 gathers in flight
       if (variant == 2) return launch<2, 1, 2, false, 2, 8>(A, X, ldx, dvec, ep, lp, st);   // 16
       if (variant == 3) return launch<2, 1, 2, false, 6, 2>(A, X, ldx, dvec, ep, lp, st);   // 4, 48 warps / SM
+      if (variant == 5) return launch<2, 1, 2, false, 4, 4, true>(A, X, ldx, dvec, ep, lp, st);   // 8, gathers bypass the L1
+      if (variant == 6) return launch<2, 1, 2, false, 3, 8, true>(A, X, ldx, dvec, ep, lp, st);   // 16, gathers bypass the L1
       return launch<2, 1, 2, false, 4, 4>(A, X, ldx, dvec, ep, lp, st);                     // 8
     case 16:
       if (variant == 1) return launch<4, 1, 4, false, 4>(A, X, ldx, dvec, ep, lp, st);      // 4 gathers in flight
       if (variant == 2) return launch<4, 1, 4, false, 2, 4>(A, X, ldx, dvec, ep, lp, st);   // 16
       if (variant == 3) return launch<4, 1, 4, false, 6>(A, X, ldx, dvec, ep, lp, st);      // 4, 48 warps / SM
+      if (variant == 5) return launch<4, 1, 4, false, 4, 2, true>(A, X, ldx, dvec, ep, lp, st);   // 8, gathers bypass the L1
+      if (variant == 6) return launch<4, 1, 4, false, 3, 4, true>(A, X, ldx, dvec, ep, lp, st);   // 16, gathers bypass the L1
       return launch<4, 1, 4, false, 4, 2>(A, X, ldx, dvec, ep, lp, st);                     // 8
     case 32:
       if (variant == 1) return launch<8, 1, 8, false, 2, 2>(A, X, ldx, dvec, ep, lp, st);   // 16 gathers in flight

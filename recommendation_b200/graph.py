@@ -72,6 +72,46 @@ def default_tile_nnz(nnz_short: int) -> int:
     return int(min(512, max(64, (t + 15) // 16 * 16)))
 
 
+# hub columns per half of the operator; 0 = off, the default: measured on cfg1-cfg4 (profiles/r02_exp_hub_l1.log) the L1 residency
+# hints are neutral at 4 CTAs/SM and 5-15 % slower at 3 CTAs/SM than the unflagged kernel, for every hub count tried
+DEFAULT_HUBS = int(os.environ.get("GCF_SPMM_HUBS", "0"))
+HUB_MAX_NNZ = int(os.environ.get("GCF_SPMM_HUB_MAX_NNZ", str(64_000_000)))
+HUB_MIN_DEGREE = 128
+
+
+def hub_flagged_columns(row_ptr: torch.Tensor, col_idx: torch.Tensor, n_cols: int, n_hubs: int,
+                        min_degree: int = HUB_MIN_DEGREE) -> Optional[torch.Tensor]:
+    """Copy of col_idx with bit 31 set on the entries that reference a hub column (gcf_csr_t.hub_col_idx).
+
+    The rows are cut into two blocks holding half of the entries each (for the bipartite operators of the reference that
+    is exactly user rows | item rows, whose entries reference item / user columns respectively); inside a block the hubs
+    are its `n_hubs` most-referenced columns, provided they are referenced at least `min_degree` times (a row that each
+    SM gathers less than about once is not worth keeping in its L1).  Build-time index arithmetic on the device (torch
+    ops, once per operator); returns None when no column qualifies."""
+    nnz = int(col_idx.numel())
+    if nnz == 0 or n_hubs <= 0:
+        return None
+    half = int(torch.searchsorted(row_ptr.to(torch.int64), torch.tensor([nnz // 2], device=row_ptr.device), right=False)[0].item())
+    cut = int(row_ptr[min(half, row_ptr.numel() - 1)].item())
+    out = col_idx.clone()
+    any_hub = False
+    for e0, e1 in ((0, cut), (cut, nnz)):
+        if e1 <= e0:
+            continue
+        cols = col_idx[e0:e1].to(torch.int64)
+        deg = torch.bincount(cols, minlength=n_cols)
+        top_deg, top_col = torch.topk(deg, min(n_hubs, n_cols))
+        top_col = top_col[top_deg >= min_degree]
+        if top_col.numel() == 0:
+            continue
+        is_hub = torch.zeros(n_cols, dtype=torch.bool, device=col_idx.device)
+        is_hub[top_col] = True
+        flag = is_hub[cols]
+        out[e0:e1] = torch.where(flag, col_idx[e0:e1] | torch.tensor(-2**31, dtype=torch.int32, device=col_idx.device), col_idx[e0:e1])
+        any_hub = True
+    return out if any_hub else None
+
+
 def plan_tiles(row_ptr: np.ndarray, chunk: int, tile_nnz: int):
     """Flat-stream schedule (pure numpy).  Returns (tiles, nz_rows, nz_row_ptr, empty_rows):
 
@@ -114,7 +154,7 @@ class CSRGraph:
 
     def __init__(self, row_ptr: torch.Tensor, col_idx: torch.Tensor, vals: torch.Tensor, n_rows: int, n_cols: int,
                  *, symmetric: bool = False, chunk: Optional[int] = None, rowsum: Optional[torch.Tensor] = None,
-                 dinv: Optional[torch.Tensor] = None, tile_nnz: Optional[int] = None):
+                 dinv: Optional[torch.Tensor] = None, tile_nnz: Optional[int] = None, hubs: Optional[int] = None):
         for name, t, dt in (("row_ptr", row_ptr, torch.int32), ("col_idx", col_idx, torch.int32), ("vals", vals, torch.float32)):
             _require_cuda(t, name)
             if t.dtype != dt or not t.is_contiguous():
@@ -149,6 +189,9 @@ class CSRGraph:
         self._long_rows = torch.from_numpy(plan.long_rows).to(self.device)
         self._long_chunk_ptr = torch.from_numpy(plan.long_chunk_ptr).to(self.device)
         self._chunk_long = torch.from_numpy(plan.chunk_long).to(self.device)
+        # hub flags for the flat-stream kernel: operators small enough for their working set to live in the L2
+        n_hubs = (DEFAULT_HUBS if self.nnz <= HUB_MAX_NNZ else 0) if hubs is None else int(hubs)
+        self._hub_col_idx = hub_flagged_columns(row_ptr, col_idx, self.n_cols, n_hubs) if (n_hubs > 0 and self.n_tiles) else None
         self._struct = _lib.CsrStruct(
             n_rows=self.n_rows, n_cols=self.n_cols, nnz=self.nnz,
             row_ptr=row_ptr.data_ptr(), col_idx=col_idx.data_ptr() if self.nnz else None,
@@ -159,13 +202,14 @@ class CSRGraph:
             chunk_long=self._chunk_long.data_ptr() if plan.n_long else None,
             tiles=self._tiles.data_ptr() if self.n_tiles else None, n_tiles=self.n_tiles, n_empty=self.n_empty,
             empty_rows=_lib.ptr(self._empty_rows), nz_row_ptr=_lib.ptr(self._nz_row_ptr), nz_rows=_lib.ptr(self._nz_rows),
+            hub_col_idx=_lib.ptr(self._hub_col_idx),
         )
 
     # ---- construction ---------------------------------------------------------------------
     @classmethod
     def from_coo(cls, rows: torch.Tensor, cols: torch.Tensor, vals: Optional[torch.Tensor], n_rows: int, n_cols: int,
                  *, norm: str = "none", symmetric: bool = False, chunk: Optional[int] = None,
-                 tile_nnz: Optional[int] = None) -> "CSRGraph":
+                 tile_nnz: Optional[int] = None, hubs: Optional[int] = None) -> "CSRGraph":
         """COO (int64 indices, duplicates allowed) -> canonical CSR, then value normalisation."""
         if norm not in _NORM_CODES:
             raise ValueError(f"norm must be one of {sorted(_NORM_CODES)}")
@@ -209,11 +253,12 @@ class CSRGraph:
                                            n_rows, n_cols, _lib.ptr(normed), _lib.ptr(rowsum), _lib.ptr(dinv), stream),
                        "gcf_norm_values")
         return cls(row_ptr, col_idx, normed, n_rows, n_cols, symmetric=symmetric, chunk=chunk, rowsum=rowsum, dinv=dinv,
-                   tile_nnz=tile_nnz)
+                   tile_nnz=tile_nnz, hubs=hubs)
 
     @classmethod
     def from_edge_index(cls, edge_index: torch.Tensor, num_nodes: int, *, norm: str = "sym",
-                        symmetric: bool = True, chunk: Optional[int] = None, tile_nnz: Optional[int] = None) -> "CSRGraph":
+                        symmetric: bool = True, chunk: Optional[int] = None, tile_nnz: Optional[int] = None,
+                        hubs: Optional[int] = None) -> "CSRGraph":
         """edge_index [2, E'] (PyG convention: message flows row -> col, out[col] += w * x[row]).
 
         The operator applied to X is therefore M with M[col, row] = w, i.e. CSR rows = edge_index[1].
@@ -222,11 +267,11 @@ class CSRGraph:
         if edge_index.dim() != 2 or edge_index.shape[0] != 2:
             raise ValueError("edge_index must have shape [2, E]")
         return cls.from_coo(edge_index[1], edge_index[0], None, num_nodes, num_nodes, norm=norm,
-                            symmetric=symmetric, chunk=chunk, tile_nnz=tile_nnz)
+                            symmetric=symmetric, chunk=chunk, tile_nnz=tile_nnz, hubs=hubs)
 
     @classmethod
     def from_pairs(cls, users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int, *, norm: str = "sym",
-                   chunk: Optional[int] = None, tile_nnz: Optional[int] = None) -> "CSRGraph":
+                   chunk: Optional[int] = None, tile_nnz: Optional[int] = None, hubs: Optional[int] = None) -> "CSRGraph":
         """Bipartite user-item pairs -> symmetric (U+I)x(U+I) adjacency [[0,R],[R^T,0]]."""
         lib = _lib.load()
         _require_cuda(users, "users")
@@ -238,11 +283,12 @@ class CSRGraph:
         _lib.check(lib.gcf_bipartite_edge_index(_lib.ptr(users), _lib.ptr(items), e, n_users, _lib.ptr(rows), _lib.ptr(cols),
                                                 _lib.current_stream()), "gcf_bipartite_edge_index")
         n = n_users + n_items
-        return cls.from_coo(rows, cols, None, n, n, norm=norm, symmetric=True, chunk=chunk, tile_nnz=tile_nnz)
+        return cls.from_coo(rows, cols, None, n, n, norm=norm, symmetric=True, chunk=chunk, tile_nnz=tile_nnz, hubs=hubs)
 
     @classmethod
     def from_scipy(cls, mat, *, norm: str = "none", device: Optional[torch.device] = None,
-                   symmetric: Optional[bool] = None, chunk: Optional[int] = None, tile_nnz: Optional[int] = None) -> "CSRGraph":
+                   symmetric: Optional[bool] = None, chunk: Optional[int] = None, tile_nnz: Optional[int] = None,
+                   hubs: Optional[int] = None) -> "CSRGraph":
         """Any scipy.sparse matrix (the reference's `data.norm_adj`); COO triplets are uploaded as they are
         (duplicates kept, like convert_sparse_mat_to_tensor) and canonicalised on the GPU."""
         coo = mat.tocoo()
@@ -256,7 +302,8 @@ class CSRGraph:
             if n_rows == n_cols:
                 diff = (mat - mat.T)
                 symmetric = diff.nnz == 0 or float(abs(diff).max()) == 0.0
-        return cls.from_coo(rows, cols, vals, n_rows, n_cols, norm=norm, symmetric=symmetric, chunk=chunk, tile_nnz=tile_nnz)
+        return cls.from_coo(rows, cols, vals, n_rows, n_cols, norm=norm, symmetric=symmetric, chunk=chunk, tile_nnz=tile_nnz,
+                            hubs=hubs)
 
     # ---- derived operators ----------------------------------------------------------------
     def transpose(self) -> "CSRGraph":

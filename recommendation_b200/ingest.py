@@ -12,7 +12,8 @@
         .interaction_mat, .sampler(), .user_ids() / .item_ids() (the id strings, decoded on demand)
 
 Everything between the file bytes and the CSR operator runs in libgcf kernels (tokenising, key packing, radix sort + run
-heads, binary-search lookup, the COO -> CSR build); ids longer than 8 bytes are rejected with an error (no silent fallback).
+heads, binary-search lookup, the COO -> CSR build).  Ids of up to 8 bytes travel as one 64-bit key; longer ones (up to
+MAX_ID_BYTES) as tuples of 64-bit words, sorted word by word (stable LSD radix passes) -- ncl.py:60-61 sorts arbitrary strings.
 """
 from __future__ import annotations
 
@@ -23,6 +24,9 @@ import torch
 
 from . import _lib
 from .graph import CSRGraph
+
+
+MAX_ID_BYTES = 256      # 32 key words; the reference's datasets use ids of a few bytes
 
 
 def _device(device=None) -> torch.device:
@@ -40,7 +44,8 @@ def read_text(path: str, device=None) -> torch.Tensor:
 
 def parse_pairs(text: torch.Tensor, *, numeric: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """(first, second): int64 tensors holding the uint64 keys of the first two tokens of every record (see gcf.h);
-    numeric=True parses decimal integers instead of packing the id bytes."""
+    numeric=True parses decimal integers instead of packing the id bytes.  String ids longer than 8 bytes come back as
+    [n_words, n_records] tensors (word-major key tuples, gcf_text_parse_pairs_words); otherwise the tensors are 1-D."""
     if not text.is_cuda or text.dtype != torch.uint8:
         raise RuntimeError("parse_pairs needs a uint8 CUDA tensor: recommendation_b200 has no CPU path")
     lib, st, dev = _lib.load(), _lib.current_stream(), text.device
@@ -54,17 +59,68 @@ def parse_pairs(text: torch.Tensor, *, numeric: bool = False) -> Tuple[torch.Ten
     r = int(n_rec.item())
     first = torch.empty(max(r, 1), dtype=torch.int64, device=dev)[:r]
     second = torch.empty(max(r, 1), dtype=torch.int64, device=dev)[:r]
-    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    if numeric:
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        if r:
+            _lib.check(lib.gcf_text_parse_pairs(_lib.ptr(text), n, 1, _lib.ptr(first), _lib.ptr(second), _lib.ptr(status),
+                                                _lib.ptr(ws), ws_bytes, st), "gcf_text_parse_pairs")
+        flags = int(status.item())
+        if flags & 1:
+            raise ValueError("parse_pairs: a line has fewer than two fields")
+        if flags & 2:
+            raise ValueError("parse_pairs: an id is not a decimal integer")
+        return first, second
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
     if r:
-        _lib.check(lib.gcf_text_parse_pairs(_lib.ptr(text), n, 1 if numeric else 0, _lib.ptr(first), _lib.ptr(second),
-                                            _lib.ptr(status), _lib.ptr(ws), ws_bytes, st), "gcf_text_parse_pairs")
-    flags = int(status.item())
+        _lib.check(lib.gcf_text_parse_pairs_words(_lib.ptr(text), n, 1, r, _lib.ptr(first), _lib.ptr(second), _lib.ptr(status),
+                                                  _lib.ptr(ws), ws_bytes, st), "gcf_text_parse_pairs_words")
+    flags, longest = (int(v) for v in status.tolist())
     if flags & 1:
         raise ValueError("parse_pairs: a line has fewer than two fields")
-    if flags & 2:
-        raise ValueError("parse_pairs: an id is not a decimal integer" if numeric else
-                         "parse_pairs: an id is longer than 8 bytes (the packed-key format of the GPU ingest path)")
+    if flags & 2:                                        # an id longer than 8 bytes: parse again into key tuples
+        if longest > MAX_ID_BYTES:
+            raise ValueError(f"parse_pairs: an id of {longest} bytes exceeds MAX_ID_BYTES = {MAX_ID_BYTES}")
+        w = -(-longest // 8)
+        first = torch.empty(w, r, dtype=torch.int64, device=dev)
+        second = torch.empty(w, r, dtype=torch.int64, device=dev)
+        _lib.check(lib.gcf_text_parse_pairs_words(_lib.ptr(text), n, w, r, _lib.ptr(first), _lib.ptr(second), _lib.ptr(status),
+                                                  _lib.ptr(ws), ws_bytes, st), "gcf_text_parse_pairs_words")
     return first, second
+
+
+def _as_words(keys: torch.Tensor, n_words: int) -> torch.Tensor:
+    """[n] or [w, n] keys -> [n_words, n] (zero words appended: shorter ids are zero padded anyway)."""
+    k = keys.unsqueeze(0) if keys.dim() == 1 else keys
+    if k.shape[0] < n_words:
+        k = torch.cat([k, torch.zeros(n_words - k.shape[0], k.shape[1], dtype=k.dtype, device=k.device)], 0)
+    return k.contiguous()
+
+
+def sort_unique_words(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Key tuples [W, n] -> (distinct tuples ascending [W, m], first occurrence of each [m], dense index of every input [n])."""
+    lib, st, dev = _lib.load(), _lib.current_stream(), keys.device
+    w, n = keys.shape
+    uniq = torch.empty(w, max(n, 1), dtype=torch.int64, device=dev)
+    first = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    rank = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    n_uniq = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws_bytes = lib.gcf_sort_unique_words_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.gcf_sort_unique_words(_lib.ptr(keys.contiguous()) if n else None, w, n, _lib.ptr(uniq), _lib.ptr(first),
+                                         _lib.ptr(n_uniq), _lib.ptr(rank), _lib.ptr(ws), ws_bytes, st), "gcf_sort_unique_words")
+    m = int(n_uniq.item())
+    return uniq[:, :m].contiguous(), first[:m].clone(), rank[:n].clone()
+
+
+def lookup_words(table: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
+    """Position of every key tuple ([W, n]) in the ascending `table` ([W, m]), -1 when absent."""
+    lib = _lib.load()
+    w, n = keys.shape
+    m = int(table.shape[1])
+    out = torch.empty(max(n, 1), dtype=torch.int64, device=keys.device)[:n]
+    _lib.check(lib.gcf_lookup_sorted_words(_lib.ptr(table.contiguous()) if m else None, w, m, m, _lib.ptr(keys.contiguous()) if n else None,
+                                           n, _lib.ptr(out) if n else None, _lib.current_stream()), "gcf_lookup_sorted_words")
+    return out
 
 
 def sort_unique(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -93,17 +149,25 @@ def lookup(table: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
 
 
 def decode_keys(keys: torch.Tensor) -> List[str]:
-    """The id strings of packed string keys (host side, for reports and `data.user`-style dictionaries)."""
-    raw = keys.cpu().numpy().astype(">u8").tobytes()
-    return [raw[8 * k: 8 * k + 8].rstrip(b"\0").decode("ascii") for k in range(keys.numel())]
+    """The id strings of packed string keys, [n] or [W, n] (host side, for reports and `data.user`-style dictionaries)."""
+    k = keys.unsqueeze(0) if keys.dim() == 1 else keys
+    w, n = k.shape
+    raw = np.ascontiguousarray(k.t().cpu().numpy().astype(">u8")).tobytes()       # record-major: 8 * w bytes per id
+    return [raw[8 * w * j: 8 * w * (j + 1)].rstrip(b"\0").decode("ascii") for j in range(n)]
 
 
 class _IdMap:
-    """Dense numbering of one id column: `table` = distinct keys ascending, `rank[j]` = dense index of table[j]."""
+    """Dense numbering of one id column: `table` = distinct keys ascending, `rank[j]` = dense index of table[j].
+    Keys are [n] (ids of up to 8 bytes) or [W, n] word tuples (longer ids)."""
 
     def __init__(self, keys: torch.Tensor, order: str):
-        self.table, first = sort_unique(keys)
-        n = int(self.table.numel())
+        self.n_words = 1 if keys.dim() == 1 else int(keys.shape[0])
+        if self.n_words == 1:
+            self.table, first = sort_unique(keys.reshape(-1))
+            n = int(self.table.numel())
+        else:
+            self.table, first, _ = sort_unique_words(keys)
+            n = int(self.table.shape[1])
         if order == "appearance":                       # number the distinct ids by the position of their first occurrence
             by_first = torch.argsort(first)
             self.rank = torch.empty(n, dtype=torch.int64, device=keys.device)
@@ -113,7 +177,12 @@ class _IdMap:
         self.count = n
 
     def index(self, keys: torch.Tensor) -> torch.Tensor:
-        pos = lookup(self.table, keys)
+        kw = 1 if keys.dim() == 1 else int(keys.shape[0])
+        if self.n_words == 1 and kw == 1:
+            pos = lookup(self.table, keys.reshape(-1))
+        else:
+            w = max(self.n_words, kw)                   # e.g. a test file with longer ids than the training file
+            pos = lookup_words(_as_words(self.table, w), _as_words(keys, w))
         if self.rank is None:
             return pos
         return torch.where(pos >= 0, self.rank[pos.clamp_min(0)], pos)

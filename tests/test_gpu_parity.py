@@ -769,8 +769,10 @@ def test_ingest_numeric_ids_and_errors(cuda, golden, tmp_path):
     assert (d.user_num, d.item_num) == (int(z["num_user_count"]), int(z["num_item_count"]))
     assert d.edge_index().shape == (2, 2 * d.users.numel())
     t = lambda s: torch.frombuffer(bytearray(s.encode()), dtype=torch.uint8).to(cuda)
-    with pytest.raises(ValueError, match="8 bytes"):
-        ingest.parse_pairs(t("user_123456 7 1\n"))
+    a, b = ingest.parse_pairs(t("user_123456 7 1\n"))          # an 11-byte id: two key words
+    assert a.shape == (2, 1) and b.shape == (2, 1) and ingest.decode_keys(a) == ["user_123456"] and ingest.decode_keys(b) == ["7"]
+    with pytest.raises(ValueError, match="MAX_ID_BYTES"):
+        ingest.parse_pairs(t("x" * 300 + " 7 1\n"))
     with pytest.raises(ValueError, match="fewer than two"):
         ingest.parse_pairs(t("a b 1\nlonely\n"))
     with pytest.raises(ValueError, match="decimal"):
@@ -787,3 +789,30 @@ def test_ingest_numeric_ids_and_errors(cuda, golden, tmp_path):
     um, im = ingest_ref.number_ids([p[0] for p in pairs], "sorted"), ingest_ref.number_ids([p[1] for p in pairs], "sorted")
     assert di.users.numel() == len(pairs) and di.user_num == len(um) and di.item_num == len(im)
     assert np.array_equal(di.users.cpu().numpy(), [um[p[0]] for p in pairs]) and np.array_equal(di.items.cpu().numpy(), [im[p[1]] for p in pairs])
+
+
+@pytest.mark.parametrize("order", ["sorted", "appearance"])
+def test_ingest_ids_longer_than_eight_bytes(cuda, order):
+    """ncl.py:55-62 numbers arbitrary id STRINGS (sorted(set(ids))); selfcf.py:281-288 by first appearance.  Ids of 1..40
+    bytes, shared prefixes, a test file with ids the training file does not hold (and longer ones) -- against the oracle."""
+    from oracle import ingest_ref
+    from recommendation_b200 import ingest
+
+    rng = np.random.default_rng(21)
+    stems = ["u", "user_", "customer-id:", "A" * 17, "A" * 17 + "B", "x" * 33 + "_"]
+    users = [stems[rng.integers(0, len(stems))] + str(rng.integers(0, 3000)) for _ in range(40000)]
+    items = ["item" + str(rng.integers(0, 800)).zfill(int(rng.integers(1, 12))) for _ in range(40000)]
+    blob = "".join(f"{u} {i} 1\n" for u, i in zip(users, items)).encode()
+    test_blob = (f"{users[5]} {items[7]} 1\nnever_seen_user_with_a_long_name {items[0]} 1\n{users[9]} {'z' * 50} 1\n").encode()
+    t = lambda b: torch.frombuffer(bytearray(b), dtype=torch.uint8).to(cuda)
+    di = ingest.DeviceInteraction(t(blob), t(test_blob), id_order=order)
+    pairs = ingest_ref.load_pairs(blob)
+    um, im = ingest_ref.number_ids([p[0] for p in pairs], order), ingest_ref.number_ids([p[1] for p in pairs], order)
+    assert (di.user_num, di.item_num) == (len(um), len(im))
+    assert np.array_equal(di.users.cpu().numpy(), [um[p[0]] for p in pairs])
+    assert np.array_equal(di.items.cpu().numpy(), [im[p[1]] for p in pairs])
+    assert di.test_users.cpu().tolist() == [um[users[5]], -1, um[users[9]]]
+    assert di.test_items.cpu().tolist() == [im[items[7]], im[items[0]], -1]
+    inv_u = {v: k for k, v in um.items()}
+    assert di.user_ids() == [inv_u[k] for k in range(len(um))]                            # id2user, strings decoded from the key tuples
+    assert di.norm_adj.nnz > 0

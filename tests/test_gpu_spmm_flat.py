@@ -102,3 +102,40 @@ def test_flat_kernel_duplicate_entries_and_row_strides(cuda):
     want = torch.from_numpy(mat.toarray().astype(np.float64)).to(cuda) @ xbuf[:, :d].double()
     assert float((ybuf[:, :d].double() - want).abs().max()) <= 1e-5 * (float(want.abs().max()) + 1)
     assert float(ybuf[:, d:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_hub_flagged_gathers_are_bit_identical(cuda, d):
+    """Hub flags only change the cache policy of the gathers (L1::evict_last for hub columns, L1::no_allocate for the rest):
+    same columns, same order, same bits as the unflagged kernel (variant 15) and as the row kernel (variant 4)."""
+    from recommendation_b200 import _lib, functional as F_
+    from recommendation_b200.graph import CSRGraph, hub_flagged_columns
+
+    rng = np.random.default_rng(7 + d)
+    deg = rng.poisson(12.0, 3000); deg[rng.choice(3000, 6, replace=False)] = 900      # a few hub ROWS (chunked path) as well
+    rows = np.repeat(np.arange(3000), deg)
+    cols = (rng.zipf(1.3, rows.size) - 1) % 3000                                         # skewed column popularity
+    mat = sp.coo_matrix((rng.standard_normal(rows.size).astype(np.float32), (rows, cols)), shape=(3000, 3000)).tocsr()
+    mat.sum_duplicates()
+    g = CSRGraph.from_scipy(mat, device=cuda, chunk=256, tile_nnz=96, hubs=64)
+    assert g._hub_col_idx is not None
+    flagged = g._hub_col_idx
+    assert torch.equal(flagged & 0x7FFFFFFF, g.col_idx)                       # bit 31 is the only difference
+    n_flag = int((flagged < 0).sum())
+    assert 0 < n_flag < g.nnz
+    # every flagged entry references one of the 64 most-referenced columns of its half
+    deg = torch.bincount(g.col_idx.long(), minlength=3000)
+    assert int(deg[g.col_idx[flagged < 0].long()].min()) >= 128
+    plain = CSRGraph.from_scipy(mat, device=cuda, chunk=256, tile_nnz=96, hubs=0)
+    assert plain._hub_col_idx is None
+    x = torch.from_numpy(rng.standard_normal((3000, d)).astype(np.float32)).to(cuda)
+    add = torch.from_numpy(rng.standard_normal((3000, d)).astype(np.float32)).to(cuda)
+    outs = []
+    for graph, variant in ((g, 0), (g, 16), (g, 15), (plain, 0), (g, 4)):
+        y = torch.empty(3000, d, device=cuda); o = torch.empty(3000, d, device=cuda)
+        F_.spmm_raw(graph, x, y=y, variant=variant)
+        F_.spmm_raw(graph, x, out=o, alpha=0.5, addends=[add], betas=[2.0], variant=variant)
+        outs.append((y, o))
+    for y, o in outs[1:]:
+        assert torch.equal(y, outs[0][0]) and torch.equal(o, outs[0][1])
+    assert hub_flagged_columns(g.row_ptr, g.col_idx, 3000, 64, min_degree=10**9) is None

@@ -451,3 +451,19 @@ def test_packed_key_round_trip_on_the_host():
     assert ingest.decode_keys(t) == ids
     order = np.argsort(keys, kind="stable")
     assert [ids[k] for k in order] == sorted(ids)               # unsigned key order == Python's string order
+
+
+def test_key_tuples_of_long_ids_round_trip_and_order_on_the_host():
+    """Ids longer than 8 bytes travel as tuples of 64-bit words (gcf_text_parse_pairs_words): tuple order == string order,
+    and ingest.decode_keys inverts the packing for word-major [W, n] tensors."""
+    from oracle import ingest_ref
+    from recommendation_b200 import ingest
+
+    ids = ["user_1", "user_10", "user_2", "customer-id:000123", "customer-id:00012", "A" * 17, "A" * 17 + "B", "b", "~" * 24]
+    w = 3
+    tuples = [ingest_ref.pack_words(s, w) for s in ids]
+    assert [s for _, s in sorted(zip(tuples, ids))] == sorted(ids)
+    arr = np.array(tuples, dtype=np.uint64).T.copy()              # [W, n] word-major
+    assert ingest.decode_keys(torch.from_numpy(arr.view(np.int64))) == ids
+    with pytest.raises(ValueError):
+        ingest_ref.pack_words("x" * 25, 3)
