@@ -313,12 +313,20 @@ def run_ours(args):
             args.loss_layout = "scores" if world <= 2 else "rows"
         if F == world:
             trainer = FeatureShardedLightGCNTrainer(users, items, U, I, d=d, n_layers=K, lr=0.01, reg_weight=1e-4, seed=1234,
-                                                    loss_layout=args.loss_layout, overlap=args.overlap_exchange)
+                                                    loss_layout=args.loss_layout, overlap=args.overlap_exchange,
+                                                    exchange=args.exchange)
             nnz, spmm_rows, spmm_d = trainer.local_nnz, n, trainer.dg
             parallelism = (f"feature-sharded over {world} GPUs: every rank owns d/G = {trainer.dg} columns of all [N, d] tables, "
                            f"propagation / Adam without any collective; ")
             if args.loss_layout == "rows":
-                parallelism += ("loss on full-width rows of one user block per rank: item slices all-gathered, user slices "
+                if trainer.exchange == "peer":
+                    parallelism += ("loss on full-width rows of one user block per rank: every rank pulls the column slices it needs "
+                                    "straight out of the peers' memory over NVLink (one gather kernel per table that also lays the "
+                                    "rows out), fused BPR on E/G triples, gradients pulled back the same way (one summing kernel for "
+                                    "the items, one copy kernel for the users); two stream-ordered barriers per step, no NCCL "
+                                    "collective on the data path")
+                else:
+                    parallelism += ("loss on full-width rows of one user block per rank: item slices all-gathered, user slices "
                                 "all-to-all'ed, fused BPR on E/G triples, gradients returned by one reduce-scatter + one all-to-all"
                                 + ("; exchanges overlapped with item-row / user-row blocks of the adjacent propagation layers"
                                    if trainer.overlap else ""))
@@ -558,6 +566,9 @@ def main():
     ap.add_argument("--loss-layout", choices=("auto", "rows", "scores"), default=os.environ.get("GCF_BENCH_LOSS_LAYOUT", "auto"),
                     help="feature-sharded layout only: where the BPR loss is evaluated (see dist.FeatureShardedLightGCNTrainer); "
                          "auto = measured default: all-reduced scores on 2 GPUs (60.5 vs 61.6 ms), full-width rows from 4 GPUs on")
+    ap.add_argument("--exchange", choices=("peer", "nccl"), default=os.environ.get("GCF_BENCH_EXCHANGE", "peer"),
+                    help="feature-sharded layout, loss on rows: 'peer' = slices pulled out of the peers' memory over NVLink by "
+                         "csrc/peer.cu (default), 'nccl' = all-gather / all-to-all / reduce-scatter + layout passes (r01/r02)")
     ap.add_argument("--overlap-exchange", action="store_true",
                     help="feature-sharded layout, loss on rows: overlap the exchanges with row blocks of the adjacent propagation "
                          "layers (measured neutral on cfg5 at 2 and 4 GPUs)")

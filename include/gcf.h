@@ -209,6 +209,36 @@ int gcf_slices_to_rows(const float* blocked, float* rows, int64_t ld_rows, int64
 int gcf_rows_to_slices(const float* rows, int64_t ld_rows, float* blocked, int64_t n_rows, int32_t n_slices, int32_t w,
                        gcf_stream_t stream);
 
+/* Peer-memory exchange of the feature-sharded multi-GPU step over NVLink / NVSwitch (the reference has no
+ * distributed code -- these replace the NCCL all-gather / all-to-all / reduce-scatter + layout-pass pairs around the loss).
+ * Buffers that peers read are cudaMalloc blocks of their own (gcf_peer_alloc: zero-filled, exportable at offset 0);
+ * gcf_peer_export writes the 64-byte CUDA IPC handle that another PROCESS on the same box turns into a device pointer with
+ * gcf_peer_open (peer access enabled lazily).  The three movers take an array of n_src (<= 16) source pointers, local or
+ * peer mappings, all with leading dimension ld_src; w % 4 == 0, 16-byte aligned pointers:
+ *   gather_cols: dst[r, g*w : (g+1)*w] = src[g][r, 0:w]             r < n_rows   (column slices -> full-width rows)
+ *   sum_cols   : dst[r, 0:w] = src[0][r, 0:w] + ... + src[n_src-1][r, 0:w]       (fixed order: deterministic)
+ *   copy_blocks: dst[off_g + r * ld_dst + 0:w] = src[g][r, 0:w], r < rows_per_src[g]; off_g = dst_offsets[g] floats, or, with
+ *                dst_offsets == NULL, the blocks stacked: off_g = (rows_per_src[0] + ... + rows_per_src[g-1]) * ld_dst
+ * The caller orders the ranks (data ready before the call, buffers not rewritten while peers read): the kernels themselves
+ * do not synchronise across devices. */
+#define GCF_PEER_HANDLE_BYTES 64
+int gcf_peer_alloc(size_t bytes, void** dev_ptr);
+int gcf_peer_free(void* dev_ptr);
+int gcf_peer_export(const void* dev_ptr, void* handle64);
+int gcf_peer_open(const void* handle64, void** peer_ptr);
+int gcf_peer_close(void* peer_ptr);
+int gcf_peer_gather_cols(const float* const* src, int32_t n_src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t n_rows,
+                         int32_t w, gcf_stream_t stream);
+int gcf_peer_sum_cols(const float* const* src, int32_t n_src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t n_rows,
+                      int32_t w, gcf_stream_t stream);
+/* the general mover: n_blocks (<= 16) independent 2-D blocks, dst[g][r * ld_dst + 0:w] = src[g][r * ld_src + 0:w], r < rows[g];
+ * either side of a block may be peer memory (pull = remote loads, push = remote stores).  ctas_per_block = 0: the library's default
+ * (a small fixed budget shared by the blocks: NVLink throughput DROPS when too many requests are outstanding). */
+int gcf_peer_copy2d(const float* const* src, float* const* dst, const int64_t* rows, int32_t n_blocks, int64_t ld_src,
+                    int64_t ld_dst, int32_t w, int32_t ctas_per_block, gcf_stream_t stream);
+int gcf_peer_copy_blocks(const float* const* src, const int64_t* rows_per_src, const int64_t* dst_offsets, int32_t n_src,
+                         int64_t ld_src, float* dst, int64_t ld_dst, int32_t w, gcf_stream_t stream);
+
 /* Philox4x32-10 counter-based negative sampler.  For triple t and negative slot j the
  * candidate stream is Philox(key=seed, counter=(t*n_negs+j, trial/4, offset_lo, offset_hi)),
  * candidate = mulhi32(word, n_items).  Without a positives CSR (pos_row_ptr == NULL) the
@@ -226,6 +256,11 @@ int gcf_sample_negatives(uint64_t seed, uint64_t offset, const int64_t* users, i
 int gcf_sample_negatives_at(uint64_t seed, uint64_t offset, int64_t slot_base, const int64_t* users, int64_t n,
                             int32_t n_negs, int64_t n_items, const int32_t* pos_row_ptr, const int32_t* pos_col_idx,
                             int32_t max_trials, int64_t* out, gcf_stream_t stream);
+
+/* The same stream for an ARBITRARY subset of the triples: slot_pos[t] = position of local triple t in the global list, so
+ * ranks that own interleaved subsets (users dealt out cyclically) draw what the single-GPU run draws.  No rejection. */
+int gcf_sample_negatives_pos(uint64_t seed, uint64_t offset, const int64_t* slot_pos, int64_t n, int32_t n_negs,
+                             int64_t n_items, int64_t* out, gcf_stream_t stream);
 
 /* Stochastic edge dropout of a sparse operator's values (buir.py:300-309 sparse_dropout):
  *   out[j] = keep(e) ? vals[e] / (1 - rate) : 0,   e = index ? index[j] : j,

@@ -70,10 +70,22 @@ _SIGNATURES = {
                                        c_void_p, c_size_t, c_void_p]),
     "gcf_slices_to_rows": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p]),
     "gcf_rows_to_slices": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
+    "gcf_peer_alloc": (c_int32, [c_size_t, POINTER(c_void_p)]),
+    "gcf_peer_free": (c_int32, [c_void_p]),
+    "gcf_peer_export": (c_int32, [c_void_p, c_void_p]),
+    "gcf_peer_open": (c_int32, [c_void_p, POINTER(c_void_p)]),
+    "gcf_peer_close": (c_int32, [c_void_p]),
+    "gcf_peer_gather_cols": (c_int32, [POINTER(c_void_p), c_int32, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p]),
+    "gcf_peer_sum_cols": (c_int32, [POINTER(c_void_p), c_int32, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p]),
+    "gcf_peer_copy2d": (c_int32, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int32, c_int64, c_int64, c_int32, c_int32,
+                                  c_void_p]),
+    "gcf_peer_copy_blocks": (c_int32, [POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64), c_int32, c_int64, c_void_p, c_int64,
+                                       c_int32, c_void_p]),
     "gcf_sample_negatives": (c_int32, [c_uint64, c_uint64, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p,
                                        c_int32, c_void_p, c_void_p]),
     "gcf_sample_negatives_at": (c_int32, [c_uint64, c_uint64, c_int64, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p,
                                           c_int32, c_void_p, c_void_p]),
+    "gcf_sample_negatives_pos": (c_int32, [c_uint64, c_uint64, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p]),
     "gcf_philox_keys": (c_int32, [c_int64, c_uint64, c_uint64, c_void_p, c_void_p]),
     "gcf_csr_dropout_values": (c_int32, [c_void_p, c_int64, c_void_p, c_float, c_uint64, c_uint64, c_void_p, c_void_p]),
     "gcf_bpr_workspace_bytes": (c_size_t, [c_int64]),
@@ -196,6 +208,14 @@ def ptr_array(tensors):
     arr = (c_void_p * max(len(tensors), 1))()
     for i, t in enumerate(tensors):
         arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def ptr_values(addresses):
+    """Host array of raw device addresses (ints)."""
+    arr = (c_void_p * max(len(addresses), 1))()
+    for i, a in enumerate(addresses):
+        arr[i] = int(a)
     return arr
 
 

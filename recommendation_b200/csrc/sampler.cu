@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256)
 sample_negatives_kernel(uint32_t seed_lo, uint32_t key_hi, uint32_t offset_lo, const int64_t* __restrict__ users,
                         long long n_slots, int n_negs, uint32_t n_items, const int* __restrict__ pos_row_ptr,
                         const int* __restrict__ pos_col_idx, int max_trials, unsigned long long slot_base,
-                        int64_t* __restrict__ out) {
+                        const int64_t* __restrict__ slot_pos, int64_t* __restrict__ out) {
   for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots;
        slot += (long long)gridDim.x * blockDim.x) {
     int ps = 0, pe = 0;
@@ -47,7 +47,9 @@ sample_negatives_kernel(uint32_t seed_lo, uint32_t key_hi, uint32_t offset_lo, c
     uint32_t w[4];
     for (int trial = 0; trial < max_trials; ++trial) {
       if ((trial & 3) == 0) {
-        const unsigned long long gslot = slot_base + (unsigned long long)slot;   // position in the GLOBAL slot numbering
+        // position in the GLOBAL slot numbering: a window of it (slot_base) or an explicit list of triple positions
+        const unsigned long long gslot = slot_pos == nullptr ? slot_base + (unsigned long long)slot
+            : (unsigned long long)slot_pos[slot / n_negs] * (unsigned long long)n_negs + (unsigned long long)(slot % n_negs);
         philox4x32_10((uint32_t)gslot, (uint32_t)(gslot >> 32), offset_lo, (uint32_t)(trial >> 2), seed_lo, key_hi, w);
       }
       cand = __umulhi(w[trial & 3], n_items);
@@ -131,7 +133,22 @@ extern "C" int gcf_sample_negatives_at(uint64_t seed, uint64_t offset, int64_t s
   const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(slots, 256), (long long)sm_count() * 16));
   sample_negatives_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32), (uint32_t)offset, users, slots, n_negs,
-      (uint32_t)n_items, pos_row_ptr, pos_col_idx, max_trials, (unsigned long long)slot_base, out);
+      (uint32_t)n_items, pos_row_ptr, pos_col_idx, max_trials, (unsigned long long)slot_base, nullptr, out);
+  GCF_LAUNCH_CHECK("sample_negatives_kernel");
+  return GCF_OK;
+}
+
+extern "C" int gcf_sample_negatives_pos(uint64_t seed, uint64_t offset, const int64_t* slot_pos, int64_t n, int32_t n_negs,
+                                        int64_t n_items, int64_t* out, gcf_stream_t stream) {
+  GCF_REQUIRE(n >= 0 && n_negs >= 1, "gcf_sample_negatives_pos: bad n / n_negs");
+  GCF_REQUIRE(n_items >= 1 && n_items < 4294967296LL, "gcf_sample_negatives_pos: n_items must be in [1, 2^32)");
+  if (n == 0) return GCF_OK;
+  GCF_REQUIRE(out != nullptr && slot_pos != nullptr, "gcf_sample_negatives_pos: null positions or output");
+  const long long slots = (long long)n * n_negs;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(cdiv(slots, 256), (long long)sm_count() * 16));
+  sample_negatives_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32), (uint32_t)offset, nullptr, slots, n_negs,
+      (uint32_t)n_items, nullptr, nullptr, 1, 0ULL, slot_pos, out);
   GCF_LAUNCH_CHECK("sample_negatives_kernel");
   return GCF_OK;
 }

@@ -29,7 +29,7 @@ from typing import List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, peer
 from .graph import CSRGraph
 from .tables import xavier_uniform_table
 
@@ -435,8 +435,13 @@ class FeatureShardedLightGCNTrainer:
 
     def __init__(self, users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int, *, d: int = 64,
                  n_layers: int = 3, lr: float = 0.01, reg_weight: float = 1e-4, seed: int = 0,
-                 init_table: Optional[torch.Tensor] = None, loss_layout: str = "rows", overlap: bool = False):
-        """overlap (loss_layout="rows", n_layers >= 2): the last forward layer and the first backward layer are launched as
+                 init_table: Optional[torch.Tensor] = None, loss_layout: str = "rows", overlap: bool = False,
+                 exchange: str = "peer"):
+        """exchange (loss_layout="rows"): "peer" (default) -- the column slices are read straight out of the peers' memory
+        over NVLink by one kernel per direction that also converts the layout (csrc/peer.cu; two stream-ordered barriers per
+        step are the only collectives of the loss); "nccl" -- the r01 path: all-gather / all-to-all / reduce-scatter with a
+        layout pass on either side.
+        overlap (loss_layout="rows", exchange="nccl", n_layers >= 2): the last forward layer and the first backward layer are launched as
         an item-row block and a user-row block of the (bipartite) operator, so that the item all-gather runs while the user
         rows are still being computed and the item reduce-scatter while the item rows of the first backward product are.
         Measured neutral on cfg5 (2 GPUs 61.7 vs 61.4 ms, 4 GPUs 40.1 vs 40.2 ms: the collectives compete with the SpMM for
@@ -445,8 +450,11 @@ class FeatureShardedLightGCNTrainer:
             raise RuntimeError("FeatureShardedLightGCNTrainer needs an initialised torch.distributed process group")
         if loss_layout not in ("rows", "scores"):
             raise ValueError("loss_layout must be 'rows' or 'scores'")
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
         self.loss_layout = loss_layout
-        self.overlap = bool(overlap) and loss_layout == "rows" and n_layers >= 2
+        self.exchange = exchange if loss_layout == "rows" else "nccl"
+        self.overlap = bool(overlap) and loss_layout == "rows" and n_layers >= 2 and self.exchange == "nccl"
         if not users.is_cuda:
             raise RuntimeError("FeatureShardedLightGCNTrainer: tensors must be on the rank's CUDA device")
         self.lib = _lib.load()
@@ -494,28 +502,59 @@ class FeatureShardedLightGCNTrainer:
             self.collectives_per_step = 2  # E-float score all-reduce + scalar loss all-reduce
         else:
             G = self.world
-            self.blocks = UserBlockPlan.build(pos_u, n_users, G)
-            self.block_rows = self.blocks.block_sizes()
-            u_lo, u_hi = self.blocks.block(self.rank)
-            t_lo, t_hi = self.blocks.triple_range(self.rank)
-            self.t_lo, self.t_hi, self.ub = t_lo, t_hi, u_hi - u_lo
-            self.n_local = t_hi - t_lo
-            self.loc_u = (pos_u[t_lo:t_hi] - u_lo).contiguous()       # row inside my user block
-            self.loc_i = pos_i[t_lo:t_hi].contiguous()
-            del pos_u, pos_i
-            ub = self.ub
-            self.item_blk = torch.empty(G, n_items, dg, device=dev)    # all-gather target / reduce-scatter source
             self.item_full = torch.empty(n_items, d, device=dev)
-            self.g_item_full = torch.empty(n_items, d, device=dev)
-            self.user_blk = torch.empty(G * ub, dg, device=dev)        # [G, Ub, d/G]: all-to-all target / source
-            self.user_full = torch.empty(ub, d, device=dev)
-            self.g_user_full = torch.empty(ub, d, device=dev)
+            if self.exchange == "peer":
+                # users are dealt out cyclically (u % G): triples AND user rows are balanced over the ranks whatever the degree
+                # law (contiguous triple-balanced blocks give the hub block few users and the tail block many, so the row
+                # exchange of the two directions is lopsided and every rank waits for the slowest one twice).  A peer pull
+                # can read any stride; only NCCL's all-to-all needs contiguous blocks.
+                r = self.rank
+                mine = (pos_u % G) == r
+                self.positions = torch.nonzero(mine).reshape(-1)       # my triples' positions in the global user-major list
+                self.loc_u = torch.div(pos_u[mine], G, rounding_mode="floor").contiguous()   # row inside my user set
+                self.loc_i = pos_i[mine].contiguous()
+                del pos_u, pos_i, mine
+                self.n_local = int(self.loc_u.numel())
+                self.block_rows = [max(0, (n_users - g + G - 1) // G) for g in range(G)]
+                self.ub = ub = self.block_rows[r]
+                self.user_full = torch.empty(ub, d, device=dev)
+                # what the peers read: my column slice of the final embeddings, my full-width gradient partials
+                self._pb_final = peer.PeerBuffer(n, dg, dev)
+                self._pb_gu = peer.PeerBuffer(max(ub, 1), d, dev)
+                # item gradients travel the other way: every rank PUSHES the column pieces of its [I, d] partial into the
+                # owners' staging slices [G][I][dg] (contiguous on the remote side: 32-byte pieces of a wider remote row
+                # move at half the rate, tools/peer_bw.py), which the owner then sums locally in rank order
+                self._pb_stage = peer.PeerBuffer(G * n_items, dg, dev)
+                self.final = self._pb_final.tensor
+                self.g_item_full = torch.empty(n_items, d, device=dev)
+                self._rows_items64 = peer.int64_array([n_items] * G)
+                self.g_user_full = self._pb_gu.tensor[:ub]
+                self._block_rows64 = peer.int64_array(self.block_rows)
+                self._user_dst_off64 = peer.int64_array([g * dg for g in range(G)])   # user u = g + j G -> row u of [U, dg]
+            else:
+                self.blocks = UserBlockPlan.build(pos_u, n_users, G)
+                self.block_rows = self.blocks.block_sizes()
+                u_lo, u_hi = self.blocks.block(self.rank)
+                t_lo, t_hi = self.blocks.triple_range(self.rank)
+                self.t_lo, self.t_hi, self.ub = t_lo, t_hi, u_hi - u_lo
+                self.n_local = t_hi - t_lo
+                self.loc_u = (pos_u[t_lo:t_hi] - u_lo).contiguous()       # row inside my user block
+                self.loc_i = pos_i[t_lo:t_hi].contiguous()
+                del pos_u, pos_i
+                ub = self.ub
+                self.user_full = torch.empty(ub, d, device=dev)
+                self.item_blk = torch.empty(G, n_items, dg, device=dev)    # all-gather target / reduce-scatter source
+                self.g_item_full = torch.empty(n_items, d, device=dev)
+                self.user_blk = torch.empty(G * ub, dg, device=dev)        # [G, Ub, d/G]: all-to-all target / source
+                self.g_user_full = torch.empty(ub, d, device=dev)
             self.neg = torch.empty(max(self.n_local, 1), dtype=torch.int64, device=dev)
             self.bpr_ws_bytes = self.lib.gcf_bpr_workspace_bytes(self.n_local)
             self.bpr_ws = torch.empty(self.bpr_ws_bytes, dtype=torch.uint8, device=dev)
             # K fwd + K bwd SpMM (Adam fused into the last), sampler, 2 + 2 layout conversions, fused BPR + its reduction
             self.launches_per_step = 2 * n_layers + 7
-            self.collectives_per_step = 5  # item all-gather, user all-to-all, item reduce-scatter, user all-to-all, loss all-reduce
+            # nccl: item all-gather, user all-to-all, item reduce-scatter, user all-to-all, loss all-reduce; peer: two
+            # stream-ordered barriers + the loss all-reduce (2 gathers + 1 sum + 1 copy replace the 4 layout passes)
+            self.collectives_per_step = 5 if self.exchange == "nccl" else 3
             if self.overlap:
                 # row blocks of the replicated operator as views of its arrays: user rows gather item columns only and
                 # vice versa (bipartite), so each block depends on ONE side of the exchanged gradient / produces one side
@@ -530,6 +569,14 @@ class FeatureShardedLightGCNTrainer:
                 self.ws_i, self.ws_i_bytes = self.g_items.workspace(dg)
                 self.p_buf = new()                      # A g_final, handed to the rest of the backward chain as extra[K-1]
                 self.launches_per_step += 3             # two block launches instead of one (forward, backward) + the G(K-1) axpby
+
+    phase_marks: Optional[list] = None   # tools/phase_dist.py: a list that receives (label, CUDA event) pairs of one step
+
+    def _mark(self, label: str) -> None:
+        if self.phase_marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.phase_marks.append((label, ev))
 
     def _loss_on_scores(self, neg_items: Optional[torch.Tensor]) -> torch.Tensor:
         """loss_layout="scores": partial scores on the local columns, one all-reduce of E floats, local gradient pass."""
@@ -548,16 +595,20 @@ class FeatureShardedLightGCNTrainer:
         # 1. partial scores over the local columns (+ the local part of the squared-norm regulariser)
         _lib.check(lib.gcf_bpr_fwd(*args, _lib.BPR_RAW_SCORE, 0.0, _lib.REDUCE_SUM, self.reg, self.reg, 0.0, _lib.ptr(self.loss_reg),
                                    _lib.ptr(self.scores), _lib.ptr(self.bpr_ws), self.bpr_ws_bytes, st), "gcf_bpr_fwd")
+        self._mark("sampler + partial scores")
         # 2. the one data-path collective of the step
         dist.all_reduce(self.scores, op=dist.ReduceOp.SUM)
+        self._mark("score all-reduce")
         # 3. pointwise loss on the complete scores (redundantly on every rank: E floats)
         _lib.check(lib.gcf_bpr_coef_from_scores(_lib.ptr(self.scores), self.n_triples, _lib.BPR_SOFTPLUS, 0.0, _lib.REDUCE_MEAN,
                                                 _lib.ptr(self.loss_pt), _lib.ptr(self.coef), _lib.ptr(self.bpr_ws),
                                                 self.bpr_ws_bytes, st), "gcf_bpr_coef_from_scores")
+        self._mark("coefficients")
         # 4. gradients w.r.t. the local columns
         self.g_final.zero_()
         _lib.check(lib.gcf_bpr_bwd(*args, _lib.ptr(self.coef), None, self.reg, self.reg, 0.0, _lib.ptr(self.g_final[:u]), dg,
                                    _lib.ptr(self.g_final[u:]), dg, st), "gcf_bpr_bwd")
+        self._mark("gradient pass")
         return self.loss_pt / self.world + self.loss_reg   # the pointwise part is replicated: count it once over the ranks
 
     def _exchange_items(self):
@@ -568,6 +619,81 @@ class FeatureShardedLightGCNTrainer:
         """user slices [U, d/G] -> the [G, Ub, d/G] slices of this rank's user block (asynchronous)."""
         return dist.all_to_all_single(self.user_blk, self.final[:self.n_users], output_split_sizes=[self.ub] * self.world,
                                       input_split_sizes=self.block_rows, async_op=True)
+
+    def _loss_on_rows_peer(self, neg_items: Optional[torch.Tensor]) -> torch.Tensor:
+        """loss_layout="rows", exchange="peer": the same dataflow as _loss_on_rows, but the slices are pulled out of the peers'
+        memory (csrc/peer.cu) instead of being sent by NCCL and re-laid out afterwards:
+
+            barrier (every rank's slice of `final` is complete; nobody still reads last step's gradient partials)
+            item_full[i, g*dg:(g+1)*dg] = final_g[U + i, :]         for all g    (gcf_peer_gather_cols over NVLink)
+            user_full[j, g*dg:(g+1)*dg] = final_g[rank + j G, :]    my users: u % G == rank
+            fused BPR on my E/G triples -> g_item_full [I, d] (local), g_user_full [Ub, d] (peer-visible)
+            stage_g[rank][i, :] = g_item_full[i, lo_g:hi_g]          for all g    (gcf_peer_copy2d: remote stores)
+            barrier (every rank's partials are complete and delivered)
+            g_final[U + i, :] = sum_g stage[g][i, :]                 fixed order g = 0..G-1 (gcf_peer_sum_cols, local)
+            g_final[g + j G, :] = g_user_full_g[j, lo:hi]            (gcf_peer_copy_blocks)
+        """
+        lib, st, dg, d, G, u, ub = self.lib, _lib.current_stream(), self.dg, self.d_full, self.world, self.n_users, self.ub
+        if neg_items is None:
+            # Philox slot = position in the user-major list of ALL triples: the draws do not depend on the number of ranks
+            if self.n_local > 0:
+                _lib.check(lib.gcf_sample_negatives_pos(self.seed, self.step_count, _lib.ptr(self.positions), self.n_local, 1,
+                                                        self.n_items, _lib.ptr(self.neg), st), "gcf_sample_negatives_pos")
+            neg = self.neg
+        else:
+            neg = neg_items.to(torch.int64).reshape(-1)
+            if self.order is not None:
+                neg = neg[self.order]
+            neg = neg[self.positions].contiguous()
+        self._mark("sampler")
+        peer.stream_barrier(self.dev)
+        self._mark("barrier 1")
+        # only now may the partials be cleared: before the barrier a slow peer could still be summing last step's
+        self.g_item_full.zero_()
+        self.g_user_full.zero_()
+        self.loss_pt.zero_()
+        self._mark("memsets")
+        _lib.check(lib.gcf_peer_gather_cols(self._pb_final.pointers(u * dg), G, dg, _lib.ptr(self.item_full), d, self.n_items, dg, st),
+                   "gcf_peer_gather_cols")
+        self._mark("item slices -> rows (peer gather)")
+        if ub > 0:
+            # my users are rows rank, rank + G, ... of every peer's [N, dg] slice
+            _lib.check(lib.gcf_peer_gather_cols(self._pb_final.pointers(self.rank * dg), G, G * dg, _lib.ptr(self.user_full), d, ub,
+                                                dg, st), "gcf_peer_gather_cols")
+        self._mark("user slices -> rows (peer gather)")
+        w = 1.0 / max(self.n_triples, 1)
+        if self.n_local > 0:
+            _lib.check(lib.gcf_bpr_fwd_bwd(_lib.ptr(self.user_full), d, _lib.ptr(self.item_full), d, d, _lib.ptr(self.loc_u),
+                                           _lib.ptr(self.loc_i), _lib.ptr(neg), self.n_local, 1, _lib.BPR_SOFTPLUS, 0.0,
+                                           _lib.REDUCE_SUM, self.reg / w, self.reg / w, 0.0, w, _lib.ptr(self.loss_pt), None,
+                                           _lib.ptr(self.g_user_full), d, _lib.ptr(self.g_item_full), d,
+                                           _lib.ptr(self.bpr_ws), self.bpr_ws_bytes, st), "gcf_bpr_fwd_bwd")
+        self._mark("fused BPR")
+        # my partial's column piece g -> slot `rank` of rank g's staging buffer (remote stores, contiguous slices)
+        src = _lib.ptr_values([self.g_item_full.data_ptr() + 4 * g * dg for g in range(G)])
+        dst = _lib.ptr_values([self._pb_stage.base[g] + 4 * self.rank * self.n_items * dg for g in range(G)])
+        _lib.check(lib.gcf_peer_copy2d(src, dst, self._rows_items64, G, d, dg, dg, 0, st), "gcf_peer_copy2d")
+        self._mark("item gradients: column pieces -> owners (peer push)")
+        peer.stream_barrier(self.dev)
+        self._mark("barrier 2")
+        stage = self._pb_stage.tensor
+        _lib.check(lib.gcf_peer_sum_cols(_lib.ptr_values([stage.data_ptr() + 4 * g * self.n_items * dg for g in range(G)]), G, dg,
+                                         _lib.ptr(self.g_final[u:]), dg, self.n_items, dg, st), "gcf_peer_sum_cols")
+        self._mark("item gradients: sum of the G staged slices (local)")
+        _lib.check(lib.gcf_peer_copy_blocks(self._pb_gu.pointers(self.lo), self._block_rows64, self._user_dst_off64, G, d,
+                                            _lib.ptr(self.g_final[:u]), G * dg, dg, st), "gcf_peer_copy_blocks")
+        self._mark("user gradients: rows -> my slice (peer copy)")
+        return self.loss_pt * w
+
+    def close(self) -> None:
+        """Release the peer-visible buffers (collective: every rank, after its last step)."""
+        if getattr(self, "_pb_final", None) is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            for pb in (self._pb_final, self._pb_stage, self._pb_gu):
+                pb.close()
+            self._pb_final = self._pb_stage = self._pb_gu = None
+            self.final = self.g_user_full = None
 
     def _loss_on_rows(self, neg_items: Optional[torch.Tensor], pending=None, defer_wait: bool = False):
         """loss_layout="rows": exchange column slices for full rows, fused BPR on this rank's user block, gradients back
@@ -593,13 +719,18 @@ class FeatureShardedLightGCNTrainer:
         self.g_item_full.zero_()
         self.g_user_full.zero_()
         self.loss_pt.zero_()
+        self._mark("sampler + memsets")
         w_items.wait()
+        self._mark("item all-gather (exposed)")
         _lib.check(lib.gcf_slices_to_rows(_lib.ptr(self.item_blk), _lib.ptr(self.item_full), d, self.n_items, G, dg, st),
                    "gcf_slices_to_rows")
+        self._mark("item slices -> rows")
         w_users.wait()
+        self._mark("user all-to-all (exposed)")
         if ub > 0:
             _lib.check(lib.gcf_slices_to_rows(_lib.ptr(self.user_blk), _lib.ptr(self.user_full), d, ub, G, dg, st),
                        "gcf_slices_to_rows")
+        self._mark("user slices -> rows")
         w = 1.0 / max(self.n_triples, 1)
         if self.n_local > 0:
             # per-rank partial of the global mean: reduction = sum, loss and gradients scaled by 1/E (as in the row layout)
@@ -608,6 +739,7 @@ class FeatureShardedLightGCNTrainer:
                                            _lib.REDUCE_SUM, self.reg / w, self.reg / w, 0.0, w, _lib.ptr(self.loss_pt), None,
                                            _lib.ptr(self.g_user_full), d, _lib.ptr(self.g_item_full), d,
                                            _lib.ptr(self.bpr_ws), self.bpr_ws_bytes, st), "gcf_bpr_fwd_bwd")
+        self._mark("fused BPR")
         # the (small) user exchange goes first: the item rows of the first backward product only need the user gradients
         if ub > 0:
             _lib.check(lib.gcf_rows_to_slices(_lib.ptr(self.g_user_full), d, _lib.ptr(self.user_blk), ub, G, dg, st),
@@ -618,10 +750,12 @@ class FeatureShardedLightGCNTrainer:
                    "gcf_rows_to_slices")
         w_items = dist.reduce_scatter_tensor(self.g_final[u:].reshape(-1), self.item_blk.view(-1), op=dist.ReduceOp.SUM,
                                              async_op=True)
+        self._mark("rows -> slices (users, items)")
         if defer_wait:
             return self.loss_pt * w, (w_users, w_items)
         w_users.wait()
         w_items.wait()
+        self._mark("gradient all-to-all + reduce-scatter (exposed)")
         return self.loss_pt * w
 
     def index_buffers(self) -> List[torch.Tensor]:
@@ -640,14 +774,16 @@ class FeatureShardedLightGCNTrainer:
             e0.record()
         if self.overlap:
             return self._step_overlapped(neg_items, marks, (e0, e1, e2, e3) if marks is not None else None, wait_before_loss)
+        self._mark("start")
         _lib.check(lib.gcf_propagate_fwd(g.struct_ref(), dg, K, _lib.ptr(self.table), _lib.ptr_array(self.layers),
                                          _lib.ptr(self.final), 1.0, _lib.ptr(self.ws), self.ws_bytes, st), "gcf_propagate_fwd")
+        self._mark("forward propagation (K SpMM)")
         if marks is not None:
             e1.record()
         if wait_before_loss is not None:
             torch.cuda.current_stream().wait_event(wait_before_loss)
         if self.loss_layout == "rows":
-            loss_local = self._loss_on_rows(neg_items)
+            loss_local = self._loss_on_rows_peer(neg_items) if self.exchange == "peer" else self._loss_on_rows(neg_items)
         else:
             loss_local = self._loss_on_scores(neg_items)
         if marks is not None:
@@ -661,6 +797,7 @@ class FeatureShardedLightGCNTrainer:
             e3.record()
             marks.append((e0, e1, K))
             marks.append((e2, e3, K))
+        self._mark("backward propagation + Adam (K SpMM)")
         loss = loss_local.clone()
         dist.all_reduce(loss, op=dist.ReduceOp.SUM)   # every rank holds 1/G of the global value ("scores") or its block's share ("rows")
         return loss

@@ -162,6 +162,68 @@ def test_slices_rows_layout_conversion(cuda, shape):
     assert lib.gcf_slices_to_rows(_lib.ptr(blocked), _lib.ptr(rows), 4, n, G, w, st) != 0   # ld too small is rejected
 
 
+@pytest.mark.parametrize("shape", [(1000, 8, 8), (777, 4, 16), (5, 2, 32), (301, 3, 12), (64, 16, 4)])
+def test_peer_movers_on_local_sources(cuda, shape):
+    """csrc/peer.cu's three movers with every "peer" on this GPU (the multi-GPU trainers hand them IPC mappings of other ranks'
+    buffers; the arithmetic is the same): gather_cols = slices -> rows, sum_cols = fixed-order sum of column slices,
+    copy_blocks = row blocks of different heights stacked.  Pure data movement / one rounding per add: bit-exact."""
+    import ctypes
+
+    n, G, w = shape
+    lib, st = _lib.load(), _lib.current_stream()
+    # gather_cols: G sources [n, w] (leading dimension w + 4) -> [n, G*w]
+    srcs = [torch.randn(n, w + 4, device=cuda) for _ in range(G)]
+    rows = torch.full((n, G * w + 8), -7.0, device=cuda)
+    _lib.check(lib.gcf_peer_gather_cols(_lib.ptr_array(srcs), G, w + 4, _lib.ptr(rows), rows.stride(0), n, w, st), "gcf_peer_gather_cols")
+    want = torch.cat([t[:, :w] for t in srcs], dim=1)
+    assert torch.equal(rows[:, : G * w], want) and bool((rows[:, G * w:] == -7.0).all())
+    # sum_cols: column slice [lo, lo + w) of G full-width partials, summed in source order
+    d = G * w
+    parts = [torch.randn(n, d, device=cuda) for _ in range(G)]
+    lo = (G - 1) * w
+    ptrs = (ctypes.c_void_p * G)(*[t.data_ptr() + 4 * lo for t in parts])
+    out = torch.full((n, w + 4), 3.0, device=cuda)
+    _lib.check(lib.gcf_peer_sum_cols(ptrs, G, d, _lib.ptr(out), out.stride(0), n, w, st), "gcf_peer_sum_cols")
+    acc = torch.zeros(n, w, device=cuda)
+    for t in parts:
+        acc = acc + t[:, lo:lo + w]
+    assert torch.equal(out[:, :w], acc) and bool((out[:, w:] == 3.0).all())
+    # copy_blocks: blocks of 0 .. n rows stacked in source order
+    heights = [(n * (g + 1)) // (G + 1) if g % 3 != 1 else 0 for g in range(G)]
+    ptrs = (ctypes.c_void_p * G)(*[t.data_ptr() + 4 * lo for t in parts])
+    hts = (ctypes.c_int64 * G)(*heights)
+    stack = torch.full((sum(heights) + 1, w), -1.0, device=cuda)
+    _lib.check(lib.gcf_peer_copy_blocks(ptrs, hts, None, G, d, _lib.ptr(stack), w, w, st), "gcf_peer_copy_blocks")
+    want = torch.cat([t[:h, lo:lo + w] for t, h in zip(parts, heights)], dim=0)
+    assert torch.equal(stack[: sum(heights)], want) and bool((stack[sum(heights):] == -1.0).all())
+    # the same with explicit destination offsets: source g fills rows g, g + G, ... (users dealt out cyclically)
+    hts = (ctypes.c_int64 * G)(*[(n - g + G - 1) // G for g in range(G)])
+    offs = (ctypes.c_int64 * G)(*[g * w for g in range(G)])
+    inter = torch.full((n, w), -1.0, device=cuda)
+    _lib.check(lib.gcf_peer_copy_blocks(ptrs, hts, offs, G, d, _lib.ptr(inter), G * w, w, st), "gcf_peer_copy_blocks")
+    for g in range(G):
+        assert torch.equal(inter[g::G], parts[g][: (n - g + G - 1) // G, lo:lo + w])
+    assert lib.gcf_peer_gather_cols(_lib.ptr_array(srcs), G, w + 4, _lib.ptr(rows), w, n, w, st) != 0   # ld_dst too small is rejected
+
+
+def test_peer_alloc_export_roundtrip(cuda):
+    """gcf_peer_alloc hands out a zero-filled block torch can alias, gcf_peer_export a 64-byte IPC handle for it (opening it
+    takes a second process: tests/test_dist.py)."""
+    import ctypes
+
+    from recommendation_b200 import peer
+
+    blk = peer._Block(1000)
+    t = torch.as_tensor(blk, device=cuda)
+    assert t.data_ptr() == blk.ptr and t.numel() == 1000 and float(t.abs().sum()) == 0.0
+    t.fill_(2.0)
+    handle = ctypes.create_string_buffer(peer.HANDLE_BYTES)
+    _lib.check(_lib.load().gcf_peer_export(ctypes.c_void_p(blk.ptr), handle), "gcf_peer_export")
+    assert any(handle.raw)
+    del t
+    blk.free()
+
+
 def test_spmm_epilogues(cuda):
     rng = np.random.default_rng(2)
     n, d = 600, 64
@@ -335,6 +397,13 @@ def test_sampler_window_equals_slice_of_the_full_draw(cuda):
     from oracle import philox_ref
     want = philox_ref.sample_negatives(3, 1, 10, 1, 1000, slot_base=base)
     assert out.cpu().tolist() == want.tolist()
+    # gcf_sample_negatives_pos: an interleaved subset of the triples (users dealt out cyclically over the ranks)
+    for r, G in ((0, 2), (3, 8)):
+        pos = torch.arange(r, n, G, dtype=torch.int64, device=cuda)
+        out = torch.empty(pos.numel() * n_negs, dtype=torch.int64, device=cuda)
+        _lib.check(lib.gcf_sample_negatives_pos(99, 7, _lib.ptr(pos), pos.numel(), n_negs, n_items, _lib.ptr(out),
+                                                _lib.current_stream()), "gcf_sample_negatives_pos")
+        assert torch.equal(out.view(-1, n_negs), full[pos])
 
 
 def test_xavier_table_is_a_function_of_seed_row_and_column(cuda):
