@@ -310,11 +310,12 @@ def run_ours(args):
         while F > 1 and (world % F != 0 or d % F != 0 or (d // F) % 4 != 0 or d // F < 8):
             F //= 2
         if args.loss_layout == "auto":
-            args.loss_layout = "scores" if world <= 2 else "rows"
+            args.loss_layout = "rows"   # r03: with the peer-memory exchange the rows layout wins at every N (2 GPUs 49.7 vs 54.5 ms)
         if F == world:
             trainer = FeatureShardedLightGCNTrainer(users, items, U, I, d=d, n_layers=K, lr=0.01, reg_weight=1e-4, seed=1234,
-                                                    loss_layout=args.loss_layout, overlap=args.overlap_exchange,
-                                                    exchange=args.exchange)
+                                                    loss_layout=args.loss_layout, exchange=args.exchange,
+                                                    overlap=(args.overlap_exchange == "on" or
+                                                             (args.overlap_exchange == "auto" and args.exchange == "peer")))
             nnz, spmm_rows, spmm_d = trainer.local_nnz, n, trainer.dg
             parallelism = (f"feature-sharded over {world} GPUs: every rank owns d/G = {trainer.dg} columns of all [N, d] tables, "
                            f"propagation / Adam without any collective; ")
@@ -323,8 +324,11 @@ def run_ours(args):
                     parallelism += ("loss on full-width rows of one user block per rank: every rank pulls the column slices it needs "
                                     "straight out of the peers' memory over NVLink (one gather kernel per table that also lays the "
                                     "rows out), fused BPR on E/G triples, gradients pulled back the same way (one summing kernel for "
-                                    "the items, one copy kernel for the users); two stream-ordered barriers per step, no NCCL "
-                                    "collective on the data path")
+                                    "the items, one copy kernel for the users); device-side barriers over peer flag words, no NCCL "
+                                    "collective on the data path"
+                                    + ("; the item-side transfers run on a high-priority side stream next to the user-row block of "
+                                       "the last forward layer / the item-row block of the first backward product"
+                                       if trainer.overlap else ""))
                 else:
                     parallelism += ("loss on full-width rows of one user block per rank: item slices all-gathered, user slices "
                                 "all-to-all'ed, fused BPR on E/G triples, gradients returned by one reduce-scatter + one all-to-all"
@@ -565,13 +569,15 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("GCF_BENCH_WORKLOAD", "cfg5"))
     ap.add_argument("--loss-layout", choices=("auto", "rows", "scores"), default=os.environ.get("GCF_BENCH_LOSS_LAYOUT", "auto"),
                     help="feature-sharded layout only: where the BPR loss is evaluated (see dist.FeatureShardedLightGCNTrainer); "
-                         "auto = measured default: all-reduced scores on 2 GPUs (60.5 vs 61.6 ms), full-width rows from 4 GPUs on")
+                         "auto = measured default: full-width rows at every N")
     ap.add_argument("--exchange", choices=("peer", "nccl"), default=os.environ.get("GCF_BENCH_EXCHANGE", "peer"),
                     help="feature-sharded layout, loss on rows: 'peer' = slices pulled out of the peers' memory over NVLink by "
                          "csrc/peer.cu (default), 'nccl' = all-gather / all-to-all / reduce-scatter + layout passes (r01/r02)")
-    ap.add_argument("--overlap-exchange", action="store_true",
-                    help="feature-sharded layout, loss on rows: overlap the exchanges with row blocks of the adjacent propagation "
-                         "layers (measured neutral on cfg5 at 2 and 4 GPUs)")
+    ap.add_argument("--overlap-exchange", choices=("auto", "on", "off"), nargs="?", const="on",
+                    default=os.environ.get("GCF_BENCH_OVERLAP", "auto"),
+                    help="feature-sharded layout, loss on rows: run the item-side exchanges next to row blocks of the adjacent "
+                         "propagation layers.  auto = on with the peer-memory exchange (cfg5, 8 GPUs: 25.8 -> 24.2 ms; 4 GPUs: "
+                         "36.7 -> 36.0 ms), off with the NCCL exchange (measured neutral in r01)")
     ap.add_argument("--feature-shards", type=int, default=int(os.environ.get("GCF_BENCH_FEATURE_SHARDS", "0")),
                     help="N > 1 only: F feature shards x N/F row shards (1 = row-sharded, N = feature-sharded, 0 = measured default)")
     ap.add_argument("--no-e2e", action="store_true")

@@ -227,6 +227,10 @@ int gcf_peer_free(void* dev_ptr);
 int gcf_peer_export(const void* dev_ptr, void* handle64);
 int gcf_peer_open(const void* handle64, void** peer_ptr);
 int gcf_peer_close(void* peer_ptr);
+/* Device-side barrier of the n_ranks processes on `stream`: flag_arrays[g] = rank g's zero-initialised array of >= n_ranks
+ * uint32 (peer mappings except flag_arrays[rank]); epoch = 1, 2, 3, ... (compared modulo 2^32), the same on every rank for the same barrier.  Work
+ * enqueued on the stream before the call (on any rank) is complete and visible before work enqueued after it starts. */
+int gcf_peer_barrier(void* const* flag_arrays, int32_t n_ranks, int32_t rank, uint64_t epoch, gcf_stream_t stream);
 int gcf_peer_gather_cols(const float* const* src, int32_t n_src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t n_rows,
                          int32_t w, gcf_stream_t stream);
 int gcf_peer_sum_cols(const float* const* src, int32_t n_src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t n_rows,

@@ -75,6 +75,7 @@ _SIGNATURES = {
     "gcf_peer_export": (c_int32, [c_void_p, c_void_p]),
     "gcf_peer_open": (c_int32, [c_void_p, POINTER(c_void_p)]),
     "gcf_peer_close": (c_int32, [c_void_p]),
+    "gcf_peer_barrier": (c_int32, [POINTER(c_void_p), c_int32, c_int32, c_uint64, c_void_p]),
     "gcf_peer_gather_cols": (c_int32, [POINTER(c_void_p), c_int32, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p]),
     "gcf_peer_sum_cols": (c_int32, [POINTER(c_void_p), c_int32, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p]),
     "gcf_peer_copy2d": (c_int32, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int32, c_int64, c_int64, c_int32, c_int32,

@@ -72,6 +72,33 @@ peer_copy2d_kernel(PeerBlocks b, long long ld_src4, long long ld_dst4, int w4, i
   }
 }
 
+// Stream-ordered barrier between the GPUs of the group, on the device: every rank stores the epoch into slot `rank` of every
+// peer's flag array (system-scope release: all earlier writes of this stream, local or remote, are visible first) and then
+// waits until its own array shows the epoch in every slot.  One warp; the kernel of a rank can only finish once every other
+// rank has LAUNCHED the same barrier, so all ranks must issue their barriers in the same order.
+struct PeerFlags { unsigned* p[kMaxPeers]; };
+__global__ void peer_barrier_kernel(PeerFlags flags, int n, int rank, unsigned epoch) {
+  const int g = threadIdx.x;
+  if (g < n) {
+    __threadfence_system();
+    // max, not a plain store: barriers issued from two streams of one rank may execute out of issue order, and a flag
+    // that stepped back from epoch e + 1 to e would strand a peer that waits for e + 1
+    asm volatile("red.release.sys.global.max.u32 [%0], %1;" ::"l"(flags.p[g] + rank), "r"(epoch) : "memory");
+    unsigned v;
+    unsigned long long t0 = 0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags.p[rank] + g) : "memory");
+      if ((++spins & 0xfffu) == 0) {            // a peer that never arrives (crashed process) must not hang the GPU for ever
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 30ull * 1000000000ull) __trap();
+      }
+    } while ((int)(v - epoch) < 0);
+    __threadfence_system();
+  }
+}
+
 template <int UNR>
 __global__ void __launch_bounds__(256)
 peer_sum_kernel(PeerSrc src, int n_src, long long ld_src4, float4* __restrict__ dst, long long ld_dst4, int w4, int shift,
@@ -194,6 +221,19 @@ extern "C" int gcf_peer_open(const void* handle64, void** peer_ptr) {
 
 extern "C" int gcf_peer_close(void* peer_ptr) {
   if (peer_ptr != nullptr) GCF_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+  return GCF_OK;
+}
+
+extern "C" int gcf_peer_barrier(void* const* flag_arrays, int32_t n_ranks, int32_t rank, uint64_t epoch, gcf_stream_t stream) {
+  GCF_REQUIRE(flag_arrays != nullptr && n_ranks >= 1 && n_ranks <= kMaxPeers && rank >= 0 && rank < n_ranks,
+              "gcf_peer_barrier: bad rank / n_ranks (<= %d)", kMaxPeers);
+  PeerFlags f{};
+  for (int g = 0; g < n_ranks; ++g) {
+    GCF_REQUIRE(flag_arrays[g] != nullptr, "gcf_peer_barrier: null flag array %d", g);
+    f.p[g] = static_cast<unsigned*>(flag_arrays[g]);
+  }
+  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(f, n_ranks, rank, (unsigned)epoch);
+  GCF_LAUNCH_CHECK("peer_barrier_kernel");
   return GCF_OK;
 }
 

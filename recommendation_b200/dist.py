@@ -438,10 +438,10 @@ class FeatureShardedLightGCNTrainer:
                  init_table: Optional[torch.Tensor] = None, loss_layout: str = "rows", overlap: bool = False,
                  exchange: str = "peer"):
         """exchange (loss_layout="rows"): "peer" (default) -- the column slices are read straight out of the peers' memory
-        over NVLink by one kernel per direction that also converts the layout (csrc/peer.cu; two stream-ordered barriers per
-        step are the only collectives of the loss); "nccl" -- the r01 path: all-gather / all-to-all / reduce-scatter with a
+        over NVLink by one kernel per direction that also converts the layout (csrc/peer.cu; two device-side barriers over peer
+        flag words per step; the only NCCL call left is the all-reduce of the scalar loss); "nccl" -- the r01 path: all-gather / all-to-all / reduce-scatter with a
         layout pass on either side.
-        overlap (loss_layout="rows", exchange="nccl", n_layers >= 2): the last forward layer and the first backward layer are launched as
+        overlap (loss_layout="rows", n_layers >= 2): the last forward layer and the first backward layer are launched as
         an item-row block and a user-row block of the (bipartite) operator, so that the item all-gather runs while the user
         rows are still being computed and the item reduce-scatter while the item rows of the first backward product are.
         Measured neutral on cfg5 (2 GPUs 61.7 vs 61.4 ms, 4 GPUs 40.1 vs 40.2 ms: the collectives compete with the SpMM for
@@ -454,7 +454,7 @@ class FeatureShardedLightGCNTrainer:
             raise ValueError("exchange must be 'peer' or 'nccl'")
         self.loss_layout = loss_layout
         self.exchange = exchange if loss_layout == "rows" else "nccl"
-        self.overlap = bool(overlap) and loss_layout == "rows" and n_layers >= 2 and self.exchange == "nccl"
+        self.overlap = bool(overlap) and loss_layout == "rows" and n_layers >= 2
         if not users.is_cuda:
             raise RuntimeError("FeatureShardedLightGCNTrainer: tensors must be on the rank's CUDA device")
         self.lib = _lib.load()
@@ -519,6 +519,7 @@ class FeatureShardedLightGCNTrainer:
                 self.ub = ub = self.block_rows[r]
                 self.user_full = torch.empty(ub, d, device=dev)
                 # what the peers read: my column slice of the final embeddings, my full-width gradient partials
+                self._barrier = peer.PeerBarrier(dev)
                 self._pb_final = peer.PeerBuffer(n, dg, dev)
                 self._pb_gu = peer.PeerBuffer(max(ub, 1), d, dev)
                 # item gradients travel the other way: every rank PUSHES the column pieces of its [I, d] partial into the
@@ -568,6 +569,8 @@ class FeatureShardedLightGCNTrainer:
                 self.ws_u, self.ws_u_bytes = self.g_users.workspace(dg)
                 self.ws_i, self.ws_i_bytes = self.g_items.workspace(dg)
                 self.p_buf = new()                      # A g_final, handed to the rest of the backward chain as extra[K-1]
+                # high priority: the movers' few CTAs must get SM slots while a propagation launch has thousands queued
+                self._side = torch.cuda.Stream(device=dev, priority=-1) if self.exchange == "peer" else None
                 self.launches_per_step += 3             # two block launches instead of one (forward, backward) + the G(K-1) axpby
 
     phase_marks: Optional[list] = None   # tools/phase_dist.py: a list that receives (label, CUDA event) pairs of one step
@@ -646,7 +649,7 @@ class FeatureShardedLightGCNTrainer:
                 neg = neg[self.order]
             neg = neg[self.positions].contiguous()
         self._mark("sampler")
-        peer.stream_barrier(self.dev)
+        self._barrier()
         self._mark("barrier 1")
         # only now may the partials be cleared: before the barrier a slow peer could still be summing last step's
         self.g_item_full.zero_()
@@ -674,7 +677,7 @@ class FeatureShardedLightGCNTrainer:
         dst = _lib.ptr_values([self._pb_stage.base[g] + 4 * self.rank * self.n_items * dg for g in range(G)])
         _lib.check(lib.gcf_peer_copy2d(src, dst, self._rows_items64, G, d, dg, dg, 0, st), "gcf_peer_copy2d")
         self._mark("item gradients: column pieces -> owners (peer push)")
-        peer.stream_barrier(self.dev)
+        self._barrier()
         self._mark("barrier 2")
         stage = self._pb_stage.tensor
         _lib.check(lib.gcf_peer_sum_cols(_lib.ptr_values([stage.data_ptr() + 4 * g * self.n_items * dg for g in range(G)]), G, dg,
@@ -690,7 +693,7 @@ class FeatureShardedLightGCNTrainer:
         if getattr(self, "_pb_final", None) is not None:
             torch.cuda.synchronize()
             dist.barrier()
-            for pb in (self._pb_final, self._pb_stage, self._pb_gu):
+            for pb in (self._pb_final, self._pb_stage, self._pb_gu, self._barrier):
                 pb.close()
             self._pb_final = self._pb_stage = self._pb_gu = None
             self.final = self.g_user_full = None
@@ -773,7 +776,8 @@ class FeatureShardedLightGCNTrainer:
             e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
             e0.record()
         if self.overlap:
-            return self._step_overlapped(neg_items, marks, (e0, e1, e2, e3) if marks is not None else None, wait_before_loss)
+            run = self._step_overlapped_peer if self.exchange == "peer" else self._step_overlapped
+            return run(neg_items, marks, (e0, e1, e2, e3) if marks is not None else None, wait_before_loss)
         self._mark("start")
         _lib.check(lib.gcf_propagate_fwd(g.struct_ref(), dg, K, _lib.ptr(self.table), _lib.ptr_array(self.layers),
                                          _lib.ptr(self.final), 1.0, _lib.ptr(self.ws), self.ws_bytes, st), "gcf_propagate_fwd")
@@ -846,6 +850,110 @@ class FeatureShardedLightGCNTrainer:
             marks.append((events[0], events[1], K))
             marks.append((events[2], events[3], K))
         loss = loss_local.clone()
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+        return loss
+
+    def _step_overlapped_peer(self, neg_items, marks, events, wait_before_loss=None) -> torch.Tensor:
+        """exchange="peer" with the item-side transfers hidden behind row blocks of the adjacent propagation layers.
+
+        The operator is bipartite: item rows gather user columns only and vice versa.  So the LAST forward layer is launched
+        as its item-row block first -- the moment every rank has its item slice (barrier on the side stream) the peer gather
+        of the item table runs on the side stream while the main stream computes the user-row block -- and the FIRST backward
+        product as its item-row block (needs the user gradients only) while the side stream pushes the item-gradient pieces
+        to their owners and sums them.  The peer movers run ~128 CTAs and touch little local HBM, so they share the GPU with
+        the SpMM at small cost.  Four stream-ordered barriers per step instead of two."""
+        lib, g, dg, d, G, K, u, ub = self.lib, self.graph, self.dg, self.d_full, self.world, self.k, self.n_users, self.ub
+        main, side = torch.cuda.current_stream(), self._side
+        st = main.cuda_stream
+        self._mark("start")
+        # ---- forward: K-1 full layers, then the last one (with the layer sum) item rows first ----
+        cur = self.table
+        for k in range(K - 1):
+            _lib.check(lib.gcf_spmm_csr_f32(g.struct_ref(), dg, _lib.ptr(cur), dg, _lib.ptr(self.layers[k]), dg, None, 0,
+                                            _lib.EPILOGUE_NONE, 1.0, 1.0, 0, _lib.ptr_array([]), _lib.float_array([]),
+                                            _lib.ptr(self.ws), self.ws_bytes, 0, st), "gcf_spmm_csr_f32")
+            cur = self.layers[k]
+        prev = [self.table] + self.layers[: K - 1]
+        self._block_spmm(self.g_items, self.ws_i, self.ws_i_bytes, cur, self.final[u:], [t[u:] for t in prev], "gcf_spmm_csr_f32")
+        items_ready = torch.cuda.Event()
+        items_ready.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(items_ready)
+            self._barrier()                      # every rank's item slice of `final` is complete
+            _lib.check(lib.gcf_peer_gather_cols(self._pb_final.pointers(u * dg), G, dg, _lib.ptr(self.item_full), d, self.n_items, dg,
+                                                side.cuda_stream), "gcf_peer_gather_cols")
+            items_gathered = torch.cuda.Event()
+            items_gathered.record(side)
+        self._block_spmm(self.g_users, self.ws_u, self.ws_u_bytes, cur, self.final[:u], [t[:u] for t in prev], "gcf_spmm_csr_f32")
+        self._mark("forward propagation (last layer in two row blocks; item gather on the side stream)")
+        if events is not None:
+            events[1].record()
+        if wait_before_loss is not None:
+            main.wait_event(wait_before_loss)
+        # ---- loss ----
+        if neg_items is None:
+            if self.n_local > 0:
+                _lib.check(lib.gcf_sample_negatives_pos(self.seed, self.step_count, _lib.ptr(self.positions), self.n_local, 1,
+                                                        self.n_items, _lib.ptr(self.neg), st), "gcf_sample_negatives_pos")
+            neg = self.neg
+        else:
+            neg = neg_items.to(torch.int64).reshape(-1)
+            if self.order is not None:
+                neg = neg[self.order]
+            neg = neg[self.positions].contiguous()
+        self._barrier()                          # every rank's user slice is complete; last step's partials are consumed
+        self.g_item_full.zero_()
+        self.g_user_full.zero_()
+        self.loss_pt.zero_()
+        if ub > 0:
+            _lib.check(lib.gcf_peer_gather_cols(self._pb_final.pointers(self.rank * dg), G, G * dg, _lib.ptr(self.user_full), d, ub,
+                                                dg, st), "gcf_peer_gather_cols")
+        main.wait_event(items_gathered)
+        self._mark("sampler, barrier, memsets, user gather (+ wait for the item gather)")
+        w = 1.0 / max(self.n_triples, 1)
+        if self.n_local > 0:
+            _lib.check(lib.gcf_bpr_fwd_bwd(_lib.ptr(self.user_full), d, _lib.ptr(self.item_full), d, d, _lib.ptr(self.loc_u),
+                                           _lib.ptr(self.loc_i), _lib.ptr(neg), self.n_local, 1, _lib.BPR_SOFTPLUS, 0.0,
+                                           _lib.REDUCE_SUM, self.reg / w, self.reg / w, 0.0, w, _lib.ptr(self.loss_pt), None,
+                                           _lib.ptr(self.g_user_full), d, _lib.ptr(self.g_item_full), d,
+                                           _lib.ptr(self.bpr_ws), self.bpr_ws_bytes, st), "gcf_bpr_fwd_bwd")
+        self._mark("fused BPR")
+        if events is not None:
+            events[2].record()
+        # ---- backward: P = A g_final block by block, the item gradients travel while the item rows of P are computed ----
+        self._barrier()                                        # every rank's BPR is done: the user partials may be pulled
+        _lib.check(lib.gcf_peer_copy_blocks(self._pb_gu.pointers(self.lo), self._block_rows64, self._user_dst_off64, G, d,
+                                            _lib.ptr(self.g_final[:u]), G * dg, dg, st), "gcf_peer_copy_blocks")
+        users_done = torch.cuda.Event()
+        users_done.record(main)
+        with torch.cuda.stream(side):
+            # starts once the user copy has left the links, i.e. together with the item-row block below
+            side.wait_event(users_done)
+            src = _lib.ptr_values([self.g_item_full.data_ptr() + 4 * q * dg for q in range(G)])
+            dst = _lib.ptr_values([self._pb_stage.base[q] + 4 * self.rank * self.n_items * dg for q in range(G)])
+            _lib.check(lib.gcf_peer_copy2d(src, dst, self._rows_items64, G, d, dg, dg, 0, side.cuda_stream), "gcf_peer_copy2d")
+            self._barrier()                                    # every rank's pieces have been delivered
+            stage = self._pb_stage.tensor
+            _lib.check(lib.gcf_peer_sum_cols(_lib.ptr_values([stage.data_ptr() + 4 * q * self.n_items * dg for q in range(G)]), G, dg,
+                                             _lib.ptr(self.g_final[u:]), dg, self.n_items, dg, side.cuda_stream), "gcf_peer_sum_cols")
+            item_grads = torch.cuda.Event()
+            item_grads.record(side)
+        self._mark("barrier + user gradients (peer copy)")
+        self._block_spmm(self.g_items, self.ws_i, self.ws_i_bytes, self.g_final, self.p_buf[u:], [], "gcf_spmm_csr_f32")
+        main.wait_event(item_grads)
+        self._mark("item rows of A g (item gradients pushed + summed on the side stream)")
+        self._block_spmm(self.g_users, self.ws_u, self.ws_u_bytes, self.g_final, self.p_buf[:u], [], "gcf_spmm_csr_f32")
+        extra = [None] * (K - 1) + [self.p_buf]
+        _lib.check(lib.gcf_propagate_bwd_adam(g.struct_ref(), dg, K - 1, _lib.ptr(self.g_final), _lib.ptr_array(extra), 1.0,
+                                              _lib.ptr(self.ping), _lib.ptr(self.pong), None, _lib.ptr(self.table),
+                                              _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), self.lr, 0.9, 0.999, 1e-8, 0.0, 0,
+                                              self.step_count, _lib.ptr(self.ws), self.ws_bytes, st), "gcf_propagate_bwd_adam")
+        self._mark("user rows of A g + remaining backward layers + Adam")
+        if events is not None:
+            events[3].record()
+            marks.append((events[0], events[1], K))
+            marks.append((events[2], events[3], K))
+        loss = (self.loss_pt * w).clone()
         dist.all_reduce(loss, op=dist.ReduceOp.SUM)
         return loss
 

@@ -5,13 +5,13 @@ address space (CUDA IPC, `gcf_peer_export` / `gcf_peer_open`), so that a kernel 
 over NVLink -- csrc/peer.cu's movers take the list of per-rank base pointers this class hands out.  The reference has no
 distributed code; this replaces NCCL + layout-pass pairs of the loss exchange (dist.py).
 
-Nothing here synchronises ranks: `stream_barrier()` is the ordering primitive the trainers use between a producer kernel on
-one rank and a consumer kernel on another (a one-element all-reduce enqueued on the current stream).
+`PeerBarrier` is the ordering primitive the trainers use between a producer kernel on one rank and a consumer kernel on
+another: a one-warp kernel over peer-visible flag words, enqueued on the current stream.
 """
 from __future__ import annotations
 
 import ctypes
-from typing import List, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -89,17 +89,26 @@ class PeerBuffer:
         self._block.free()
 
 
-_flag = {}
+class PeerBarrier:
+    """Stream-ordered barrier of the ranks on the device (gcf_peer_barrier): every rank's work enqueued on its current stream
+    BEFORE the call completes, and is visible to the peers, before any rank's work enqueued AFTER it starts.  A one-warp
+    kernel over peer-visible flag words -- no NCCL kernel, so it also works from a high-priority side stream while the default
+    stream is busy.  All ranks must call it in the same order (each call advances the epoch)."""
 
+    def __init__(self, device: torch.device, group=None):
+        self._flags = PeerBuffer(1, 64, device, group)        # 64 zero-initialised 32-bit words per rank
+        self.rank, self.world = self._flags.rank, self._flags.world
+        self._ptrs = self._flags.pointers()
+        self._epoch = 0
+        self._lib = _lib.load()
 
-def stream_barrier(device: torch.device, group=None) -> None:
-    """Every rank's work enqueued on its current stream BEFORE this call completes before any rank's work enqueued AFTER it
-    starts: a one-element NCCL all-reduce (its kernel waits for the current stream and the current stream waits for it)."""
-    key = (device.index, id(group))
-    t = _flag.get(key)
-    if t is None:
-        t = _flag[key] = torch.zeros(1, dtype=torch.float32, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    def __call__(self, stream: Optional[int] = None) -> None:
+        self._epoch += 1
+        _lib.check(self._lib.gcf_peer_barrier(self._ptrs, self.world, self.rank, self._epoch & 0xFFFFFFFF,
+                                              _lib.current_stream() if stream is None else stream), "gcf_peer_barrier")
+
+    def close(self) -> None:
+        self._flags.close()
 
 
 def int64_array(values: Sequence[int]) -> "ctypes.Array":

@@ -254,7 +254,9 @@ def _nccl_feature_worker(rank, world, port, n_users, n_items, users, items, tabl
         tr = FeatureShardedLightGCNTrainer(users_t, items_t, n_users, n_items, d=table0.shape[1], n_layers=k, lr=0.01,
                                            reg_weight=1e-4, init_table=torch.from_numpy(table0),
                                            loss_layout=loss_layout.split("-")[0], overlap=loss_layout.endswith("-overlap"),
-                                           exchange="nccl" if loss_layout.endswith(("-nccl", "-overlap")) else "peer")
+                                           exchange="nccl" if loss_layout in ("rows-nccl", "rows-overlap") else "peer")
+        if loss_layout == "rows-peer-overlap":
+            assert tr.overlap and tr.exchange == "peer"
         losses = [float(tr.step(neg_items=torch.from_numpy(negs[s]).to(dev)).item()) for s in range(negs.shape[0])]
         table = tr.gathered_table().cpu().numpy()
         if rank == 0:
@@ -264,7 +266,7 @@ def _nccl_feature_worker(rank, world, port, n_users, n_items, users, items, tabl
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("loss_layout", ["rows", "rows-nccl", "rows-overlap", "scores"])
+@pytest.mark.parametrize("loss_layout", ["rows", "rows-peer-overlap", "rows-nccl", "rows-overlap", "scores"])
 def test_feature_sharded_trainer_matches_single_gpu(loss_layout):
     """"rows" = the default: slices pulled out of the peers' memory over NVLink (csrc/peer.cu); "rows-nccl" / "rows-overlap" =
     the NCCL exchanges with layout passes; "scores" = one all-reduce of partial scores."""
