@@ -11,7 +11,10 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint64, c_vo
 from pathlib import Path
 from typing import Optional
 
-LIB_PATH = Path(__file__).with_name("libgcf.so")
+import os
+
+# GCF_LIB_PATH: load another build of the same sources (tuning sweeps, tools/sweep_infonce_poly.sh); default = the in-tree library
+LIB_PATH = Path(os.environ["GCF_LIB_PATH"]) if os.environ.get("GCF_LIB_PATH") else Path(__file__).with_name("libgcf.so")
 
 MAX_ADDENDS = 8
 EPILOGUE_NONE, EPILOGUE_L2NORM = 0, 1

@@ -33,7 +33,10 @@ constexpr int kChunkK = 64;      // bf16 elements per 128-byte swizzled row
 constexpr int kLseStages = 4;    // TMA ring depth (one stage = one [kTileN x 64] chunk = 32 KB)
 constexpr int kLseThreads = 320; // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue (two per TMEM lane quadrant)
 constexpr int kMaxChunks = 16;   // d <= 1024 (the tuner grids of ncl.py / ssl4rec.py / gcl.py go up to 1024)
-constexpr int kPolyOf8 = 2;       // exponentials evaluated on the FMA pipe per 8 logits (measured best of 0 / 2 / 3 / 4: r01 profiles)
+#ifndef GCF_POLY_OF_8
+#define GCF_POLY_OF_8 2           // measured best of 0 / 2 / 3 / 4 (r01) and of 2 / 3 / 4 / 5 (r03: tools/sweep_infonce_poly.sh, profiles/r03_infonce_poly_sweep.log)
+#endif
+constexpr int kPolyOf8 = GCF_POLY_OF_8;   // exponentials evaluated on the FMA pipe per 8 logits
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 

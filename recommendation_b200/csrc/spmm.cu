@@ -687,7 +687,15 @@ static int spmm_impl(const gcf_csr_t* A, int32_t d, const float* X, int64_t ldx,
   // 4.10 vs 3.70 ms (d = 16), but 4.12 vs 5.59 ms at d = 32 and 7.02 vs 9.09 ms at d = 64.
   const bool flat_default = d == 32 || (d >= 36 && d <= 128);
   const bool flat_capable = flat_default || d == 8 || d == 16;
-  if (A->n_tiles > 0 && A->tiles != nullptr && ((variant == 0 && flat_default) || (variant >= 10 && flat_capable))) {
+  // Launches with an epilogue (addends / normalise / Adam) on operators whose X table sits in the L2 go back to the row-walking
+  // kernel: the flat kernel parks finished rows in a shared-memory stash and pays ~2x the instructions for it, which only
+  // hides behind DRAM time.  Measured (gpurun_out/r03/exp_spmm_small_epilogue.log, one addend): cfg1 79.9 vs 63.6 us, cfg2
+  // 184 vs 149 us, cfg3 (d = 128) 199 vs 125 us, cfg4 330 vs 301 us -- but cfg5 (3.84 GB table) 8.31 vs 10.1 ms.  Both kernels
+  // sum in the same order: the choice does not change a bit of the result.
+  const bool plain_launch = adam == nullptr && epilogue == GCF_EPILOGUE_NONE && OUT == nullptr;
+  const bool table_in_l2 = (long long)A->n_cols * d * 4 <= (256LL << 20);
+  const bool flat_ok = plain_launch || !table_in_l2;
+  if (A->n_tiles > 0 && A->tiles != nullptr && ((variant == 0 && flat_default && flat_ok) || (variant >= 10 && flat_capable))) {
     GCF_REQUIRE(A->n_empty == 0 || (A->empty_rows != nullptr && A->nz_row_ptr != nullptr && A->nz_rows != nullptr),
                 "gcf_spmm_csr_f32: operator has empty rows but no compact row numbering");
     const bool plain = adam == nullptr && epilogue == GCF_EPILOGUE_NONE && OUT == nullptr;   // Y = A X and nothing else
