@@ -454,6 +454,8 @@ class FeatureShardedLightGCNTrainer:
             raise ValueError("exchange must be 'peer' or 'nccl'")
         self.loss_layout = loss_layout
         self.exchange = exchange if loss_layout == "rows" else "nccl"
+        if self.exchange == "peer" and not peer.available(users.device):
+            self.exchange = "nccl"      # agreed on by all ranks (collective probe); reported by bench.py's `parallelism` string
         self.overlap = bool(overlap) and loss_layout == "rows" and n_layers >= 2
         if not users.is_cuda:
             raise RuntimeError("FeatureShardedLightGCNTrainer: tensors must be on the rank's CUDA device")

@@ -111,6 +111,66 @@ class PeerBarrier:
         self._flags.close()
 
 
+_probe_result = {}
+
+
+def available(device: torch.device, group=None) -> bool:
+    """Collective probe: can every rank of the group map every other rank's memory (CUDA IPC + peer access)?  Every rank
+    exports a small block, tries to open everybody else's and the ranks agree on the outcome (all-reduce of a flag), so that
+    a box without peer access makes ALL ranks choose the NCCL exchange instead of leaving some of them stuck in a collective."""
+    key = (device.index, id(group))
+    if key in _probe_result:
+        return _probe_result[key]
+    import os
+
+    if os.environ.get("GCF_PEER_DISABLE", "") not in ("", "0"):     # operator switch (set it for every rank)
+        _probe_result[key] = False
+        return False
+    lib = _lib.load()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ok, why = True, ""
+    block, payload = None, None
+    try:
+        block = _Block(64)
+        handle = ctypes.create_string_buffer(HANDLE_BYTES)
+        _lib.check(lib.gcf_peer_export(ctypes.c_void_p(block.ptr), handle), "gcf_peer_export")
+        payload = handle.raw
+    except Exception as e:   # noqa: BLE001 -- any failure means "not available"
+        ok, why = False, str(e)
+    handles: List[Optional[bytes]] = [None] * world
+    dist.all_gather_object(handles, payload, group=group)
+    opened = []
+    if ok:
+        for g in range(world):
+            if g == rank:
+                continue
+            if handles[g] is None:
+                ok, why = False, f"rank {g} could not export a block"
+                break
+            out = ctypes.c_void_p()
+            buf = ctypes.create_string_buffer(handles[g], HANDLE_BYTES)
+            if lib.gcf_peer_open(buf, ctypes.byref(out)) != 0:
+                ok, why = False, _lib.last_error()
+                break
+            opened.append(int(out.value))
+    flag = torch.tensor([1.0 if ok else 0.0], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    torch.cuda.synchronize(device)
+    for p in opened:
+        lib.gcf_peer_close(ctypes.c_void_p(p))
+    dist.barrier(group=group)            # nobody frees its block while a peer still has it mapped
+    if block is not None:
+        block.free()
+    result = bool(flag.item() > 0.5)
+    if not result and rank == 0:
+        import sys
+
+        print(f"[recommendation_b200.peer] peer memory is not available on this box ({why or 'another rank failed'}): "
+              "falling back to the NCCL exchange", file=sys.stderr, flush=True)
+    _probe_result[key] = result
+    return result
+
+
 def int64_array(values: Sequence[int]) -> "ctypes.Array":
     arr = (ctypes.c_int64 * max(len(values), 1))()
     for i, v in enumerate(values):

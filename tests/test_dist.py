@@ -251,12 +251,16 @@ def _nccl_feature_worker(rank, world, port, n_users, n_items, users, items, tabl
         from recommendation_b200.dist import FeatureShardedLightGCNTrainer
 
         users_t, items_t = torch.from_numpy(users).to(dev), torch.from_numpy(items).to(dev)
+        if loss_layout == "rows-peer-unavailable":
+            os.environ["GCF_PEER_DISABLE"] = "1"       # what a box without peer access looks like to peer.available()
         tr = FeatureShardedLightGCNTrainer(users_t, items_t, n_users, n_items, d=table0.shape[1], n_layers=k, lr=0.01,
                                            reg_weight=1e-4, init_table=torch.from_numpy(table0),
                                            loss_layout=loss_layout.split("-")[0], overlap=loss_layout.endswith("-overlap"),
                                            exchange="nccl" if loss_layout in ("rows-nccl", "rows-overlap") else "peer")
         if loss_layout == "rows-peer-overlap":
             assert tr.overlap and tr.exchange == "peer"
+        if loss_layout == "rows-peer-unavailable":
+            assert tr.exchange == "nccl"               # every rank fell back to the NCCL exchange
         losses = [float(tr.step(neg_items=torch.from_numpy(negs[s]).to(dev)).item()) for s in range(negs.shape[0])]
         table = tr.gathered_table().cpu().numpy()
         if rank == 0:
@@ -266,7 +270,7 @@ def _nccl_feature_worker(rank, world, port, n_users, n_items, users, items, tabl
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("loss_layout", ["rows", "rows-peer-overlap", "rows-nccl", "rows-overlap", "scores"])
+@pytest.mark.parametrize("loss_layout", ["rows", "rows-peer-overlap", "rows-peer-unavailable", "rows-nccl", "rows-overlap", "scores"])
 def test_feature_sharded_trainer_matches_single_gpu(loss_layout):
     """"rows" = the default: slices pulled out of the peers' memory over NVLink (csrc/peer.cu); "rows-nccl" / "rows-overlap" =
     the NCCL exchanges with layout passes; "scores" = one all-reduce of partial scores."""
