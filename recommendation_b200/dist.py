@@ -401,6 +401,22 @@ class UserBlockPlan:
         return UserBlockPlan(tuple(cuts), tuple(tcuts))
 
 
+def cyclic_user_shard(sorted_users: torch.Tensor, sorted_items: torch.Tensor, n_users: int, world: int, rank: int):
+    """Users dealt out cyclically over the ranks (user u belongs to rank u % world, where it is row u // world of the rank's
+    user set): pure index arithmetic, any device (CPU-testable).
+
+    sorted_users / sorted_items: the training triples in the global user-major order.  Returns (positions, loc_u, loc_i,
+    rows_per_rank): the positions of this rank's triples in the global list (ascending, so the rank's list is user-major too and
+    its Philox negatives can be drawn by position), their user rows inside the rank's user set, their items, and the number of
+    users of every rank."""
+    mine = (sorted_users % world) == rank
+    positions = torch.nonzero(mine).reshape(-1)
+    loc_u = torch.div(sorted_users[mine], world, rounding_mode="floor").contiguous()
+    loc_i = sorted_items[mine].contiguous()
+    rows_per_rank = [max(0, (n_users - g + world - 1) // world) for g in range(world)]
+    return positions, loc_u, loc_i, rows_per_rank
+
+
 class FeatureShardedLightGCNTrainer:
     """The same full-batch step, parallelised over the embedding dimension.
 
@@ -511,13 +527,9 @@ class FeatureShardedLightGCNTrainer:
                 # exchange of the two directions is lopsided and every rank waits for the slowest one twice).  A peer pull
                 # can read any stride; only NCCL's all-to-all needs contiguous blocks.
                 r = self.rank
-                mine = (pos_u % G) == r
-                self.positions = torch.nonzero(mine).reshape(-1)       # my triples' positions in the global user-major list
-                self.loc_u = torch.div(pos_u[mine], G, rounding_mode="floor").contiguous()   # row inside my user set
-                self.loc_i = pos_i[mine].contiguous()
-                del pos_u, pos_i, mine
+                self.positions, self.loc_u, self.loc_i, self.block_rows = cyclic_user_shard(pos_u, pos_i, n_users, G, r)
+                del pos_u, pos_i
                 self.n_local = int(self.loc_u.numel())
-                self.block_rows = [max(0, (n_users - g + G - 1) // G) for g in range(G)]
                 self.ub = ub = self.block_rows[r]
                 self.user_full = torch.empty(ub, d, device=dev)
                 # what the peers read: my column slice of the final embeddings, my full-width gradient partials

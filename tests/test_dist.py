@@ -396,6 +396,30 @@ def test_rows_layout_loss_exchange_gloo_world2():
     np.testing.assert_allclose(got_grad, xt.grad.numpy(), rtol=1e-9, atol=1e-12)
 
 
+def test_cyclic_user_shard_partitions_the_triples():
+    """dist.cyclic_user_shard (host logic of the peer-memory exchange): every triple belongs to exactly one rank, a rank's list
+    stays user-major, local rows map back to the users, row counts add up -- for worlds that do and do not divide U."""
+    from recommendation_b200.dist import cyclic_user_shard
+
+    rng = np.random.default_rng(3)
+    for n_users, world in ((10, 2), (11, 4), (1000, 8), (5, 8)):
+        u = np.sort(rng.integers(0, n_users, 4000))
+        i = rng.integers(0, 77, 4000)
+        ut, it = torch.from_numpy(u), torch.from_numpy(i)
+        seen = torch.zeros(4000, dtype=torch.int64)
+        rows_total = 0
+        for r in range(world):
+            pos, loc_u, loc_i, rows = cyclic_user_shard(ut, it, n_users, world, r)
+            seen[pos] += 1
+            assert bool((pos[1:] > pos[:-1]).all()) if pos.numel() > 1 else True
+            assert torch.equal(loc_u * world + r, ut[pos]) and torch.equal(loc_i, it[pos])
+            assert bool((loc_u[1:] >= loc_u[:-1]).all()) if loc_u.numel() > 1 else True      # still user-major
+            assert loc_u.numel() == 0 or int(loc_u.max()) < rows[r]
+            assert rows == [len(range(g, n_users, world)) for g in range(world)]
+            rows_total = sum(rows)
+        assert bool((seen == 1).all()) and rows_total == n_users
+
+
 # ---------------------------------------------------------------------------------------------- world-size independence
 def _nccl_default_init_worker(rank, world, port, n_users, n_items, users, items, k, steps, kind, out_q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
