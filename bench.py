@@ -313,7 +313,7 @@ def run_ours(args):
             args.loss_layout = "rows"   # r03: with the peer-memory exchange the rows layout wins at every N (2 GPUs 49.7 vs 54.5 ms)
         if F == world:
             trainer = FeatureShardedLightGCNTrainer(users, items, U, I, d=d, n_layers=K, lr=0.01, reg_weight=1e-4, seed=1234,
-                                                    loss_layout=args.loss_layout, exchange=args.exchange,
+                                                    loss_layout=args.loss_layout, exchange=args.exchange, user_rows=args.user_rows,
                                                     overlap=(args.overlap_exchange == "on" or
                                                              (args.overlap_exchange == "auto" and args.exchange == "peer")))
             nnz, spmm_rows, spmm_d = trainer.local_nnz, n, trainer.dg
@@ -573,6 +573,9 @@ def main():
     ap.add_argument("--exchange", choices=("peer", "nccl"), default=os.environ.get("GCF_BENCH_EXCHANGE", "peer"),
                     help="feature-sharded layout, loss on rows: 'peer' = slices pulled out of the peers' memory over NVLink by "
                          "csrc/peer.cu (default), 'nccl' = all-gather / all-to-all / reduce-scatter + layout passes (r01/r02)")
+    ap.add_argument("--user-rows", choices=("owner", "natural"), default=os.environ.get("GCF_BENCH_USER_ROWS", "owner"),
+                    help="feature-sharded layout, peer exchange: numbering of the user rows inside the trainer's tables "
+                         "(owner = each rank's users contiguous in every slice: contiguous NVLink transfers)")
     ap.add_argument("--overlap-exchange", choices=("auto", "on", "off"), nargs="?", const="on",
                     default=os.environ.get("GCF_BENCH_OVERLAP", "auto"),
                     help="feature-sharded layout, loss on rows: run the item-side exchanges next to row blocks of the adjacent "

@@ -452,11 +452,15 @@ class FeatureShardedLightGCNTrainer:
     def __init__(self, users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int, *, d: int = 64,
                  n_layers: int = 3, lr: float = 0.01, reg_weight: float = 1e-4, seed: int = 0,
                  init_table: Optional[torch.Tensor] = None, loss_layout: str = "rows", overlap: bool = False,
-                 exchange: str = "peer"):
+                 exchange: str = "peer", user_rows: str = "owner"):
         """exchange (loss_layout="rows"): "peer" (default) -- the column slices are read straight out of the peers' memory
         over NVLink by one kernel per direction that also converts the layout (csrc/peer.cu; two device-side barriers over peer
         flag words per step; the only NCCL call left is the all-reduce of the scalar loss); "nccl" -- the r01 path: all-gather / all-to-all / reduce-scatter with a
         layout pass on either side.
+        user_rows (exchange="peer"): "owner" (default) -- inside the trainer the user rows of every [N, d/G] table are stored
+        owner-major (user u, dealt to rank u % G, sits at row (u % G) * ceil(U / G) + u // G; the graph is built on that
+        numbering), so a rank's users are ONE contiguous block of every peer's slice and both user transfers are contiguous on
+        the remote side (the links move 32-byte pieces of wider remote rows at half the rate); "natural" keeps node order.
         overlap (loss_layout="rows", n_layers >= 2): the last forward layer and the first backward layer are launched as
         an item-row block and a user-row block of the (bipartite) operator, so that the item all-gather runs while the user
         rows are still being computed and the item reduce-scatter while the item rows of the first backward product are.
@@ -469,21 +473,34 @@ class FeatureShardedLightGCNTrainer:
         if exchange not in ("peer", "nccl"):
             raise ValueError("exchange must be 'peer' or 'nccl'")
         self.loss_layout = loss_layout
+        if not users.is_cuda:
+            raise RuntimeError("FeatureShardedLightGCNTrainer: tensors must be on the rank's CUDA device")
         self.exchange = exchange if loss_layout == "rows" else "nccl"
         if self.exchange == "peer" and not peer.available(users.device):
             self.exchange = "nccl"      # agreed on by all ranks (collective probe); reported by bench.py's `parallelism` string
         self.overlap = bool(overlap) and loss_layout == "rows" and n_layers >= 2
-        if not users.is_cuda:
-            raise RuntimeError("FeatureShardedLightGCNTrainer: tensors must be on the rank's CUDA device")
         self.lib = _lib.load()
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.lo, self.hi = feature_slice(d, self.world, self.rank)
         self.dg = self.hi - self.lo
         dev = users.device
         self.dev, self.d_full = dev, d
-        self.n_users, self.n_items, self.n = n_users, n_items, n_users + n_items
+        if user_rows not in ("owner", "natural"):
+            raise ValueError("user_rows must be 'owner' or 'natural'")
+        self.true_users = n_users
+        self.owner_major = user_rows == "owner" and self.exchange == "peer" and self.world > 1
+        users_g, u_rows = users, n_users
+        if self.owner_major:
+            G = self.world
+            self.ubm = -(-n_users // G)                       # rows reserved per owner (the last owners may have one fewer user)
+            u_rows = self.ubm * G                             # user rows of the tables, padding rows included (isolated, all-zero)
+            u64 = users.to(torch.int64)
+            users_g = (u64 % G) * self.ubm + torch.div(u64, G, rounding_mode="floor")
+        # n_users = number of user ROWS in the [N, d/G] tables (what every row offset below needs); true_users = U
+        self.n_users, self.n_items, self.n = u_rows, n_items, u_rows + n_items
         self.k, self.lr, self.reg, self.seed = n_layers, lr, reg_weight, seed
-        self.graph = CSRGraph.from_pairs(users, items, n_users, n_items, norm="sym")  # replicated operator
+        self.graph = CSRGraph.from_pairs(users_g, items, u_rows, n_items, norm="sym")  # replicated operator
+        del users_g
         self.local_nnz = self.graph.nnz
         self.rows_per_rank = self.n
         n, dg = self.n, self.dg
@@ -491,6 +508,12 @@ class FeatureShardedLightGCNTrainer:
             self.table = init_table.to(dev)[:, self.lo:self.hi].contiguous()
         else:
             self.table = xavier_uniform_table(n_users, n_items, d, seed=seed, device=dev, cols=(self.lo, self.hi))
+        if self.owner_major:
+            nat = self.table
+            self.table = torch.zeros(n, dg, device=dev)
+            self.table[self._user_row(torch.arange(n_users, device=dev))] = nat[:n_users]
+            self.table[u_rows:] = nat[n_users:]
+            del nat
         pos_u, pos_i = users.to(torch.int64), items.to(torch.int64)
         self.n_edges = self.n_triples = int(pos_u.numel())
         self.order = torch.argsort(pos_u * n_items + pos_i) if self.n_triples > 1 else None  # user-major (see lightgcn.py)
@@ -546,6 +569,12 @@ class FeatureShardedLightGCNTrainer:
                 self.g_user_full = self._pb_gu.tensor[:ub]
                 self._block_rows64 = peer.int64_array(self.block_rows)
                 self._user_dst_off64 = peer.int64_array([g * dg for g in range(G)])   # user u = g + j G -> row u of [U, dg]
+                if self.owner_major:
+                    # user gradients are PUSHED by their owner into the contiguous block of my slice that holds its users; the
+                    # block starts zeroed and nobody ever writes its padding rows, so they stay zero (and so do their table rows)
+                    self._pb_gfinal = peer.PeerBuffer(n, dg, dev)
+                    self.g_final = self._pb_gfinal.tensor
+                    self._rows_mine64 = peer.int64_array([ub] * G)
             else:
                 self.blocks = UserBlockPlan.build(pos_u, n_users, G)
                 self.block_rows = self.blocks.block_sizes()
@@ -574,18 +603,53 @@ class FeatureShardedLightGCNTrainer:
                 # row blocks of the replicated operator as views of its arrays: user rows gather item columns only and
                 # vice versa (bipartite), so each block depends on ONE side of the exchanged gradient / produces one side
                 gr = self.graph
-                cut = int(gr.row_ptr[n_users].item())
+                cut = int(gr.row_ptr[self.n_users].item())
 
                 def block(r0, r1, e0, e1):
                     rp = (gr.row_ptr[r0:r1 + 1] - e0).contiguous()
                     return CSRGraph(rp, gr.col_idx[e0:e1], gr.vals[e0:e1], r1 - r0, n, chunk=gr.chunk)
-                self.g_users, self.g_items = block(0, n_users, 0, cut), block(n_users, n, cut, gr.nnz)
+                self.g_users, self.g_items = block(0, self.n_users, 0, cut), block(self.n_users, n, cut, gr.nnz)
                 self.ws_u, self.ws_u_bytes = self.g_users.workspace(dg)
                 self.ws_i, self.ws_i_bytes = self.g_items.workspace(dg)
                 self.p_buf = new()                      # A g_final, handed to the rest of the backward chain as extra[K-1]
                 # high priority: the movers' few CTAs must get SM slots while a propagation launch has thousands queued
                 self._side = torch.cuda.Stream(device=dev, priority=-1) if self.exchange == "peer" else None
                 self.launches_per_step += 3             # two block launches instead of one (forward, backward) + the G(K-1) axpby
+
+    def _user_row(self, u: torch.Tensor) -> torch.Tensor:
+        """Table row of user u (owner-major numbering: owner block u % G, row u // G inside it)."""
+        if not self.owner_major:
+            return u
+        return (u % self.world) * self.ubm + torch.div(u, self.world, rounding_mode="floor")
+
+    def _pull_user_rows(self, st) -> None:
+        """user_full[j, g*dg:(g+1)*dg] = final_g[row of my j-th user, :] for every rank g (gcf_peer_gather_cols on stream st)."""
+        if self.ub == 0:
+            return
+        dg, G = self.dg, self.world
+        if self.owner_major:       # my users are rows [rank * ubm, rank * ubm + ub) of every slice: contiguous remote reads
+            src, ld_src = self._pb_final.pointers(self.rank * self.ubm * dg), dg
+        else:                      # rows rank, rank + G, ...: pieces of dg floats at a pitch of G * dg
+            src, ld_src = self._pb_final.pointers(self.rank * dg), G * dg
+        _lib.check(self.lib.gcf_peer_gather_cols(src, G, ld_src, _lib.ptr(self.user_full), self.d_full, self.ub, dg, st),
+                   "gcf_peer_gather_cols")
+
+    def _push_user_grads(self, st) -> None:
+        """owner-major only: g_final_g[rank * ubm + j, :] = g_user_full[j, lo_g:hi_g] for every rank g -- remote stores into ONE
+        contiguous block per peer (call before the barrier that precedes the backward propagation)."""
+        if self.ub == 0:
+            return
+        dg, G = self.dg, self.world
+        src = _lib.ptr_values([self.g_user_full.data_ptr() + 4 * g * dg for g in range(G)])
+        dst = _lib.ptr_values([self._pb_gfinal.base[g] + 4 * self.rank * self.ubm * dg for g in range(G)])
+        _lib.check(self.lib.gcf_peer_copy2d(src, dst, self._rows_mine64, G, self.d_full, dg, dg, 0, st), "gcf_peer_copy2d")
+
+    def _pull_user_grads(self, st) -> None:
+        """natural numbering only: g_final[g + j G, :] = g_user_full_g[j, lo:hi] (call after the barrier that follows the BPR)."""
+        dg, G = self.dg, self.world
+        _lib.check(self.lib.gcf_peer_copy_blocks(self._pb_gu.pointers(self.lo), self._block_rows64, self._user_dst_off64, G,
+                                                 self.d_full, _lib.ptr(self.g_final[:self.n_users]), G * dg, dg, st),
+                   "gcf_peer_copy_blocks")
 
     phase_marks: Optional[list] = None   # tools/phase_dist.py: a list that receives (label, CUDA event) pairs of one step
 
@@ -673,10 +737,7 @@ class FeatureShardedLightGCNTrainer:
         _lib.check(lib.gcf_peer_gather_cols(self._pb_final.pointers(u * dg), G, dg, _lib.ptr(self.item_full), d, self.n_items, dg, st),
                    "gcf_peer_gather_cols")
         self._mark("item slices -> rows (peer gather)")
-        if ub > 0:
-            # my users are rows rank, rank + G, ... of every peer's [N, dg] slice
-            _lib.check(lib.gcf_peer_gather_cols(self._pb_final.pointers(self.rank * dg), G, G * dg, _lib.ptr(self.user_full), d, ub,
-                                                dg, st), "gcf_peer_gather_cols")
+        self._pull_user_rows(st)
         self._mark("user slices -> rows (peer gather)")
         w = 1.0 / max(self.n_triples, 1)
         if self.n_local > 0:
@@ -691,15 +752,18 @@ class FeatureShardedLightGCNTrainer:
         dst = _lib.ptr_values([self._pb_stage.base[g] + 4 * self.rank * self.n_items * dg for g in range(G)])
         _lib.check(lib.gcf_peer_copy2d(src, dst, self._rows_items64, G, d, dg, dg, 0, st), "gcf_peer_copy2d")
         self._mark("item gradients: column pieces -> owners (peer push)")
+        if self.owner_major:
+            self._push_user_grads(st)
+            self._mark("user gradients: column pieces -> owners (peer push)")
         self._barrier()
         self._mark("barrier 2")
         stage = self._pb_stage.tensor
         _lib.check(lib.gcf_peer_sum_cols(_lib.ptr_values([stage.data_ptr() + 4 * g * self.n_items * dg for g in range(G)]), G, dg,
                                          _lib.ptr(self.g_final[u:]), dg, self.n_items, dg, st), "gcf_peer_sum_cols")
         self._mark("item gradients: sum of the G staged slices (local)")
-        _lib.check(lib.gcf_peer_copy_blocks(self._pb_gu.pointers(self.lo), self._block_rows64, self._user_dst_off64, G, d,
-                                            _lib.ptr(self.g_final[:u]), G * dg, dg, st), "gcf_peer_copy_blocks")
-        self._mark("user gradients: rows -> my slice (peer copy)")
+        if not self.owner_major:
+            self._pull_user_grads(st)
+            self._mark("user gradients: rows -> my slice (peer copy)")
         return self.loss_pt * w
 
     def close(self) -> None:
@@ -707,8 +771,9 @@ class FeatureShardedLightGCNTrainer:
         if getattr(self, "_pb_final", None) is not None:
             torch.cuda.synchronize()
             dist.barrier()
-            for pb in (self._pb_final, self._pb_stage, self._pb_gu, self._barrier):
-                pb.close()
+            for pb in (self._pb_final, self._pb_stage, self._pb_gu, self._barrier, getattr(self, "_pb_gfinal", None)):
+                if pb is not None:
+                    pb.close()
             self._pb_final = self._pb_stage = self._pb_gu = None
             self.final = self.g_user_full = None
 
@@ -919,9 +984,7 @@ class FeatureShardedLightGCNTrainer:
         self.g_item_full.zero_()
         self.g_user_full.zero_()
         self.loss_pt.zero_()
-        if ub > 0:
-            _lib.check(lib.gcf_peer_gather_cols(self._pb_final.pointers(self.rank * dg), G, G * dg, _lib.ptr(self.user_full), d, ub,
-                                                dg, st), "gcf_peer_gather_cols")
+        self._pull_user_rows(st)
         main.wait_event(items_gathered)
         self._mark("sampler, barrier, memsets, user gather (+ wait for the item gather)")
         w = 1.0 / max(self.n_triples, 1)
@@ -935,9 +998,11 @@ class FeatureShardedLightGCNTrainer:
         if events is not None:
             events[2].record()
         # ---- backward: P = A g_final block by block, the item gradients travel while the item rows of P are computed ----
-        self._barrier()                                        # every rank's BPR is done: the user partials may be pulled
-        _lib.check(lib.gcf_peer_copy_blocks(self._pb_gu.pointers(self.lo), self._block_rows64, self._user_dst_off64, G, d,
-                                            _lib.ptr(self.g_final[:u]), G * dg, dg, st), "gcf_peer_copy_blocks")
+        if self.owner_major:
+            self._push_user_grads(st)                          # delivered into the owners' slices before the barrier
+        self._barrier()                                        # every rank's BPR is done (and its user gradients delivered)
+        if not self.owner_major:
+            self._pull_user_grads(st)
         users_done = torch.cuda.Event()
         users_done.record(main)
         with torch.cuda.stream(side):
@@ -972,7 +1037,11 @@ class FeatureShardedLightGCNTrainer:
         return loss
 
     def gathered_table(self) -> torch.Tensor:
-        """[N, d] table on every rank (for checks / evaluation)."""
+        """[U + I, d] table in node order on every rank (for checks / evaluation)."""
         parts = [torch.empty_like(self.table) for _ in range(self.world)]
         dist.all_gather(parts, self.table)
-        return torch.cat(parts, dim=1)
+        full = torch.cat(parts, dim=1)
+        if not self.owner_major:
+            return full
+        users = full[self._user_row(torch.arange(self.true_users, device=full.device))]
+        return torch.cat([users, full[self.n_users:]], dim=0)

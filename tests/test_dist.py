@@ -256,7 +256,10 @@ def _nccl_feature_worker(rank, world, port, n_users, n_items, users, items, tabl
         tr = FeatureShardedLightGCNTrainer(users_t, items_t, n_users, n_items, d=table0.shape[1], n_layers=k, lr=0.01,
                                            reg_weight=1e-4, init_table=torch.from_numpy(table0),
                                            loss_layout=loss_layout.split("-")[0], overlap=loss_layout.endswith("-overlap"),
-                                           exchange="nccl" if loss_layout in ("rows-nccl", "rows-overlap") else "peer")
+                                           exchange="nccl" if loss_layout in ("rows-nccl", "rows-overlap") else "peer",
+                                           user_rows="natural" if loss_layout == "rows-natural" else "owner")
+        if loss_layout in ("rows", "rows-pad", "rows-peer-overlap"):
+            assert tr.owner_major and tr.n_users % world == 0 and tr.n_users >= n_users
         if loss_layout == "rows-peer-overlap":
             assert tr.overlap and tr.exchange == "peer"
         if loss_layout == "rows-peer-unavailable":
@@ -270,7 +273,8 @@ def _nccl_feature_worker(rank, world, port, n_users, n_items, users, items, tabl
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("loss_layout", ["rows", "rows-peer-overlap", "rows-peer-unavailable", "rows-nccl", "rows-overlap", "scores"])
+@pytest.mark.parametrize("loss_layout", ["rows", "rows-pad", "rows-natural", "rows-peer-overlap", "rows-peer-unavailable", "rows-nccl",
+                                         "rows-overlap", "scores"])
 def test_feature_sharded_trainer_matches_single_gpu(loss_layout):
     """"rows" = the default: slices pulled out of the peers' memory over NVLink (csrc/peer.cu); "rows-nccl" / "rows-overlap" =
     the NCCL exchanges with layout passes; "scores" = one all-reduce of partial scores."""
@@ -280,7 +284,9 @@ def test_feature_sharded_trainer_matches_single_gpu(loss_layout):
     from recommendation_b200.lightgcn import FusedLightGCNTrainer
 
     inter = synth.power_law_bipartite(3000, 4000, 100000, seed=6)
-    U, I, d, k, steps = 3000, 4000, 64, 3, 3
+    # "rows-pad": three more users than the interactions name (isolated nodes), so U is not a multiple of the world size and
+    # the owner-major user blocks carry padding rows
+    U, I, d, k, steps = (3003 if loss_layout == "rows-pad" else 3000), 4000, 64, 3, 3
     rng = np.random.default_rng(1)
     table0 = (rng.standard_normal((U + I, d)) * 0.05).astype(np.float32)
     negs = rng.integers(0, I, (steps, inter.n_edges))
@@ -303,6 +309,7 @@ def test_feature_sharded_trainer_matches_single_gpu(loss_layout):
         p.join(timeout=120)
         assert p.exitcode == 0
     np.testing.assert_allclose(got_losses, want_losses, rtol=1e-4)
+    assert got_table.shape == (U + I, d)
     _tables_close(got_table, ref.table.cpu().numpy())
 
 

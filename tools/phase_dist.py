@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--loss-layout", default="rows")
     ap.add_argument("--exchange", default="peer")
     ap.add_argument("--overlap", action="store_true")
+    ap.add_argument("--user-rows", default="owner")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--out", default="")
@@ -37,7 +38,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     U, I, E, d, K, users, items = bench.make_workload(args.workload, dev)
     tr = FeatureShardedLightGCNTrainer(users, items, U, I, d=d, n_layers=K, lr=0.01, reg_weight=1e-4, seed=1234,
-                                       loss_layout=args.loss_layout, exchange=args.exchange, overlap=args.overlap)
+                                       loss_layout=args.loss_layout, exchange=args.exchange, overlap=args.overlap, user_rows=args.user_rows)
     for _ in range(args.warmup):
         tr.step()
     dist.barrier(); torch.cuda.synchronize()
@@ -62,7 +63,7 @@ def main():
                "phases_ms": [{"phase": k, "rank0": round(float(vals[i]), 3), "max_over_ranks": round(float(vmax[i]), 3)}
                              for i, k in enumerate(order)],
                "step_ms": {"rank0": round(float(vals[-1]), 3), "max_over_ranks": round(float(vmax[-1]), 3)}}
-        print(f"== {args.workload}, {world} GPUs, loss on {args.loss_layout} (exchange: {tr.exchange}{', overlapped' if tr.overlap else ''}), d/G = {tr.dg}")
+        print(f"== {args.workload}, {world} GPUs, loss on {args.loss_layout} (exchange: {tr.exchange}{', overlapped' if tr.overlap else ''}{', owner-major user rows' if getattr(tr, 'owner_major', False) else ''}), d/G = {tr.dg}")
         for p in rec["phases_ms"]:
             print(f"  {p['phase']:<52s} {p['rank0']:8.3f} ms   (max over ranks {p['max_over_ranks']:8.3f})")
         print(f"  {'step (first to last mark)':<52s} {rec['step_ms']['rank0']:8.3f} ms   (max over ranks {rec['step_ms']['max_over_ranks']:8.3f})")
