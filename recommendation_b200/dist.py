@@ -401,6 +401,13 @@ class UserBlockPlan:
         return UserBlockPlan(tuple(cuts), tuple(tcuts))
 
 
+def owner_major_row(u: torch.Tensor, world: int, rows_per_owner: int) -> torch.Tensor:
+    """Row of user u in the owner-major numbering of the feature-sharded tables: the users of rank g = u % world occupy the
+    contiguous block [g * rows_per_owner, (g + 1) * rows_per_owner), in ascending user order (rows_per_owner = ceil(U / world);
+    blocks of ranks with one user fewer end in a padding row)."""
+    return (u % world) * rows_per_owner + torch.div(u, world, rounding_mode="floor")
+
+
 def cyclic_user_shard(sorted_users: torch.Tensor, sorted_items: torch.Tensor, n_users: int, world: int, rank: int):
     """Users dealt out cyclically over the ranks (user u belongs to rank u % world, where it is row u // world of the rank's
     user set): pure index arithmetic, any device (CPU-testable).
@@ -494,8 +501,7 @@ class FeatureShardedLightGCNTrainer:
             G = self.world
             self.ubm = -(-n_users // G)                       # rows reserved per owner (the last owners may have one fewer user)
             u_rows = self.ubm * G                             # user rows of the tables, padding rows included (isolated, all-zero)
-            u64 = users.to(torch.int64)
-            users_g = (u64 % G) * self.ubm + torch.div(u64, G, rounding_mode="floor")
+            users_g = owner_major_row(users.to(torch.int64), G, self.ubm)
         # n_users = number of user ROWS in the [N, d/G] tables (what every row offset below needs); true_users = U
         self.n_users, self.n_items, self.n = u_rows, n_items, u_rows + n_items
         self.k, self.lr, self.reg, self.seed = n_layers, lr, reg_weight, seed
@@ -618,9 +624,7 @@ class FeatureShardedLightGCNTrainer:
 
     def _user_row(self, u: torch.Tensor) -> torch.Tensor:
         """Table row of user u (owner-major numbering: owner block u % G, row u // G inside it)."""
-        if not self.owner_major:
-            return u
-        return (u % self.world) * self.ubm + torch.div(u, self.world, rounding_mode="floor")
+        return owner_major_row(u, self.world, self.ubm) if self.owner_major else u
 
     def _pull_user_rows(self, st) -> None:
         """user_full[j, g*dg:(g+1)*dg] = final_g[row of my j-th user, :] for every rank g (gcf_peer_gather_cols on stream st)."""

@@ -403,6 +403,27 @@ def test_rows_layout_loss_exchange_gloo_world2():
     np.testing.assert_allclose(got_grad, xt.grad.numpy(), rtol=1e-9, atol=1e-12)
 
 
+def test_owner_major_rows_are_a_blockwise_bijection():
+    """dist.owner_major_row: user u -> row (u % G) * ceil(U / G) + u // G is injective, keeps a rank's users contiguous and in
+    ascending order, and leaves at most one padding row at the end of a block; consistent with cyclic_user_shard's local rows."""
+    from recommendation_b200.dist import cyclic_user_shard, owner_major_row
+
+    for n_users, world in ((10, 2), (11, 4), (3003, 8), (5, 8), (64, 8)):
+        per = -(-n_users // world)
+        u = torch.arange(n_users)
+        rows = owner_major_row(u, world, per)
+        assert rows.unique().numel() == n_users and int(rows.max()) < per * world
+        for g in range(world):
+            mine = rows[u % world == g]
+            n_g = len(range(g, n_users, world))
+            assert mine.tolist() == list(range(g * per, g * per + n_g)) and per - n_g in (0, 1) or n_g == 0
+        # the row inside the owner's block is what cyclic_user_shard hands the loss kernel as the local user row
+        ut = torch.sort(torch.randint(0, n_users, (500,))).values
+        for g in range(world):
+            pos, loc_u, _, _ = cyclic_user_shard(ut, torch.zeros_like(ut), n_users, world, g)
+            assert torch.equal(owner_major_row(ut[pos], world, per), g * per + loc_u)
+
+
 def test_cyclic_user_shard_partitions_the_triples():
     """dist.cyclic_user_shard (host logic of the peer-memory exchange): every triple belongs to exactly one rank, a rank's list
     stays user-major, local rows map back to the users, row counts add up -- for worlds that do and do not divide U."""
