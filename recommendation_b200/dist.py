@@ -600,8 +600,10 @@ class FeatureShardedLightGCNTrainer:
             self.neg = torch.empty(max(self.n_local, 1), dtype=torch.int64, device=dev)
             self.bpr_ws_bytes = self.lib.gcf_bpr_workspace_bytes(self.n_local)
             self.bpr_ws = torch.empty(self.bpr_ws_bytes, dtype=torch.uint8, device=dev)
-            # K fwd + K bwd SpMM (Adam fused into the last), sampler, 2 + 2 layout conversions, fused BPR + its reduction
-            self.launches_per_step = 2 * n_layers + 7
+            # libgcf launches per step.  nccl: K fwd + K bwd SpMM (Adam fused into the last), sampler, 2 + 2 layout conversions,
+            # fused BPR + its reduction.  peer: K + K SpMM, sampler, fused BPR + its reduction, 2 barriers, item gather, user
+            # gather, item push, item sum, user push (or pull)
+            self.launches_per_step = 2 * n_layers + (7 if self.exchange == "nccl" else 10)
             # nccl: item all-gather, user all-to-all, item reduce-scatter, user all-to-all, loss all-reduce; peer: two
             # stream-ordered barriers + the loss all-reduce (2 gathers + 1 sum + 1 copy replace the 4 layout passes)
             self.collectives_per_step = 5 if self.exchange == "nccl" else 3
@@ -620,7 +622,8 @@ class FeatureShardedLightGCNTrainer:
                 self.p_buf = new()                      # A g_final, handed to the rest of the backward chain as extra[K-1]
                 # high priority: the movers' few CTAs must get SM slots while a propagation launch has thousands queued
                 self._side = torch.cuda.Stream(device=dev, priority=-1) if self.exchange == "peer" else None
-                self.launches_per_step += 3             # two block launches instead of one (forward, backward) + the G(K-1) axpby
+                # two block launches instead of one (forward, backward) + the G(K-1) axpby; peer: two more barriers
+                self.launches_per_step += 3 if self.exchange == "nccl" else 5
 
     def _user_row(self, u: torch.Tensor) -> torch.Tensor:
         """Table row of user u (owner-major numbering: owner block u % G, row u // G inside it)."""
