@@ -34,7 +34,8 @@ for n, d in zip(names, dem):
     tensor = any(k in c for k in ("UTCHMMA", "LDTM", "UTMALDG.2D"))
     if not tensor and not any(t in short for t in ("spmm_flat_kernel<16, 1, 8, false, false, 3", "spmm_flat_kernel<16, 1, 8, false, true, 3",
                                                    "spmm_csr_kernel<2, 1, 2, false, 4, 4, false", "spmm_csr_kernel<4, 1, 4, false, 4, 2, false",
-                                                   "bpr_fused_kernel<16, 1, false, 4, 2", "gather_rows_kernel", "scatter_add_agg_kernel")):
+                                                   "bpr_fused_kernel<16, 1, false, 4, 2", "gather_rows_kernel", "scatter_add_agg_kernel",
+                                                   "peer_copy2d_kernel", "peer_sum_kernel", "peer_barrier_kernel")):
         continue
     if short in seen:
         continue
