@@ -714,12 +714,19 @@ class FeatureShardedLightGCNTrainer:
 
             barrier (every rank's slice of `final` is complete; nobody still reads last step's gradient partials)
             item_full[i, g*dg:(g+1)*dg] = final_g[U + i, :]         for all g    (gcf_peer_gather_cols over NVLink)
-            user_full[j, g*dg:(g+1)*dg] = final_g[rank + j G, :]    my users: u % G == rank
-            fused BPR on my E/G triples -> g_item_full [I, d] (local), g_user_full [Ub, d] (peer-visible)
+            user_full[j, g*dg:(g+1)*dg] = final_g[row of my j-th user, :]   my users: u % G == rank; with owner-major user rows
+                                                                     (default) they are ONE contiguous block of every slice
+            fused BPR on my E/G triples -> g_item_full [I, d], g_user_full [Ub, d]
             stage_g[rank][i, :] = g_item_full[i, lo_g:hi_g]          for all g    (gcf_peer_copy2d: remote stores)
+            owner-major: g_final_g[my block + j, :] = g_user_full[j, lo_g:hi_g]   (gcf_peer_copy2d: remote stores)
             barrier (every rank's partials are complete and delivered)
             g_final[U + i, :] = sum_g stage[g][i, :]                 fixed order g = 0..G-1 (gcf_peer_sum_cols, local)
-            g_final[g + j G, :] = g_user_full_g[j, lo:hi]            (gcf_peer_copy_blocks)
+            node-order user rows: g_final[g + j G, :] = g_user_full_g[j, lo:hi]   (gcf_peer_copy_blocks: remote loads)
+
+        Who may touch what when: a rank reads a peer's `final` only between barrier 1 and its own arrival at barrier 2 of the same
+        step, and the peer rewrites `final` only after it has passed barrier 2; staging slices and the user rows of `g_final` are
+        written by peers between barrier 1 and barrier 2 and read by their owner after barrier 2 and before it arrives at the next
+        barrier 1.  Two barriers per step are therefore enough.
         """
         lib, st, dg, d, G, u, ub = self.lib, _lib.current_stream(), self.dg, self.d_full, self.world, self.n_users, self.ub
         if neg_items is None:
