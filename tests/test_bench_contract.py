@@ -34,3 +34,19 @@ def test_product_arm_needs_cuda():
         return
     r = _run("--workload", "tiny", "--steps", "1", "--warmup", "1")
     assert r.returncode != 0 and "no CPU path" in (r.stderr + r.stdout)
+
+
+def test_multi_gpu_flags_are_accepted_and_documented():
+    """The N > 1 knobs the scaling records name (loss layout, exchange, user-row numbering, overlap) parse, carry their
+    measured defaults, and an N > 1 run without torchrun is refused with the launch line instead of silently running N = 1."""
+    r = _run("--help")
+    assert r.returncode == 0
+    for flag in ("--loss-layout", "--exchange", "--user-rows", "--overlap-exchange", "--feature-shards", "--gpus", "--steps", "--warmup",
+                 "--impl", "--workload"):
+        assert flag in r.stdout, flag
+    import torch
+
+    if not torch.cuda.is_available():
+        r = _run("--gpus", "2", "--workload", "tiny", "--steps", "1", "--warmup", "1", "--exchange", "peer", "--user-rows", "owner",
+                 "--overlap-exchange", "auto", "--loss-layout", "rows")
+        assert r.returncode != 0 and ("torch.distributed.run" in (r.stderr + r.stdout) or "no CPU path" in (r.stderr + r.stdout))
